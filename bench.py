@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Benchmark of the tri-plane render hot path (BASELINE.json metric: ray-samples/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mode fp32|bf16]
+
+A "step" is one ImportanceRenderer.forward over one batch of synthetic input of the BASELINE
+config-2 shape: 8 images x 128^2 rays x (48 coarse + 48 importance) samples, 3x32x256^2 planes per
+image, random-init OSGDecoder.  One process per GPU (torchrun for N > 1); every rank renders its own
+batch of 8 images (weak scaling) and the rendered features / depth / weight sums are all-gathered
+over NCCL, as BASELINE.json's north_star describes.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_IMG, RES, PLANE_RES, DC, DF = 8, 128, 256, 48, 48
+BYTES_PER_SAMPLE = 1536            # 3 planes x 4 taps x 32 channels x 4 B  
+METRIC = 'ray-samples/sec'
+WORKLOAD = 'config2: batch 8 x 128^2 rays x (48+48) samples, 3x32x256^2 fp32 planes/image'
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return json.load(open(p)), 'measured'
+    return {'hbm_gbs': 6650.0}, 'fallback'
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith('active')})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic workload
+# ----------------------------------------------------------------------------------------------
+def make_inputs(torch, dev, seed, n_img=N_IMG, res=RES):
+    from oracle import triplane_oracle as O         # only for the camera orbit constants (host-side numpy)
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    planes = torch.randn((n_img, 3, 32, PLANE_RES, PLANE_RES), generator=g, dtype=torch.float32)
+    c2w, K = O.orbit_cameras(n_img)
+    return planes, torch.from_numpy(c2w), torch.from_numpy(K)
+
+
+def make_decoder(torch, pkg, dev, seed):
+    torch.manual_seed(seed)
+    return pkg.OSGDecoder(32, {'decoder_lr_mul': 1, 'decoder_output_dim': 32}).to(dev).requires_grad_(False)
+
+
+OPTS = {'ray_start': 2.25, 'ray_end': 3.3, 'box_warp': 1, 'depth_resolution': DC, 'depth_resolution_importance': DF,
+        'disparity_space_sampling': False, 'clamp_mode': 'softplus'}        # train.py:312-313,328-332
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline (oracle port) -- the only place bench.py executes oracle/
+# ----------------------------------------------------------------------------------------------
+def cpu_baseline(sample_res, repeats=1):
+    """Times the CPU restatement of the reference renderer on a bounded sample of the workload:
+    1 image of the same planes/decoder shape, sample_res^2 rays, 48+48 samples."""
+    from oracle import triplane_oracle as O
+    try:
+        from oracle import c_oracle
+        have_c = c_oracle.available()
+    except Exception:
+        have_c = False
+    scene = O.synthetic_scene(3, 1, sample_res, PLANE_RES, DC, DF)
+    n_samples = sample_res * sample_res * (DC + DF)
+    if have_c:
+        cores = c_oracle.num_threads()
+        c_oracle.render(scene, dict(O.FFHQ_OPTIONS))          # warm-up (page-in, thread pool)
+        t0 = time.perf_counter()
+        for _ in range(repeats):
+            c_oracle.render(scene, dict(O.FFHQ_OPTIONS))
+        dt = (time.perf_counter() - t0) / repeats
+        kind_note = f'C/OpenMP oracle port, {cores} threads'
+    else:
+        cores = 1
+        t0 = time.perf_counter()
+        for _ in range(repeats):
+            O.render(scene['planes'], scene['dec'], scene['origins'], scene['dirs'], dict(O.FFHQ_OPTIONS),
+                     scene['jitter'], scene['u'])
+        dt = (time.perf_counter() - t0) / repeats
+        kind_note = 'numpy oracle port, 1 thread'
+    return {'value': n_samples / dt, 'unit': METRIC, 'cores': cores, 'kind': 'port',
+            'sample': f'1 image x {sample_res}^2 rays x (48+48) samples, 3x32x256^2 planes ({kind_note}); {dt:.2f} s/pass'}, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    try:
+        from oracle import c_oracle
+        fast = c_oracle.available()
+    except Exception:
+        fast = False
+    res = 128 if fast else 32
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(res)
+    times = []
+    for _ in range(args.steps):
+        base, dt = cpu_baseline(res)
+        times.append(dt)
+    dt = float(np.mean(times))
+    value = res * res * (DC + DF) / dt
+    base['value'] = value
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': METRIC, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'sample_per_step': base['sample']},
+            'cpu_baseline': base,
+            'e2e': {'value': value, 'unit': METRIC, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--mode', default='fp32', choices=['fp32', 'bf16'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module('g-nerf_b200')
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the renderer has no CPU path')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    warmup = max(args.warmup, 3)
+
+    planes_h, c2w_h, K_h = make_inputs(torch, dev, seed=100 + rank)
+    decoder = make_decoder(torch, pkg, dev, seed=0)
+    renderer, sampler = pkg.ImportanceRenderer(), pkg.RaySampler()
+    renderer.defer_depth_clamp = world > 1
+    opts = dict(OPTS, decoder_precision=args.mode)
+    planes = planes_h.to(dev)
+    origins, dirs = sampler(c2w_h.to(dev), K_h.to(dev), RES)
+    m = RES * RES
+    samples_per_step = N_IMG * m * (DC + DF)
+    L = pkg._lib.lib()
+    import ctypes
+
+    gathered = None
+    if world > 1:
+        gathered = torch.empty((world, N_IMG, m, 34), device=dev, dtype=torch.float32)
+
+    kernel_events = []
+
+    def step(record=False):
+        """The hot path as a user calls it, inputs resident in HBM."""
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            renderer._timing_events = (e0, e1)
+            kernel_events.append((e0, e1))
+        rgb, depth, wsum = renderer(planes, decoder, origins, dirs, opts)
+        renderer._timing_events = None
+        if world > 1:
+            # the one non-local dependency: the global depth min/max (VR/ray_marcher.py:50)
+            rng = renderer.last_depth_range
+            lo, hi = rng[0:1].clone(), rng[1:2].clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            rr = torch.cat([lo, hi])
+            pkg._lib.check(L.tpr_clamp_depth(ctypes.c_void_p(depth.data_ptr()), depth.numel(),
+                                             ctypes.c_void_p(rr.data_ptr()),
+                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'tpr_clamp_depth')
+            mine = gathered[rank]
+            mine[..., :32].copy_(rgb); mine[..., 32:33].copy_(depth); mine[..., 33:34].copy_(wsum)
+            dist.all_gather_into_tensor(gathered.view(-1), mine.reshape(-1))
+        return rgb, depth, wsum
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    sampler_clk = ClockSampler(local)
+    if rank == 0:
+        sampler_clk.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step(record=True)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    clocks = sampler_clk.stop() if rank == 0 else None
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
+
+    # ---- end to end: pinned host inputs -> device -> forward -> host, every step
+    planes_pin, o_pin, d_pin = planes_h.pin_memory(), origins.cpu().pin_memory(), dirs.cpu().pin_memory()
+    out_pin = [torch.empty((N_IMG, m, c), dtype=torch.float32).pin_memory() for c in (32, 1, 1)]
+    h2d = planes_pin.numel() * 4 + o_pin.numel() * 4 + d_pin.numel() * 4
+    d2h = sum(t.numel() * 4 for t in out_pin)
+
+    def e2e_step():
+        p = planes_pin.to(dev, non_blocking=True)
+        o = o_pin.to(dev, non_blocking=True)
+        d = d_pin.to(dev, non_blocking=True)
+        outs = renderer(p, decoder, o, d, opts)
+        if world > 1:
+            pkg._lib.check(L.tpr_clamp_depth(ctypes.c_void_p(outs[1].data_ptr()), outs[1].numel(),
+                                             ctypes.c_void_p(renderer.last_depth_range.data_ptr()),
+                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'tpr_clamp_depth')
+        for dst, src in zip(out_pin, outs):
+            dst.copy_(src, non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    e2e_ms = f0.elapsed_time(f1) / e2e_steps
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms, kern_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms, kern_ms = t.tolist()
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        value = world * samples_per_step / (ms * 1e-3)
+        achieved = samples_per_step * BYTES_PER_SAMPLE / (kern_ms * 1e-3) / 1e9
+        line = {
+            'metric': METRIC, 'value': value, 'unit': METRIC, 'n_gpus': world, 'steps': args.steps, 'warmup': warmup,
+            'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32' if args.mode == 'fp32' else 'bf16-mlp', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'per_gpu_batch': N_IMG, 'rays_per_image': m, 'samples_per_ray': DC + DF,
+                       'decoder_precision': args.mode, 'parallelism': f'image-batch sharding x{world}, all-gather of outputs'
+                       if world > 1 else 'single GPU',
+                       'l2': 'inputs larger than L2: 201 MB planes + 201 MB repack + 50 MB noise per step (126 MB L2)',
+                       'step': 'ImportanceRenderer.forward incl. plane repack, decoder pack, both torch.rand draws'},
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                         'frac': achieved / pk['hbm_gbs'], 'traffic': None, 'peak_kind': pk_kind,
+                         'kernel': 'render_kernel (tpr_render: +2 helper launches of ~2 us)', 'kernel_ms': kern_ms,
+                         'algorithmic_bytes_per_launch': samples_per_step * BYTES_PER_SAMPLE},
+            'e2e': {'value': world * samples_per_step / (e2e_ms * 1e-3), 'unit': METRIC, 'ms_per_step': e2e_ms,
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+            'gpu_launches': 5 * args.steps,
+            'clocks': clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'], _ = cpu_baseline(48)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

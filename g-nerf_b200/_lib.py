@@ -1,0 +1,73 @@
+"""ctypes binding of libtriplane_b200.so (include/triplane_b200.h).
+
+The library is prebuilt for sm_100a by ``build.py``; there is no fallback of any kind: if the
+shared object is missing or fails to load, importing this module's ``lib()`` raises.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
+
+from .build import LIB_PATH
+
+ABI_VERSION = 1
+MLP_FP32, MLP_BF16 = 0, 1
+
+
+class TprOptions(ctypes.Structure):
+    _fields_ = [('ray_start', c_float), ('ray_end', c_float), ('box_warp', c_float),
+                ('depth_resolution', c_int32), ('depth_resolution_importance', c_int32),
+                ('disparity_space_sampling', c_int32), ('white_back', c_int32),
+                ('flags', c_int32), ('tile_width', c_int32), ('reserved', c_int32 * 3)]
+
+
+_P = c_void_p
+_SIGNATURES = {
+    'tpr_abi_version': (ctypes.c_int, []),
+    'tpr_last_error': (c_char_p, []),
+    'tpr_packed_planes_bytes': (c_size_t, [c_int64, c_int32, c_int32]),
+    'tpr_pack_planes': (ctypes.c_int, [_P, c_int64, c_int32, c_int32, _P, _P]),
+    'tpr_packed_decoder_bytes': (c_size_t, []),
+    'tpr_pack_decoder': (ctypes.c_int, [_P, _P, _P, _P, c_float, c_float, c_float, c_float, _P, _P]),
+    'tpr_ray_sample': (ctypes.c_int, [_P, _P, c_int64, c_int32, _P, _P, _P]),
+    'tpr_run_model': (ctypes.c_int, [_P, c_int64, c_int32, c_int32, _P, _P, c_int64, c_float, _P, _P, c_int32, _P]),
+    'tpr_decode': (ctypes.c_int, [_P, c_int64, c_int64, _P, _P, _P, c_int32, _P]),
+    'tpr_render_scratch_bytes': (c_size_t, [c_int64, c_int64, ctypes.POINTER(TprOptions)]),
+    'tpr_render': (ctypes.c_int, [_P, c_int64, c_int32, c_int32, _P, _P, _P, c_int64, _P, _P, _P, _P,
+                                  ctypes.POINTER(TprOptions), _P, _P, _P, _P, _P, _P, c_int32, _P, c_size_t, _P]),
+    'tpr_clamp_depth': (ctypes.c_int, [_P, c_int64, _P, _P]),
+    'tpr_ray_march': (ctypes.c_int, [_P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, _P, c_int32, _P]),
+    'tpr_sample_importance': (ctypes.c_int, [_P, _P, _P, c_int64, c_int32, c_int32, _P, _P, _P]),
+    'tpr_sample_pdf': (ctypes.c_int, [_P, c_int32, _P, _P, c_int64, c_int32, c_int32, _P, _P, _P]),
+    'tpr_ray_limits_box': (ctypes.c_int, [_P, _P, c_int64, c_float, _P, _P, _P]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the shared library; raise loudly if it is not there."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} is missing: the sm_100a CUDA library has not been built. Run '
+                f'`python -c "import __graft_entry__ as g; g.build()"` (needs nvcc). There is no CPU or '
+                f'PyTorch fallback for the tri-plane renderer.')
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)           # AttributeError if a declared symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        got = handle.tpr_abi_version()
+        if got != ABI_VERSION:
+            raise RuntimeError(f'libtriplane_b200 ABI version {got}, binding expects {ABI_VERSION}: rebuild')
+        _lib = handle
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    """Turn a non-zero C-ABI return into RuntimeError (the reference's plugins raise RuntimeError
+    through TORCH_CHECK, torch_utils/ops/bias_act.cpp:39-55)."""
+    if code != 0:
+        msg = lib().tpr_last_error()
+        raise RuntimeError(f'{what} failed (code {code}): {msg.decode() if msg else "?"}')

@@ -1,0 +1,870 @@
+// libtriplane_b200.so -- kernels + C ABI (include/triplane_b200.h).
+//
+// Reference citations are relative to /root/reference/g_nerf/ (VR/ = training/volumetric_rendering/).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <mutex>
+#include <string>
+
+#include "triplane_b200.h"
+#include "tpr_device.cuh"
+
+namespace tpr {
+
+// =======================================================================================
+// layout preparation
+// =======================================================================================
+// [P][32][HW] -> [P][HW][32]; one CTA transposes a 32-channel x 32-pixel tile through smem.
+__global__ void __launch_bounds__(256) pack_planes_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                          int hw, int tiles_per_plane) {
+  __shared__ float tile[32][33];
+  const int plane = blockIdx.x / tiles_per_plane;
+  const int p0 = (blockIdx.x - plane * tiles_per_plane) * 32;
+  const float* s = src + (size_t)plane * kC * hw;
+  float* d = dst + (size_t)plane * kC * hw;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 rows of 32
+#pragma unroll
+  for (int c = ty; c < 32; c += 8) {
+    int p = p0 + tx;
+    tile[c][tx] = p < hw ? s[(size_t)c * hw + p] : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int pp = ty; pp < 32; pp += 8) {
+    int p = p0 + pp;
+    if (p < hw) d[(size_t)p * kC + tx] = tile[tx][pp];
+  }
+}
+
+__global__ void pack_decoder_kernel(const float* __restrict__ w1, const float* __restrict__ b1,
+                                    const float* __restrict__ w2, const float* __restrict__ b2,
+                                    float g_w1, float g_b1, float g_w2, float g_b2, float* __restrict__ out) {
+  for (int i = threadIdx.x + blockIdx.x * blockDim.x; i < kDecFloats; i += blockDim.x * gridDim.x) {
+    float v;
+    if (i < kB1Off) {                       // W1t[k][j] = W1[j][k] * gain / 3
+      int k = i / kHid, j = i - k * kHid;
+      v = __fmul_rn(w1[j * kC + k], g_w1) * (1.0f / 3.0f);
+    } else if (i < kW2tOff) {
+      v = b1[i - kB1Off] * g_b1;
+    } else if (i < kB2Off) {                // W2t[j][o] = W2[o][j] * gain
+      int r = i - kW2tOff;
+      int j = r / kOutPad, o = r - j * kOutPad;
+      v = o < TPR_OUT ? w2[o * kHid + j] * g_w2 : 0.0f;
+    } else {
+      int o = i - kB2Off;
+      v = o < TPR_OUT ? b2[o] * g_b2 : 0.0f;
+    }
+    out[i] = v;
+  }
+}
+
+// =======================================================================================
+// a1: RaySampler.forward (VR/ray_sampler.py:36-61), one thread per ray
+// =======================================================================================
+__global__ void ray_sample_kernel(const float* __restrict__ c2w, const float* __restrict__ K, int res, long long total,
+                                  float* __restrict__ origins, float* __restrict__ dirs) {
+  const long long m_per = (long long)res * res;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(g / m_per);
+    const int m = (int)(g - n * m_per);
+    const int py = m / res, pxi = m - py * res;       // x fastest (:44)
+    const float* A = c2w + n * 16;
+    const float* k = K + n * 9;
+    const float fx = k[0], sk = k[1], cx = k[2], fy = k[4], cy = k[5];
+    const float inv = 1.0f / (float)res, half = 0.5f / (float)res;
+    const float xc = __fadd_rn(__fmul_rn((float)pxi, inv), half);
+    const float yc = __fadd_rn(__fmul_rn((float)py, inv), half);
+    // (x - cx + cy*sk/fy - sk*y/fy) / fx   and   (y - cy) / fy    (:51-52)
+    float xl = __fsub_rn(__fadd_rn(__fsub_rn(xc, cx), __fdiv_rn(__fmul_rn(cy, sk), fy)), __fdiv_rn(__fmul_rn(sk, yc), fy));
+    xl = __fdiv_rn(xl, fx);
+    const float yl = __fdiv_rn(__fsub_rn(yc, cy), fy);
+    float d[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float acc = __fmul_rn(A[i * 4 + 0], xl);
+      acc = __fadd_rn(acc, __fmul_rn(A[i * 4 + 1], yl));
+      acc = __fadd_rn(acc, A[i * 4 + 2]);
+      acc = __fadd_rn(acc, A[i * 4 + 3]);
+      d[i] = __fsub_rn(acc, A[i * 4 + 3]);            // minus camera position (:58)
+    }
+    float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+    nrm = fmaxf(nrm, 1e-12f);                          // F.normalize eps (:59)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      dirs[g * 3 + i] = __fdiv_rn(d[i], nrm);
+      origins[g * 3 + i] = A[i * 4 + 3];
+    }
+  }
+}
+
+// =======================================================================================
+// a14: get_ray_limits_box (VR/math_utils.py:46-98), one thread per ray
+// =======================================================================================
+__global__ void ray_limits_box_kernel(const float* __restrict__ o, const float* __restrict__ d, long long n, float side,
+                                      float* __restrict__ tmin_out, float* __restrict__ tmax_out) {
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n; g += (long long)gridDim.x * blockDim.x) {
+    const float lo = -0.5f * side, hi = 0.5f * side;
+    float inv[3], org[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { org[i] = o[g * 3 + i]; inv[i] = __fdiv_rn(1.0f, d[g * 3 + i]); }
+    bool valid = true;
+    // slab test in the reference's order: x, then y, then z
+    float tmin = __fmul_rn(__fsub_rn(inv[0] < 0 ? hi : lo, org[0]), inv[0]);
+    float tmax = __fmul_rn(__fsub_rn(inv[0] < 0 ? lo : hi, org[0]), inv[0]);
+    float tymin = __fmul_rn(__fsub_rn(inv[1] < 0 ? hi : lo, org[1]), inv[1]);
+    float tymax = __fmul_rn(__fsub_rn(inv[1] < 0 ? lo : hi, org[1]), inv[1]);
+    if (tmin > tymax || tymin > tmax) valid = false;
+    tmin = fmaxf(tmin, tymin); tmax = fminf(tmax, tymax);
+    float tzmin = __fmul_rn(__fsub_rn(inv[2] < 0 ? hi : lo, org[2]), inv[2]);
+    float tzmax = __fmul_rn(__fsub_rn(inv[2] < 0 ? lo : hi, org[2]), inv[2]);
+    if (tmin > tzmax || tzmin > tmax) valid = false;
+    tmin = fmaxf(tmin, tzmin); tmax = fminf(tmax, tzmax);
+    tmin_out[g] = valid ? tmin : -1.0f;
+    tmax_out[g] = valid ? tmax : -2.0f;
+  }
+}
+
+// =======================================================================================
+// a8 / a5: run_model and the stand-alone decoder.  Each warp owns a private 32-row tile.
+// =======================================================================================
+constexpr int kRmThreads = 256;
+constexpr int kRmWarps = kRmThreads / 32;
+
+template <bool kFromFeatures>
+__global__ void __launch_bounds__(kRmThreads) run_model_kernel(
+    const float* __restrict__ planes, int H, int W, const float* __restrict__ dec,
+    const float* __restrict__ in /* xyz [N,P,3] or features [N,3,P,32] */, long long n_img, long long n_pts,
+    float box_scale, float* __restrict__ rgb, float* __restrict__ sigma) {
+  extern __shared__ __align__(16) float smem[];
+  float* wsm = smem;
+  float* rows = smem + kDecFloats + (threadIdx.x >> 5) * 32 * kC;
+  stage_decoder(dec, wsm);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long chunks_per_img = (n_pts + 31) >> 5;       // a chunk never straddles two images
+  const long long n_chunks = n_img * chunks_per_img;
+  const size_t img_stride = (size_t)3 * H * W * kC;
+  for (long long chunk = blockIdx.x * (long long)kRmWarps + (threadIdx.x >> 5); chunk < n_chunks;
+       chunk += (long long)gridDim.x * kRmWarps) {
+    const long long n = chunk / chunks_per_img;
+    const long long p0 = (chunk - n * chunks_per_img) * 32;
+    const int nvalid = (int)min(32LL, n_pts - p0);
+    const bool valid = lane < nvalid;
+    const long long g = n * n_pts + p0 + lane;
+    if (!kFromFeatures) {
+      float px = 0.f, py = 0.f, pz = 0.f;
+      if (valid) {
+        px = __fmul_rn(in[g * 3 + 0], box_scale);       // (2/box_warp) * coordinates (VR/renderer.py:61)
+        py = __fmul_rn(in[g * 3 + 1], box_scale);
+        pz = __fmul_rn(in[g * 3 + 2], box_scale);
+      }
+      gather_chunk(planes + n * img_stride, H, W, px, py, pz, lane, valid, rows, lane);
+    } else {
+      // features [N,3,P,32]: sum the three planes' rows, eight lanes per sample
+      const int grp = lane >> 3, sub = lane & 7;
+#pragma unroll 2
+      for (int q = 0; q < 8; ++q) {
+        const int r = q * 4 + grp;
+        if (r < nvalid) {
+          const float* f0 = in + (n * 3 * n_pts + p0 + r) * kC + sub * 4;
+          float4 a = ldg128(f0), b = ldg128(f0 + n_pts * kC), c = ldg128(f0 + 2 * n_pts * kC);
+          *reinterpret_cast<float4*>(rows + row_chunk_off(r, sub)) =
+              make_float4(a.x + b.x + c.x, a.y + b.y + c.y, a.z + b.z + c.z, a.w + b.w + c.w);
+        }
+      }
+    }
+    __syncwarp();
+    float sg = 0.f;
+    if (valid) sg = decode_row_inplace(wsm, rows, lane);
+    __syncwarp();
+    if (valid) sigma[g] = sg;
+    if (rgb != nullptr) {
+      // the 32 rows of this chunk are contiguous in rgb[N,P,32]: store them fully coalesced
+      float4* dst = reinterpret_cast<float4*>(rgb + (n * n_pts + p0) * kC);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int f = it * 32 + lane, r = f >> 3, c = f & 7;
+        if (r < nvalid) dst[f] = *reinterpret_cast<const float4*>(rows + row_chunk_off(r, c));
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// =======================================================================================
+// a13: the fused ImportanceRenderer.forward.  One persistent CTA per SM slot walks tiles of R
+// rays.  Per tile:   A  coarse depths -> gather -> decoder          (warp per 32 samples)
+//                    B  coarse march -> smoothed pdf -> CDF -> fine depths   (warp per ray)
+//                    C  gather -> decoder for the fine samples      (warp per 32 samples)
+//                    D  sort 2D samples, final march, colour sum    (warp per ray)
+// Per-sample features and colours live only in shared memory (one 128-byte row per sample).
+// =======================================================================================
+struct RenderArgs {
+  const float* planes; int H, W;
+  const float* dec;
+  const float* origins; const float* dirs;
+  const float* jitter; const float* u;
+  const float* rs; const float* re;      // optional per-ray limits
+  long long n_rays_total, rays_per_img, n_tiles, tiles_per_img;
+  float ray_start, ray_end, box_scale, lin_step, jitter_scale;
+  int Dc, Df, disparity, white_back, R;
+  float* rgb; float* depth; float* wsum; float* fine_depths; int* fine_inds;
+  unsigned* range_enc;                   // [2]: ordered-uint encoded (min, max) of all depths
+};
+
+constexpr int kRenderMaxThreads = 512;
+
+// coarse depth k of a ray (VR/renderer.py:169-192)
+__device__ __forceinline__ float coarse_depth(const RenderArgs& a, int k, float jit, float rs, float re, bool per_ray) {
+  const int D = a.Dc;
+  if (a.disparity) {                      // :174-181
+    const float step = 1.0f / (float)(D - 1);
+    float t = (k < D / 2) ? __fmul_rn(step, (float)k) : __fsub_rn(1.0f, __fmul_rn(step, (float)(D - 1 - k)));
+    t = __fadd_rn(t, __fmul_rn(jit, step));
+    float lo = __fmul_rn(__fdiv_rn(1.0f, a.ray_start), __fsub_rn(1.0f, t));
+    float hi = __fmul_rn(__fdiv_rn(1.0f, a.ray_end), t);
+    return __fdiv_rn(1.0f, __fadd_rn(lo, hi));
+  }
+  if (per_ray) {                          // :183-186 with math_utils.linspace (math_utils.py:101-118)
+    float steps = __fdiv_rn((float)k, (float)(D - 1));
+    float base = __fadd_rn(rs, __fmul_rn(steps, __fsub_rn(re, rs)));
+    float delta = __fdiv_rn(__fsub_rn(re, rs), (float)(D - 1));
+    return __fadd_rn(base, __fmul_rn(jit, delta));
+  }
+  // :188-190 with torch.linspace's two-sided formula
+  float base = (k < D / 2) ? __fadd_rn(a.ray_start, __fmul_rn(a.lin_step, (float)k))
+                           : __fsub_rn(a.ray_end, __fmul_rn(a.lin_step, (float)(D - 1 - k)));
+  return __fadd_rn(base, __fmul_rn(jit, a.jitter_scale));
+}
+
+struct TileSmem {
+  float* wsm;     // packed decoder
+  float* col;     // [R*S][32]  features, then colours
+  float* dep;     // [R*S]
+  float* sig;     // [R*S]
+  float* wa;      // [R*S]  coarse weights        | omega (phase D)
+  float* wb;      // [R*S]  pdf weights           | sorted index (phase D, as int)
+  float* wc;      // [R*S]  cdf
+  float* ray;     // [R][8]: origin xyz, dir xyz, start, end
+};
+
+// gather + decode `n_samp` = nr*Dx samples of the tile; sample s -> ray s/Dx, slot off + s%Dx
+__device__ __forceinline__ void tile_pass(const RenderArgs& a, const TileSmem& sm, const float* __restrict__ img,
+                                          int nr, int Dx, int off, int S) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int n_samp = nr * Dx;
+  for (int c0 = warp * 32; c0 < n_samp; c0 += nwarps * 32) {
+    const int s = c0 + lane;
+    const bool valid = s < n_samp;
+    int row = 0; float px = 0.f, py = 0.f, pz = 0.f;
+    if (valid) {
+      const int r = s / Dx;
+      row = r * S + off + (s - r * Dx);
+      const float d = sm.dep[row];
+      const float* ry = sm.ray + r * 8;
+      // origin + depth * direction (VR/renderer.py:105,123), then * 2/box_warp (:61)
+      px = __fmul_rn(__fadd_rn(ry[0], __fmul_rn(d, ry[3])), a.box_scale);
+      py = __fmul_rn(__fadd_rn(ry[1], __fmul_rn(d, ry[4])), a.box_scale);
+      pz = __fmul_rn(__fadd_rn(ry[2], __fmul_rn(d, ry[5])), a.box_scale);
+    }
+    gather_chunk(img, a.H, a.W, px, py, pz, row, valid, sm.col, lane);
+    __syncwarp();
+    if (valid) sm.sig[row] = decode_row_inplace(sm.wsm, sm.col, row);
+  }
+}
+
+template <int E>
+__device__ __forceinline__ void ray_composite(const RenderArgs& a, const TileSmem& sm, int r, long long g, int S,
+                                              float& mn, float& mx) {
+  const int lane = threadIdx.x & 31;
+  const float* z = sm.dep + r * S;
+  const float* sg = sm.sig + r * S;
+  float* om = sm.wa + r * S;
+  int* oi = reinterpret_cast<int*>(sm.wb + r * S);
+  float key[E]; int idx[E];
+  bool sorted = true;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    int p = lane * E + e;
+    key[e] = p < S ? z[p] : __int_as_float(0x7f800000);
+    idx[e] = p;
+    if (e > 0) sorted &= !(key[e] < key[e - 1]);
+  }
+  {
+    float prev = __shfl_up_sync(kFull, key[E - 1], 1);
+    if (lane > 0) sorted &= !(key[0] < prev);
+  }
+  if (!__all_sync(kFull, sorted)) warp_bitonic_sort<E>(key, idx, lane);
+  // sorted, blocked: position p = lane*E + e
+  float sgm[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) sgm[e] = (lane * E + e) < S ? sg[idx[e]] : 0.0f;
+  const float nk = __shfl_down_sync(kFull, key[0], 1), ns = __shfl_down_sync(kFull, sgm[0], 1);
+  float al[E], dm[E];
+  float prod = 1.0f;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int p = lane * E + e;
+    const float d1 = e + 1 < E ? key[(e + 1) % E] : nk, s1 = e + 1 < E ? sgm[(e + 1) % E] : ns;
+    if (p + 1 < S) {
+      al[e] = interval_alpha(key[e], d1, sgm[e], s1);
+      dm[e] = (key[e] + d1) * 0.5f;
+      prod *= (1.0f - al[e] + 1e-10f);
+    } else { al[e] = 0.0f; dm[e] = 0.0f; }
+  }
+  float T = warp_excl_prod(prod, lane);
+  float wsum = 0.f, dnum = 0.f, w[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    w[e] = al[e] * T;
+    T *= (1.0f - al[e] + 1e-10f);
+    wsum += w[e];
+    dnum = fmaf(w[e], dm[e], dnum);
+  }
+  wsum = warp_sum(wsum);
+  dnum = warp_sum(dnum);
+  // rgb = sum_i w_i (c_i + c_{i+1})/2 = sum_p c_p (w_{p-1} + w_p)/2     (VR/ray_marcher.py:27,44)
+  float wprev = __shfl_up_sync(kFull, w[E - 1], 1);
+  if (lane == 0) wprev = 0.0f;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int p = lane * E + e;
+    if (p < S) { om[p] = 0.5f * ((e == 0 ? wprev : w[(e + E - 1) % E]) + w[e]); oi[p] = idx[e]; }
+  }
+  // min / max of this ray's depths for the global clamp (VR/ray_marcher.py:50)
+  float lmn = key[0], lmx = -__int_as_float(0x7f800000);
+#pragma unroll
+  for (int e = 0; e < E; ++e) if (lane * E + e < S) lmx = key[e];
+  lmn = warp_min((lane * E) < S ? lmn : __int_as_float(0x7f800000));
+  lmx = warp_max(lmx);
+  mn = fminf(mn, lmn); mx = fmaxf(mx, lmx);
+  __syncwarp();
+  // colour sum: lane = channel
+  const int rowbase = r * S;
+  float acc0 = 0.f, acc1 = 0.f;
+  int p = 0;
+  for (; p + 1 < S; p += 2) {
+    const int r0 = rowbase + oi[p], r1 = rowbase + oi[p + 1];
+    acc0 = fmaf(om[p], sm.col[r0 * kC + ((((lane >> 2) ^ (r0 & 7)) << 2) | (lane & 3))], acc0);
+    acc1 = fmaf(om[p + 1], sm.col[r1 * kC + ((((lane >> 2) ^ (r1 & 7)) << 2) | (lane & 3))], acc1);
+  }
+  if (p < S) {
+    const int r0 = rowbase + oi[p];
+    acc0 = fmaf(om[p], sm.col[r0 * kC + ((((lane >> 2) ^ (r0 & 7)) << 2) | (lane & 3))], acc0);
+  }
+  float c = acc0 + acc1;
+  if (a.white_back) c = c + 1.0f - wsum;              // VR/ray_marcher.py:52-53
+  a.rgb[g * kC + lane] = c * 2.0f - 1.0f;             // :55
+  if (lane == 0) {
+    a.depth[g] = dnum / wsum;                         // NaN -> inf and the clamp happen in finish_kernel
+    a.wsum[g] = wsum;
+  }
+}
+
+template <int E>   // sort width: 32*E >= Dc + Df
+__global__ void __launch_bounds__(kRenderMaxThreads, 1) render_kernel(const RenderArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int R = a.R, Dc = a.Dc, Df = a.Df, S = Dc + Df;
+  TileSmem sm;
+  sm.wsm = smem;
+  sm.col = sm.wsm + kDecFloats;
+  sm.dep = sm.col + (size_t)R * S * kC;
+  sm.sig = sm.dep + R * S;
+  sm.wa = sm.sig + R * S;
+  sm.wb = sm.wa + R * S;
+  sm.wc = sm.wb + R * S;
+  sm.ray = sm.wc + R * S;
+  __shared__ unsigned range_sm[2];
+  if (threadIdx.x == 0) { range_sm[0] = 0xffffffffu; range_sm[1] = 0u; }
+  stage_decoder(a.dec, sm.wsm);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const bool per_ray = a.rs != nullptr;
+  const size_t img_stride = (size_t)3 * a.H * a.W * kC;
+  float mn = __int_as_float(0x7f800000), mx = -__int_as_float(0x7f800000);
+
+  for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    // a tile is R consecutive rays of ONE image, so the plane block is CTA-uniform
+    const long long n = tile / a.tiles_per_img;
+    const long long m0 = (tile - n * a.tiles_per_img) * R;
+    const long long g0 = n * a.rays_per_img + m0;
+    const int nr = (int)min((long long)R, a.rays_per_img - m0);
+    const float* img = a.planes + (size_t)n * img_stride;
+    __syncthreads();                                   // previous tile fully consumed
+    // ---- rays
+    if (threadIdx.x < nr * 6) {
+      const int r = threadIdx.x / 6, c = threadIdx.x - r * 6;
+      const long long g = g0 + r;
+      sm.ray[r * 8 + c] = c < 3 ? a.origins[g * 3 + c] : a.dirs[g * 3 + c - 3];
+      if (c == 0) {
+        sm.ray[r * 8 + 6] = per_ray ? a.rs[g] : a.ray_start;
+        sm.ray[r * 8 + 7] = per_ray ? a.re[g] : a.ray_end;
+      }
+    }
+    __syncthreads();
+    // ---- coarse depths (the jitter block of a tile is contiguous in HBM)
+    for (int s = threadIdx.x; s < nr * Dc; s += blockDim.x) {
+      const int r = s / Dc, k = s - r * Dc;
+      const float jit = __ldg(a.jitter + g0 * Dc + s);
+      sm.dep[r * S + k] = coarse_depth(a, k, jit, sm.ray[r * 8 + 6], sm.ray[r * 8 + 7], per_ray);
+    }
+    __syncthreads();
+    const int n_pass = Df > 0 ? 2 : 1;
+#pragma unroll 1
+    for (int pass = 0; pass < n_pass; ++pass) {
+      if (pass == 1) {
+        // ---- B: importance resampling, one warp per ray
+        const int nb = Dc - 3;
+        for (int r = warp; r < nr; r += nwarps) {
+          const float* z = sm.dep + r * S;
+          float* w = sm.wa + r * S; float* pw = sm.wb + r * S; float* cdf = sm.wc + r * S;
+          warp_march_weights(z, sm.sig + r * S, w, Dc, lane);
+          __syncwarp();
+          warp_smooth_weights(w, pw, nb, lane);
+          __syncwarp();
+          warp_cdf(pw, cdf, nb, lane);
+          __syncwarp();
+          const long long g = g0 + r;
+          for (int j = lane; j < Df; j += 32) {
+            int inds;
+            float smp = invert_cdf(cdf, nb, __ldg(a.u + g * Df + j),
+                                   [&](int i) { return __fmul_rn(0.5f, __fadd_rn(z[i], z[i + 1])); }, inds);
+            sm.dep[r * S + Dc + j] = smp;
+            if (a.fine_depths) a.fine_depths[g * Df + j] = smp;
+            if (a.fine_inds) a.fine_inds[g * Df + j] = inds;
+          }
+        }
+        __syncthreads();
+      }
+      // ---- A / C: gather + decode the coarse (pass 0) or fine (pass 1) samples
+      tile_pass(a, sm, img, nr, pass == 0 ? Dc : Df, pass == 0 ? 0 : Dc, S);
+      __syncthreads();
+    }
+    // ---- D: merge + final march
+    for (int r = warp; r < nr; r += nwarps) ray_composite<E>(a, sm, r, g0 + r, S, mn, mx);
+  }
+  if (lane == 0 && mn <= mx) {
+    atomicMin(&range_sm[0], float_to_ordered(mn));
+    atomicMax(&range_sm[1], float_to_ordered(mx));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && range_sm[0] <= range_sm[1]) {
+    atomicMin(a.range_enc + 0, range_sm[0]);
+    atomicMax(a.range_enc + 1, range_sm[1]);
+  }
+}
+
+__global__ void range_init_kernel(unsigned* enc) {
+  enc[0] = 0xffffffffu; enc[1] = 0u;
+}
+
+// decode the (min,max) and optionally apply nan_to_num(inf) + clamp (VR/ray_marcher.py:49-50)
+__global__ void finish_kernel(const unsigned* __restrict__ enc, float* __restrict__ range_out,
+                              float* __restrict__ depth, long long n, int do_clamp) {
+  const float lo = ordered_to_float(enc[0]), hi = ordered_to_float(enc[1]);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && range_out) { range_out[0] = lo; range_out[1] = hi; }
+  if (!do_clamp) return;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float d = depth[i];
+    if (d != d) d = __int_as_float(0x7f800000);
+    depth[i] = fminf(fmaxf(d, lo), hi);
+  }
+}
+
+__global__ void clamp_depth_kernel(float* __restrict__ depth, long long n, const float* __restrict__ range) {
+  const float lo = range[0], hi = range[1];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float d = depth[i];
+    if (d != d) d = __int_as_float(0x7f800000);
+    depth[i] = fminf(fmaxf(d, lo), hi);
+  }
+}
+
+// =======================================================================================
+// a9 stand-alone: MipRayMarcher2.forward, one warp per ray, samples in the given order
+// =======================================================================================
+__global__ void __launch_bounds__(256) ray_march_kernel(const float* __restrict__ colors, const float* __restrict__ dens,
+                                                        const float* __restrict__ depths, long long n_rays, int S, int C,
+                                                        int white_back, float* __restrict__ rgb, float* __restrict__ depth,
+                                                        float* __restrict__ weights, unsigned* __restrict__ range_enc) {
+  const int lane = threadIdx.x & 31;
+  float mn = __int_as_float(0x7f800000), mx = -mn;
+  for (long long g = blockIdx.x * 8LL + (threadIdx.x >> 5); g < n_rays; g += gridDim.x * 8LL) {
+    const float* z = depths + g * S;
+    const float* sg = dens + g * S;
+    float* w = weights + g * (S - 1);
+    warp_march_weights(z, sg, w, S, lane);
+    __syncwarp();
+    float wsum = 0.f, dnum = 0.f;
+    for (int i = lane; i < S - 1; i += 32) {
+      wsum += w[i];
+      dnum = fmaf(w[i], (z[i] + z[i + 1]) * 0.5f, dnum);
+    }
+    for (int i = lane; i < S; i += 32) { mn = fminf(mn, z[i]); mx = fmaxf(mx, z[i]); }
+    wsum = warp_sum(wsum); dnum = warp_sum(dnum);
+    const float* col = colors + g * (long long)S * C;
+    for (int c = lane; c < C; c += 32) {
+      float acc = 0.f;
+      for (int i = 0; i < S - 1; ++i) acc = fmaf(w[i], (col[(long long)i * C + c] + col[(long long)(i + 1) * C + c]) * 0.5f, acc);
+      if (white_back) acc = acc + 1.0f - wsum;
+      rgb[g * C + c] = acc * 2.0f - 1.0f;
+    }
+    if (lane == 0) depth[g] = dnum / wsum;
+  }
+  mn = warp_min(mn); mx = warp_max(mx);
+  if (lane == 0 && mn <= mx) {
+    atomicMin(range_enc + 0, float_to_ordered(mn));
+    atomicMax(range_enc + 1, float_to_ordered(mx));
+  }
+}
+
+// =======================================================================================
+// a10/a11 stand-alone, one warp per ray (same device functions as the fused kernel)
+// =======================================================================================
+constexpr int kPdfWarps = 4;
+// mode 0: sample_importance(z_vals [R,S], weights [R,S-1]);  mode 1: sample_pdf(bins, weights [R,nb])
+__global__ void __launch_bounds__(kPdfWarps * 32) resample_kernel(
+    int mode, const float* __restrict__ zin, int z_stride, const float* __restrict__ win, const float* __restrict__ u,
+    long long n_rays, int S_or_nb, int K, float* __restrict__ samples, int* __restrict__ inds_out) {
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cap = (mode == 0 ? S_or_nb : S_or_nb + 2);
+  float* z = smem + warp * 4 * cap;
+  float* w = z + cap; float* pw = w + cap; float* cdf = pw + cap;
+  for (long long g = blockIdx.x * (long long)kPdfWarps + warp; g < n_rays; g += (long long)gridDim.x * kPdfWarps) {
+    int nb;
+    if (mode == 0) {
+      const int S = S_or_nb;
+      nb = S - 3;
+      for (int i = lane; i < S; i += 32) z[i] = zin[g * z_stride + i];
+      for (int i = lane; i < S - 1; i += 32) w[i] = win[g * (S - 1) + i];
+      __syncwarp();
+      warp_smooth_weights(w, pw, nb, lane);
+    } else {
+      nb = S_or_nb;
+      for (int i = lane; i < nb + 1; i += 32) z[i] = zin[g * z_stride + i];
+      for (int i = lane; i < nb; i += 32) pw[i] = win[g * nb + i];
+    }
+    __syncwarp();
+    warp_cdf(pw, cdf, nb, lane);
+    __syncwarp();
+    for (int j = lane; j < K; j += 32) {
+      int inds; float smp;
+      const float uu = u[g * K + j];
+      if (mode == 0) smp = invert_cdf(cdf, nb, uu, [&](int i) { return __fmul_rn(0.5f, __fadd_rn(z[i], z[i + 1])); }, inds);
+      else smp = invert_cdf(cdf, nb, uu, [&](int i) { return z[i]; }, inds);
+      samples[g * K + j] = smp;
+      if (inds_out) inds_out[g * K + j] = inds;
+    }
+    __syncwarp();
+  }
+}
+
+// =======================================================================================
+// host side
+// =======================================================================================
+static thread_local std::string g_err;
+
+static int fail(int code, const char* msg) { g_err = msg; return code; }
+static int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return (int)e > 0 ? (int)e : 999;
+}
+#define TPR_CHECK_LAUNCH(what)                                   \
+  do {                                                           \
+    cudaError_t e__ = cudaGetLastError();                        \
+    if (e__ != cudaSuccess) return cuda_fail(e__, what);         \
+  } while (0)
+
+struct DeviceInfo { int sms = 0; int smem_optin = 0; bool ok = false; };
+static DeviceInfo device_info() {
+  static std::mutex mu;
+  static DeviceInfo cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return DeviceInfo();
+  std::lock_guard<std::mutex> lk(mu);
+  if (!cache[dev].ok) {
+    cudaDeviceGetAttribute(&cache[dev].sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&cache[dev].smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cache[dev].ok = cache[dev].sms > 0;
+  }
+  return cache[dev];
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+static int grid_for(long long work_items, int per_block, int sms, int waves) {
+  long long blocks = (work_items + per_block - 1) / per_block;
+  long long cap = (long long)sms * waves;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+// shared-memory bytes of render_kernel for R rays of S samples
+static size_t render_smem_bytes(int R, int S) {
+  return sizeof(float) * ((size_t)kDecFloats + (size_t)R * S * kC + (size_t)5 * R * S + (size_t)R * 8);
+}
+
+}  // namespace tpr
+
+using namespace tpr;
+
+extern "C" {
+
+int tpr_abi_version(void) { return TPR_ABI_VERSION; }
+const char* tpr_last_error(void) { return g_err.c_str(); }
+
+size_t tpr_packed_planes_bytes(int64_t n_img, int32_t height, int32_t width) {
+  if (n_img < 0 || height <= 0 || width <= 0) return 0;
+  return (size_t)n_img * TPR_PLANES * TPR_CHANNELS * height * width * sizeof(float);
+}
+
+int tpr_pack_planes(const float* planes_nchw, int64_t n_img, int32_t height, int32_t width, float* planes_packed,
+                    void* stream) {
+  if (!planes_nchw || !planes_packed) return fail(TPR_E_NULL, "tpr_pack_planes: NULL pointer");
+  if (n_img <= 0 || height <= 0 || width <= 0 || (int64_t)height * width > (1 << 26))
+    return fail(TPR_E_SHAPE, "tpr_pack_planes: bad shape");
+  const int hw = height * width;
+  const int tiles = (hw + 31) / 32;
+  const long long blocks = (long long)n_img * TPR_PLANES * tiles;
+  if (blocks > 0x7fffffffLL) return fail(TPR_E_SHAPE, "tpr_pack_planes: too many tiles");
+  pack_planes_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(planes_nchw, planes_packed, hw, tiles);
+  TPR_CHECK_LAUNCH("pack_planes_kernel");
+  return 0;
+}
+
+size_t tpr_packed_decoder_bytes(void) { return kDecFloats * sizeof(float); }
+
+int tpr_pack_decoder(const float* w1, const float* b1, const float* w2, const float* b2, float w1_gain, float b1_gain,
+                     float w2_gain, float b2_gain, float* decoder_packed, void* stream) {
+  if (!w1 || !b1 || !w2 || !b2 || !decoder_packed) return fail(TPR_E_NULL, "tpr_pack_decoder: NULL pointer");
+  pack_decoder_kernel<<<5, 256, 0, (cudaStream_t)stream>>>(w1, b1, w2, b2, w1_gain, b1_gain, w2_gain, b2_gain,
+                                                           decoder_packed);
+  TPR_CHECK_LAUNCH("pack_decoder_kernel");
+  return 0;
+}
+
+int tpr_ray_sample(const float* cam2world, const float* intrinsics, int64_t n_img, int32_t resolution, float* origins,
+                   float* dirs, void* stream) {
+  if (!cam2world || !intrinsics || !origins || !dirs) return fail(TPR_E_NULL, "tpr_ray_sample: NULL pointer");
+  if (n_img <= 0 || resolution <= 0 || resolution > 16384) return fail(TPR_E_SHAPE, "tpr_ray_sample: bad shape");
+  DeviceInfo di = device_info();
+  if (!di.ok) return fail(TPR_E_DEVICE, "tpr_ray_sample: no CUDA device");
+  const long long total = (long long)n_img * resolution * resolution;
+  ray_sample_kernel<<<grid_for(total, 256, di.sms, 16), 256, 0, (cudaStream_t)stream>>>(cam2world, intrinsics, resolution,
+                                                                                       total, origins, dirs);
+  TPR_CHECK_LAUNCH("ray_sample_kernel");
+  return 0;
+}
+
+int tpr_ray_limits_box(const float* origins, const float* dirs, int64_t n_rays, float box_side_length, float* t_min,
+                       float* t_max, void* stream) {
+  if (!origins || !dirs || !t_min || !t_max) return fail(TPR_E_NULL, "tpr_ray_limits_box: NULL pointer");
+  if (n_rays <= 0) return fail(TPR_E_SHAPE, "tpr_ray_limits_box: n_rays <= 0");
+  DeviceInfo di = device_info();
+  if (!di.ok) return fail(TPR_E_DEVICE, "tpr_ray_limits_box: no CUDA device");
+  ray_limits_box_kernel<<<grid_for(n_rays, 256, di.sms, 16), 256, 0, (cudaStream_t)stream>>>(origins, dirs, n_rays,
+                                                                                            box_side_length, t_min, t_max);
+  TPR_CHECK_LAUNCH("ray_limits_box_kernel");
+  return 0;
+}
+
+static int launch_run_model(bool from_features, const float* planes, int64_t n_img, int32_t H, int32_t W,
+                            const float* dec, const float* in, int64_t n_pts, float box_warp, float* rgb, float* sigma,
+                            int32_t flags, void* stream) {
+  if (!dec || !in || !sigma) return fail(TPR_E_NULL, "run_model: NULL pointer");
+  if (!from_features && !planes) return fail(TPR_E_NULL, "run_model: NULL planes");
+  if (n_img <= 0 || n_pts <= 0) return fail(TPR_E_SHAPE, "run_model: empty input");
+  if (!from_features && (H <= 0 || W <= 0 || (int64_t)H * W > (1 << 24))) return fail(TPR_E_SHAPE, "run_model: bad plane size");
+  if (!from_features && !(box_warp > 0.0f)) return fail(TPR_E_OPTION, "run_model: box_warp must be > 0");
+  if (flags != TPR_MLP_FP32) return fail(TPR_E_OPTION, "run_model: only TPR_MLP_FP32 is implemented in this build");
+  DeviceInfo di = device_info();
+  if (!di.ok) return fail(TPR_E_DEVICE, "run_model: no CUDA device");
+  const size_t smem = sizeof(float) * (kDecFloats + kRmWarps * 32 * kC);
+  static std::once_flag once[2];
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(once[from_features ? 1 : 0], [&] {
+    attr_err = from_features
+                   ? cudaFuncSetAttribute(run_model_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                   : cudaFuncSetAttribute(run_model_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(run_model_kernel)");
+  const long long total = (long long)n_img * n_pts;
+  const int grid = grid_for(total, kRmThreads, di.sms, env_int("TPR_RM_WAVES", 3));
+  const float box_scale = (float)(2.0 / (double)box_warp);
+  if (from_features)
+    run_model_kernel<true><<<grid, kRmThreads, smem, (cudaStream_t)stream>>>(nullptr, 0, 0, dec, in, n_img, n_pts, 0.f, rgb, sigma);
+  else
+    run_model_kernel<false><<<grid, kRmThreads, smem, (cudaStream_t)stream>>>(planes, H, W, dec, in, n_img, n_pts, box_scale, rgb, sigma);
+  TPR_CHECK_LAUNCH("run_model_kernel");
+  return 0;
+}
+
+int tpr_run_model(const float* planes_packed, int64_t n_img, int32_t height, int32_t width, const float* decoder_packed,
+                  const float* xyz, int64_t n_pts, float box_warp, float* rgb, float* sigma, int32_t flags, void* stream) {
+  return launch_run_model(false, planes_packed, n_img, height, width, decoder_packed, xyz, n_pts, box_warp, rgb, sigma,
+                          flags, stream);
+}
+
+int tpr_decode(const float* features, int64_t n_img, int64_t n_pts, const float* decoder_packed, float* rgb, float* sigma,
+               int32_t flags, void* stream) {
+  if (!rgb) return fail(TPR_E_NULL, "tpr_decode: NULL rgb");
+  return launch_run_model(true, nullptr, n_img, 0, 0, decoder_packed, features, n_pts, 1.0f, rgb, sigma, flags, stream);
+}
+
+size_t tpr_render_scratch_bytes(int64_t, int64_t, const TprOptions*) { return 256; }
+
+// pick rays-per-CTA and threads for render_kernel
+static void render_config(int Dc, int Df, int smem_optin, int& R, int& threads, size_t& smem) {
+  const int S = Dc + Df;
+  const int budget = env_int("TPR_SMEM_BUDGET", 112 * 1024);      // two CTAs per SM
+  R = env_int("TPR_RAYS_PER_CTA", 0);
+  if (R <= 0) {
+    R = 8;
+    while (R > 1 && (int)render_smem_bytes(R, S) > budget) --R;
+  }
+  while (R > 1 && (int)render_smem_bytes(R, S) > smem_optin) --R;
+  smem = render_smem_bytes(R, S);
+  threads = env_int("TPR_THREADS", 0);
+  if (threads <= 0) {
+    const int dmax = Dc > Df ? Dc : Df;
+    int warps = (R * dmax + 31) / 32;
+    if (warps < 4) warps = 4;
+    if (warps > 16) warps = 16;
+    threads = warps * 32;
+  }
+  if (threads > kRenderMaxThreads) threads = kRenderMaxThreads;
+  threads = (threads + 31) / 32 * 32;
+}
+
+int tpr_render(const float* planes_packed, int64_t n_img, int32_t height, int32_t width, const float* decoder_packed,
+               const float* origins, const float* dirs, int64_t n_rays, const float* jitter, const float* u,
+               const float* ray_start_per_ray, const float* ray_end_per_ray, const TprOptions* opt, float* rgb,
+               float* depth, float* weight_sum, float* fine_depths, int32_t* fine_inds, float* depth_range_io,
+               int32_t clamp_depth, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!planes_packed || !decoder_packed || !origins || !dirs || !jitter || !opt || !rgb || !depth || !weight_sum || !scratch)
+    return fail(TPR_E_NULL, "tpr_render: NULL pointer");
+  if ((ray_start_per_ray == nullptr) != (ray_end_per_ray == nullptr))
+    return fail(TPR_E_NULL, "tpr_render: per-ray limits need both start and end");
+  const int Dc = opt->depth_resolution, Df = opt->depth_resolution_importance;
+  if (n_img <= 0 || n_rays <= 0 || height <= 0 || width <= 0 || (int64_t)height * width > (1 << 24))
+    return fail(TPR_E_SHAPE, "tpr_render: bad shape");
+  if (Dc < 2 || Df < 0 || Dc + Df > TPR_MAX_SAMPLES) return fail(TPR_E_SHAPE, "tpr_render: depth resolutions out of range");
+  if (Df > 0 && Dc < 4) return fail(TPR_E_SHAPE, "tpr_render: importance sampling needs depth_resolution >= 4");
+  if (Df > 0 && !u) return fail(TPR_E_NULL, "tpr_render: NULL u with depth_resolution_importance > 0");
+  if (!(opt->box_warp > 0.0f)) return fail(TPR_E_OPTION, "tpr_render: box_warp must be > 0");
+  if (opt->flags != TPR_MLP_FP32) return fail(TPR_E_OPTION, "tpr_render: only TPR_MLP_FP32 is implemented in this build");
+  if (scratch_bytes < tpr_render_scratch_bytes(n_img, n_rays, opt)) return fail(TPR_E_SCRATCH, "tpr_render: scratch too small");
+  DeviceInfo di = device_info();
+  if (!di.ok) return fail(TPR_E_DEVICE, "tpr_render: no CUDA device");
+
+  int R, threads; size_t smem;
+  render_config(Dc, Df, di.smem_optin, R, threads, smem);
+  if ((int)smem > di.smem_optin) return fail(TPR_E_SHAPE, "tpr_render: sample count does not fit shared memory");
+  void (*kern)(const RenderArgs) = (Dc + Df <= 64) ? render_kernel<2> : (Dc + Df <= 128) ? render_kernel<4> : render_kernel<8>;
+  {
+    // cudaFuncSetAttribute is per device and cheap; set it on every call rather than caching per device
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(render_kernel)");
+  }
+  RenderArgs a;
+  memset(&a, 0, sizeof(a));
+  a.planes = planes_packed; a.H = height; a.W = width; a.dec = decoder_packed;
+  a.origins = origins; a.dirs = dirs; a.jitter = jitter; a.u = u;
+  a.rs = ray_start_per_ray; a.re = ray_end_per_ray;
+  a.n_rays_total = (long long)n_img * n_rays; a.rays_per_img = n_rays;
+  a.tiles_per_img = (n_rays + R - 1) / R;
+  a.n_tiles = a.tiles_per_img * n_img;
+  a.ray_start = opt->ray_start; a.ray_end = opt->ray_end;
+  a.box_scale = (float)(2.0 / (double)opt->box_warp);
+  a.lin_step = (opt->ray_end - opt->ray_start) / (float)(Dc - 1);                       // torch.linspace, float32
+  a.jitter_scale = (float)(((double)opt->ray_end - (double)opt->ray_start) / (Dc - 1)); // python float (VR/renderer.py:189)
+  a.Dc = Dc; a.Df = Df; a.disparity = opt->disparity_space_sampling; a.white_back = opt->white_back; a.R = R;
+  a.rgb = rgb; a.depth = depth; a.wsum = weight_sum; a.fine_depths = fine_depths; a.fine_inds = fine_inds;
+  a.range_enc = reinterpret_cast<unsigned*>(scratch);
+
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+  if (occ < 1) occ = 1;
+  long long grid = (long long)di.sms * occ;
+  if (grid > a.n_tiles) grid = a.n_tiles;
+  cudaStream_t st = (cudaStream_t)stream;
+  range_init_kernel<<<1, 1, 0, st>>>(a.range_enc);
+  TPR_CHECK_LAUNCH("range_init_kernel");
+  kern<<<(unsigned)grid, threads, smem, st>>>(a);
+  TPR_CHECK_LAUNCH("render_kernel");
+  finish_kernel<<<grid_for(a.n_rays_total, 256, di.sms, 4), 256, 0, st>>>(a.range_enc, depth_range_io, depth, a.n_rays_total,
+                                                                          clamp_depth);
+  TPR_CHECK_LAUNCH("finish_kernel");
+  return 0;
+}
+
+int tpr_clamp_depth(float* depth, int64_t n, const float* depth_range, void* stream) {
+  if (!depth || !depth_range) return fail(TPR_E_NULL, "tpr_clamp_depth: NULL pointer");
+  if (n <= 0) return fail(TPR_E_SHAPE, "tpr_clamp_depth: n <= 0");
+  DeviceInfo di = device_info();
+  if (!di.ok) return fail(TPR_E_DEVICE, "tpr_clamp_depth: no CUDA device");
+  clamp_depth_kernel<<<grid_for(n, 256, di.sms, 4), 256, 0, (cudaStream_t)stream>>>(depth, n, depth_range);
+  TPR_CHECK_LAUNCH("clamp_depth_kernel");
+  return 0;
+}
+
+int tpr_ray_march(const float* colors, const float* densities, const float* depths, int64_t n_rays, int32_t n_samples,
+                  int32_t n_channels, int32_t white_back, float* rgb, float* depth, float* weights, float* depth_range,
+                  int32_t clamp_depth, void* stream) {
+  if (!colors || !densities || !depths || !rgb || !depth || !weights || !depth_range)
+    return fail(TPR_E_NULL, "tpr_ray_march: NULL pointer");
+  if (n_rays <= 0 || n_samples < 2 || n_channels <= 0) return fail(TPR_E_SHAPE, "tpr_ray_march: bad shape");
+  DeviceInfo di = device_info();
+  if (!di.ok) return fail(TPR_E_DEVICE, "tpr_ray_march: no CUDA device");
+  cudaStream_t st = (cudaStream_t)stream;
+  // depth_range[2..3] hold the encoded (min,max) until finish_kernel decodes them into [0..1]
+  unsigned* enc = reinterpret_cast<unsigned*>(depth_range) + 2;
+  range_init_kernel<<<1, 1, 0, st>>>(enc);
+  TPR_CHECK_LAUNCH("range_init_kernel");
+  ray_march_kernel<<<grid_for(n_rays, 8, di.sms, 8), 256, 0, st>>>(colors, densities, depths, n_rays, n_samples, n_channels,
+                                                                   white_back, rgb, depth, weights, enc);
+  TPR_CHECK_LAUNCH("ray_march_kernel");
+  finish_kernel<<<grid_for(n_rays, 256, di.sms, 4), 256, 0, st>>>(enc, depth_range, depth, n_rays, clamp_depth);
+  TPR_CHECK_LAUNCH("finish_kernel");
+  return 0;
+}
+
+static int launch_resample(int mode, const float* z, int z_stride, const float* w, const float* u, int64_t n_rays, int S_or_nb,
+                           int K, float* samples, int32_t* inds, void* stream) {
+  if (!z || !w || !u || !samples) return fail(TPR_E_NULL, "resample: NULL pointer");
+  if (n_rays <= 0 || K <= 0) return fail(TPR_E_SHAPE, "resample: empty input");
+  if (mode == 0 && (S_or_nb < 4 || S_or_nb > 4096)) return fail(TPR_E_SHAPE, "tpr_sample_importance: need 4 <= n_samples <= 4096");
+  if (mode == 1 && (S_or_nb < 1 || S_or_nb > 4096)) return fail(TPR_E_SHAPE, "tpr_sample_pdf: need 1 <= n_weights <= 4096");
+  DeviceInfo di = device_info();
+  if (!di.ok) return fail(TPR_E_DEVICE, "resample: no CUDA device");
+  const int cap = mode == 0 ? S_or_nb : S_or_nb + 2;
+  const size_t smem = sizeof(float) * 4 * cap * kPdfWarps;
+  if (smem > 48 * 1024) {
+    static std::once_flag once;
+    std::call_once(once, [&] { cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin); });
+  }
+  resample_kernel<<<grid_for(n_rays, kPdfWarps, di.sms, 16), kPdfWarps * 32, smem, (cudaStream_t)stream>>>(
+      mode, z, z_stride, w, u, n_rays, S_or_nb, K, samples, inds);
+  TPR_CHECK_LAUNCH("resample_kernel");
+  return 0;
+}
+
+int tpr_sample_importance(const float* z_vals, const float* weights, const float* u, int64_t n_rays, int32_t n_samples,
+                          int32_t n_importance, float* samples, int32_t* inds, void* stream) {
+  return launch_resample(0, z_vals, n_samples, weights, u, n_rays, n_samples, n_importance, samples, inds, stream);
+}
+
+int tpr_sample_pdf(const float* bins, int32_t bins_stride, const float* weights, const float* u, int64_t n_rays,
+                   int32_t n_weights, int32_t n_importance, float* samples, int32_t* inds, void* stream) {
+  if (bins_stride < n_weights + 1) return fail(TPR_E_SHAPE, "tpr_sample_pdf: bins_stride < n_weights + 1");
+  return launch_resample(1, bins, bins_stride, weights, u, n_rays, n_weights, n_importance, samples, inds, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,266 @@
+"""ImportanceRenderer with the reference's interface, backed by the fused sm_100a kernels.
+
+Mirrors /root/reference/g_nerf/training/volumetric_rendering/renderer.py (VR/renderer.py below):
+same class name, same ``forward(planes, decoder, ray_origins, ray_directions, rendering_options)``
+(:88) returning ``(rgb [N,M,32], depth [N,M,1], weight_sum [N,M,1])`` (:140), same
+``run_model(planes, decoder, sample_coordinates, sample_directions, options)`` (:142-148), same
+``plane_axes`` attribute (:86).  What happens inside is one fused kernel (csrc/triplane_b200.cu)
+instead of ~40 ATen launches; nothing here computes the result with torch ops and there is no
+CPU path -- CPU tensors raise.
+"""
+import ctypes
+
+import torch
+
+from .. import _lib
+from . import math_utils
+from .ray_marcher import MipRayMarcher2
+
+
+def generate_planes():
+    """The three plane axis triples (VR/renderer.py:23-37).  Kept as the public attribute the
+    reference exposes; the kernels hard-code the resulting projection
+    (plane 0 <- (x,y), plane 1 <- (x,z), plane 2 <- (z,x))."""
+    return torch.tensor([[[1, 0, 0], [0, 1, 0], [0, 0, 1]],
+                         [[1, 0, 0], [0, 0, 1], [0, 1, 0]],
+                         [[0, 0, 1], [1, 0, 0], [0, 1, 0]]], dtype=torch.float32)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda_f32(t, name, shape_tail=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f'{name} must be a torch.Tensor')
+    if not t.is_cuda:
+        raise RuntimeError(f'{name} is on {t.device}: the B200 tri-plane renderer has no CPU path '
+                           f'(use the reference renderer for CPU tensors)')
+    if t.dtype != torch.float32:
+        raise RuntimeError(f'{name} must be float32, got {t.dtype}')
+    if shape_tail is not None and tuple(t.shape[-len(shape_tail):]) != tuple(shape_tail):
+        raise RuntimeError(f'{name} has shape {tuple(t.shape)}, expected (..., {", ".join(map(str, shape_tail))})')
+    return t.contiguous()
+
+
+def _forbid_autograd(*tensors):
+    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        raise NotImplementedError(
+            'the B200 tri-plane renderer is forward-only: call it under torch.no_grad() or with '
+            'requires_grad_(False) inputs/decoder (backward is not implemented)')
+
+
+class PackedPlanes:
+    """Tri-planes repacked channels-last ([N,3,H,W,32]: one texel = one 128-byte line)."""
+
+    def __init__(self, data, n_img, height, width):
+        self.data, self.n_img, self.height, self.width = data, n_img, height, width
+
+    @property
+    def device(self):
+        return self.data.device
+
+
+def pack_planes(planes) -> PackedPlanes:
+    """[N,3,32,H,W] (training/triplane.py:74) -> PackedPlanes.  Pass the result to forward/run_model
+    in place of ``planes`` to reuse one packing across frames."""
+    if isinstance(planes, PackedPlanes):
+        return planes
+    planes = _require_cuda_f32(planes, 'planes')
+    if planes.dim() != 5 or planes.shape[1] != 3 or planes.shape[2] != 32:
+        raise RuntimeError(f'planes must be [N,3,32,H,W], got {tuple(planes.shape)}')
+    n, _, _, h, w = planes.shape
+    out = torch.empty((n, 3, h, w, 32), dtype=torch.float32, device=planes.device)
+    with torch.cuda.device(planes.device):
+        _lib.check(_lib.lib().tpr_pack_planes(_ptr(planes), n, h, w, _ptr(out), _stream()), 'tpr_pack_planes')
+    return PackedPlanes(out, n, h, w)
+
+
+def pack_decoder(decoder) -> torch.Tensor:
+    """Read an OSGDecoder-shaped module (training/triplane.py:113-122: net[0] = FC 32->64,
+    net[1] = Softplus, net[2] = FC 64->33) and pack its parameters with the runtime gains
+    (training/networks_stylegan2.py:118-119).  Anything else raises: there is no generic fallback."""
+    net = getattr(decoder, 'net', None)
+    if net is None or len(net) != 3:
+        raise RuntimeError('decoder must be OSGDecoder-shaped: .net = [FullyConnectedLayer, Softplus, FullyConnectedLayer]')
+    fc1, act, fc2 = net[0], net[1], net[2]
+    if not isinstance(act, torch.nn.Softplus) or act.beta != 1 or act.threshold != 20:
+        raise RuntimeError('decoder.net[1] must be torch.nn.Softplus(beta=1, threshold=20)')
+    for fc, shape in ((fc1, (64, 32)), (fc2, (33, 64))):
+        if tuple(fc.weight.shape) != shape or fc.bias is None or getattr(fc, 'activation', 'linear') != 'linear':
+            raise RuntimeError(f'decoder layer must be a linear FullyConnectedLayer with weight {shape} and a bias')
+    _forbid_autograd(fc1.weight, fc1.bias, fc2.weight, fc2.bias)
+    w1 = _require_cuda_f32(fc1.weight.detach(), 'decoder.net[0].weight')
+    b1 = _require_cuda_f32(fc1.bias.detach(), 'decoder.net[0].bias')
+    w2 = _require_cuda_f32(fc2.weight.detach(), 'decoder.net[2].weight')
+    b2 = _require_cuda_f32(fc2.bias.detach(), 'decoder.net[2].bias')
+    L = _lib.lib()
+    out = torch.empty(L.tpr_packed_decoder_bytes() // 4, dtype=torch.float32, device=w1.device)
+    with torch.cuda.device(w1.device):
+        _lib.check(L.tpr_pack_decoder(_ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2),
+                                      float(fc1.weight_gain), float(fc1.bias_gain),
+                                      float(fc2.weight_gain), float(fc2.bias_gain), _ptr(out), _stream()),
+                   'tpr_pack_decoder')
+    return out
+
+
+def _mlp_flag(options):
+    mode = options.get('decoder_precision', 'fp32')
+    if mode == 'fp32':
+        return _lib.MLP_FP32
+    if mode == 'bf16':
+        return _lib.MLP_BF16
+    raise RuntimeError(f"rendering_options['decoder_precision'] must be 'fp32' or 'bf16', got {mode!r}")
+
+
+class ImportanceRenderer(torch.nn.Module):
+    _timing_events = None
+
+    def __init__(self):
+        super().__init__()
+        self.ray_marcher = MipRayMarcher2()
+        self.plane_axes = generate_planes()
+        # set by forward(); lets callers that shard rays over GPUs finish the global depth clamp
+        self.last_depth_range = None
+        self.last_fine = None
+        self.debug_outputs = False
+        self.defer_depth_clamp = False
+
+    # ------------------------------------------------------------------ forward (VR/renderer.py:88-140)
+    def forward(self, planes, decoder, ray_origins, ray_directions, rendering_options, *, noise=None):
+        """``noise=(jitter [N,M,Dc,1], u [N*M,Df])`` overrides the two uniform draws (used by parity
+        tests, which must feed the oracle and the kernels the same numbers); by default they are drawn
+        with the reference's own torch calls in the reference's order (VR/renderer.py:190,237)."""
+        opts = rendering_options
+        ray_origins = _require_cuda_f32(ray_origins, 'ray_origins', (3,))
+        ray_directions = _require_cuda_f32(ray_directions, 'ray_directions', (3,))
+        _forbid_autograd(planes if isinstance(planes, torch.Tensor) else None, ray_origins, ray_directions)
+        if opts.get('clamp_mode', None) != 'softplus':
+            raise AssertionError('MipRayMarcher only supports `clamp_mode`=`softplus`!')      # VR/ray_marcher.py:35
+        if opts.get('density_noise', 0) > 0:
+            raise NotImplementedError('density_noise > 0 (VR/renderer.py:146) is not supported by the fused renderer')
+        pp = pack_planes(planes)
+        n, m, _ = ray_origins.shape
+        if pp.n_img != n or ray_directions.shape != ray_origins.shape:
+            raise RuntimeError(f'batch mismatch: planes N={pp.n_img}, origins {tuple(ray_origins.shape)}, '
+                               f'directions {tuple(ray_directions.shape)}')
+        dev = ray_origins.device
+        dec = pack_decoder(decoder)
+        dc = int(opts['depth_resolution'])
+        df = int(opts['depth_resolution_importance'])
+        L = _lib.lib()
+
+        rs_t = re_t = None
+        if opts['ray_start'] == opts['ray_end'] == 'auto':                                # VR/renderer.py:91-97
+            rs_t, re_t = math_utils.get_ray_limits_box(ray_origins, ray_directions, box_side_length=opts['box_warp'])
+            valid = re_t > rs_t
+            if torch.any(valid).item():
+                lo, hi = rs_t[valid].min(), rs_t[valid].max()
+                rs_t[~valid] = lo
+                re_t[~valid] = hi
+            rs_t, re_t = rs_t.reshape(-1).contiguous(), re_t.reshape(-1).contiguous()
+            ray_start = ray_end = 0.0
+        else:
+            ray_start, ray_end = float(opts['ray_start']), float(opts['ray_end'])
+
+        with torch.cuda.device(dev):
+            if noise is None:
+                # same calls, shapes and order as the reference, so the CUDA generator advances identically
+                jitter = torch.rand((n, m, dc, 1), device=dev, dtype=torch.float32)
+                u = torch.rand(n * m, df, device=dev) if df > 0 else None
+            else:
+                jitter = _require_cuda_f32(noise[0], 'noise[0]').reshape(n, m, dc, 1)
+                u = _require_cuda_f32(noise[1], 'noise[1]').reshape(n * m, df) if df > 0 else None
+            o = _lib.TprOptions(ray_start=ray_start, ray_end=ray_end, box_warp=float(opts['box_warp']),
+                                depth_resolution=dc, depth_resolution_importance=df,
+                                disparity_space_sampling=int(bool(opts.get('disparity_space_sampling', False))),
+                                white_back=int(bool(opts.get('white_back', False))), flags=_mlp_flag(opts),
+                                tile_width=0)
+            rgb = torch.empty((n, m, 32), device=dev, dtype=torch.float32)
+            depth = torch.empty((n, m, 1), device=dev, dtype=torch.float32)
+            wsum = torch.empty((n, m, 1), device=dev, dtype=torch.float32)
+            rng = torch.empty(2, device=dev, dtype=torch.float32)
+            nscratch = L.tpr_render_scratch_bytes(n, m, ctypes.byref(o))
+            scratch = torch.empty(nscratch, device=dev, dtype=torch.uint8)
+            fine_d = fine_i = None
+            if self.debug_outputs and df > 0:
+                fine_d = torch.empty((n * m, df), device=dev, dtype=torch.float32)
+                fine_i = torch.empty((n * m, df), device=dev, dtype=torch.int32)
+            ev = self._timing_events          # bench.py: CUDA events bracketing the render launch on this stream
+            if ev is not None:
+                ev[0].record()
+            _lib.check(L.tpr_render(_ptr(pp.data), n, pp.height, pp.width, _ptr(dec), _ptr(ray_origins),
+                                    _ptr(ray_directions), m, _ptr(jitter), _ptr(u), _ptr(rs_t), _ptr(re_t),
+                                    ctypes.byref(o), _ptr(rgb), _ptr(depth), _ptr(wsum), _ptr(fine_d), _ptr(fine_i),
+                                    _ptr(rng), 0 if self.defer_depth_clamp else 1, _ptr(scratch), nscratch, _stream()),
+                       'tpr_render')
+            if ev is not None:
+                ev[1].record()
+        self.last_depth_range = rng
+        self.last_fine = (fine_d, fine_i)
+        return rgb, depth, wsum
+
+    # ------------------------------------------------------------------ run_model (VR/renderer.py:142-148)
+    def run_model(self, planes, decoder, sample_coordinates, sample_directions, options, *, want_rgb=True):
+        """``sample_directions`` is accepted and ignored, exactly like OSGDecoder ignores it
+        (training/triplane.py:124-136)."""
+        xyz = _require_cuda_f32(sample_coordinates, 'sample_coordinates', (3,))
+        _forbid_autograd(planes if isinstance(planes, torch.Tensor) else None, xyz)
+        if options.get('density_noise', 0) > 0:
+            raise NotImplementedError('density_noise > 0 (VR/renderer.py:146) is not supported by the fused renderer')
+        pp = pack_planes(planes)
+        n, p, _ = xyz.shape
+        if pp.n_img != n:
+            raise RuntimeError(f'batch mismatch: planes N={pp.n_img}, coordinates N={n}')
+        dec = pack_decoder(decoder)
+        dev = xyz.device
+        with torch.cuda.device(dev):
+            rgb = torch.empty((n, p, 32), device=dev, dtype=torch.float32) if want_rgb else None
+            sigma = torch.empty((n, p, 1), device=dev, dtype=torch.float32)
+            _lib.check(_lib.lib().tpr_run_model(_ptr(pp.data), n, pp.height, pp.width, _ptr(dec), _ptr(xyz), p,
+                                                float(options['box_warp']), _ptr(rgb), _ptr(sigma),
+                                                _mlp_flag(options), _stream()), 'tpr_run_model')
+        return {'rgb': rgb, 'sigma': sigma}
+
+    # ------------------------------------------------------------------ the remaining public helpers
+    def sample_stratified(self, ray_origins, ray_start, ray_end, depth_resolution, disparity_space_sampling=False):
+        raise NotImplementedError('sample_stratified is fused into forward() (csrc/triplane_b200.cu: coarse_depth)')
+
+    def sample_importance(self, z_vals, weights, N_importance, *, u=None, return_inds=False):
+        """z_vals [N,M,S,1], weights [N,M,S-1,1] -> [N,M,N_importance,1] (VR/renderer.py:194-212)."""
+        z = _require_cuda_f32(z_vals, 'z_vals')
+        w = _require_cuda_f32(weights, 'weights')
+        n, m, s, _ = z.shape
+        dev = z.device
+        with torch.cuda.device(dev):
+            if u is None:
+                u = torch.rand(n * m, N_importance, device=dev)
+            u = _require_cuda_f32(u, 'u')
+            out = torch.empty((n, m, N_importance, 1), device=dev, dtype=torch.float32)
+            inds = torch.empty((n * m, N_importance), device=dev, dtype=torch.int32)
+            _lib.check(_lib.lib().tpr_sample_importance(_ptr(z), _ptr(w), _ptr(u), n * m, s, N_importance,
+                                                        _ptr(out), _ptr(inds), _stream()), 'tpr_sample_importance')
+        return (out, inds) if return_inds else out
+
+    def sample_pdf(self, bins, weights, N_importance, det=False, eps=1e-5, *, u=None, return_inds=False):
+        """bins [R,B+2], weights [R,B] -> samples [R,N_importance] (VR/renderer.py:214-253)."""
+        if eps != 1e-5:
+            raise NotImplementedError('sample_pdf: only the reference default eps=1e-5 is supported')
+        bins = _require_cuda_f32(bins, 'bins')
+        w = _require_cuda_f32(weights, 'weights')
+        r, nb = w.shape
+        dev = w.device
+        with torch.cuda.device(dev):
+            if u is None:
+                u = (torch.linspace(0, 1, N_importance, device=dev).expand(r, N_importance) if det
+                     else torch.rand(r, N_importance, device=dev))
+            u = _require_cuda_f32(u, 'u')
+            out = torch.empty((r, N_importance), device=dev, dtype=torch.float32)
+            inds = torch.empty((r, N_importance), device=dev, dtype=torch.int32)
+            _lib.check(_lib.lib().tpr_sample_pdf(_ptr(bins), bins.shape[1], _ptr(w), _ptr(u), r, nb, N_importance,
+                                                 _ptr(out), _ptr(inds), _stream()), 'tpr_sample_pdf')
+        return (out, inds) if return_inds else out

@@ -1,0 +1,159 @@
+/*
+ * triplane_b200.h -- C ABI of libtriplane_b200.so, the sm_100a tri-plane volume renderer.
+ *
+ * This is the drop-in boundary for ONE hot path of llrtt/G-NeRF: everything
+ * ImportanceRenderer.forward does between receiving (planes, decoder, rays, options)
+ * and returning (rgb, depth, weight_sum).  Citations are relative to
+ * /root/reference/g_nerf/ ; VR/ = training/volumetric_rendering/.
+ *
+ * Conventions (mirroring the reference's plugin convention, torch_utils/ops/bias_act.cpp:39-92,
+ * behind a C ABI instead of torch::Tensor):
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless the name ends in _host;
+ *     all tensors are dense, contiguous, float32 (int32/int64 where stated);
+ *   - the caller owns all memory (inputs, outputs, scratch); the library never allocates, frees
+ *     or keeps a device pointer after the call returns;
+ *   - every entry point is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     synchronises the device, and is re-entrant across host threads and streams;
+ *   - return value: 0 = success, < 0 = argument error (TPR_E_*), > 0 = a cudaError_t from the
+ *     launch; tpr_last_error() returns a thread-local message for the last non-zero return.
+ *   - forward only: there is no backward pass.
+ */
+#ifndef TRIPLANE_B200_H_
+#define TRIPLANE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPR_ABI_VERSION 1
+
+/* fixed by the reference model: OSGDecoder(32 -> 64 -> 1+32), three planes
+ * (training/triplane.py:42,113-122; VR/renderer.py:29-37) */
+#define TPR_CHANNELS 32
+#define TPR_HIDDEN 64
+#define TPR_OUT 33
+#define TPR_PLANES 3
+#define TPR_MAX_SAMPLES 256 /* depth_resolution + depth_resolution_importance */
+
+enum {
+  TPR_E_NULL = -1,      /* a required pointer is NULL */
+  TPR_E_SHAPE = -2,     /* a size is out of the supported range */
+  TPR_E_OPTION = -3,    /* an option value the reference would also reject (e.g. clamp_mode) */
+  TPR_E_SCRATCH = -4,   /* scratch buffer too small */
+  TPR_E_DEVICE = -5     /* not an sm_100 device / kernel image missing */
+};
+
+/* flags */
+enum {
+  TPR_MLP_FP32 = 0,     /* decoder in fp32 FFMA: the 1e-4 max-abs parity mode */
+  TPR_MLP_BF16 = 1      /* decoder on tensor cores with bf16 operands: the >= 50 dB PSNR mode */
+};
+
+/* The subset of `rendering_options` the hot path reads (option table;
+ * VR/renderer.py:91-100,116,143-146; VR/ray_marcher.py:32,52). */
+typedef struct TprOptions {
+  float ray_start;               /* scalar limits (VR/renderer.py:100); ignored if per-ray limits given */
+  float ray_end;
+  float box_warp;                /* VR/renderer.py:61 */
+  int32_t depth_resolution;      /* Dc >= 2 */
+  int32_t depth_resolution_importance; /* Df >= 0; 0 = coarse pass only (VR/renderer.py:116,136-137) */
+  int32_t disparity_space_sampling;    /* VR/renderer.py:174-181 */
+  int32_t white_back;            /* VR/ray_marcher.py:52-53 */
+  int32_t flags;                 /* TPR_MLP_* */
+  int32_t tile_width;            /* perf hint only: rays form an image this many pixels wide (0 = unknown) */
+  int32_t reserved[3];
+} TprOptions;
+
+int tpr_abi_version(void);
+const char* tpr_last_error(void);
+
+/* ---- layout preparation --------------------------------------------------------------- */
+
+/* Planes arrive as [N,3,32,H,W] (training/triplane.py:74).  The renderer wants channels-last
+ * [N,3,H,W,32] so that one texel is one 128-byte line.  tpr_pack_planes does that transpose. */
+size_t tpr_packed_planes_bytes(int64_t n_img, int32_t height, int32_t width);
+int tpr_pack_planes(const float* planes_nchw, int64_t n_img, int32_t height, int32_t width,
+                    float* planes_packed, void* stream);
+
+/* Decoder parameters as stored by OSGDecoder.net[0]/net[2] (training/triplane.py:118-122) plus
+ * the runtime gains FullyConnectedLayer applies on every call (training/networks_stylegan2.py:
+ * 118-119,122-127).  Packs them (gains and the 1/3 plane mean folded in) for the kernels. */
+size_t tpr_packed_decoder_bytes(void);
+int tpr_pack_decoder(const float* w1 /*[64,32]*/, const float* b1 /*[64]*/,
+                     const float* w2 /*[33,64]*/, const float* b2 /*[33]*/,
+                     float w1_gain, float b1_gain, float w2_gain, float b2_gain,
+                     float* decoder_packed, void* stream);
+
+/* ---- a1: RaySampler.forward (VR/ray_sampler.py:24-63) ---------------------------------- */
+int tpr_ray_sample(const float* cam2world /*[N,4,4]*/, const float* intrinsics /*[N,3,3]*/,
+                   int64_t n_img, int32_t resolution,
+                   float* origins /*[N,res*res,3]*/, float* dirs /*[N,res*res,3]*/, void* stream);
+
+/* ---- a8: ImportanceRenderer.run_model (VR/renderer.py:142-148) ------------------------- */
+/* plane gather + decoder for arbitrary points; rgb may be NULL (density grids read sigma only,
+ * gen_videos.py:206). */
+int tpr_run_model(const float* planes_packed, int64_t n_img, int32_t height, int32_t width,
+                  const float* decoder_packed, const float* xyz /*[N,P,3]*/, int64_t n_pts,
+                  float box_warp, float* rgb /*[N,P,32] or NULL*/, float* sigma /*[N,P,1]*/,
+                  int32_t flags, void* stream);
+
+/* ---- a5: OSGDecoder.forward on already gathered features (training/triplane.py:124-136) - */
+int tpr_decode(const float* features /*[N,3,P,32]*/, int64_t n_img, int64_t n_pts,
+               const float* decoder_packed, float* rgb /*[N,P,32]*/, float* sigma /*[N,P,1]*/,
+               int32_t flags, void* stream);
+
+/* ---- a13: ImportanceRenderer.forward (VR/renderer.py:88-140), fused ---------------------- */
+/* jitter [N,M,Dc] stands for torch.rand_like at VR/renderer.py:190, u [N*M,Df] for torch.rand at
+ * :237 (the host shim draws both with the same torch calls, so the global RNG stream is consumed
+ * exactly as the reference consumes it).  ray_start_per_ray/ray_end_per_ray [N*M] are optional
+ * (the 'auto' limits branch, VR/renderer.py:91-97,183-186); pass NULL for scalar limits.
+ * Outputs: rgb [N,M,32], depth [N,M,1], weight_sum [N,M,1].  Optional debug outputs (NULL to
+ * skip): fine_depths [N*M,Df], fine_inds [N*M,Df] int32 (the searchsorted result, :240).
+ * scratch: tpr_render_scratch_bytes() bytes.  depth_range_io [2] (device) receives the global
+ * (min,max) of all sample depths that VR/ray_marcher.py:50 clamps against; if
+ * clamp_depth != 0 the clamp is applied by a trailing kernel, otherwise the caller applies it
+ * (after an all-reduce when rays are sharded over GPUs) with tpr_clamp_depth. */
+size_t tpr_render_scratch_bytes(int64_t n_img, int64_t n_rays, const TprOptions* opt);
+int tpr_render(const float* planes_packed, int64_t n_img, int32_t height, int32_t width,
+               const float* decoder_packed,
+               const float* origins /*[N,M,3]*/, const float* dirs /*[N,M,3]*/, int64_t n_rays,
+               const float* jitter, const float* u,
+               const float* ray_start_per_ray, const float* ray_end_per_ray,
+               const TprOptions* opt,
+               float* rgb, float* depth, float* weight_sum,
+               float* fine_depths, int32_t* fine_inds,
+               float* depth_range_io, int32_t clamp_depth,
+               void* scratch, size_t scratch_bytes, void* stream);
+int tpr_clamp_depth(float* depth, int64_t n, const float* depth_range /*[2] device*/, void* stream);
+
+/* ---- a9: MipRayMarcher2.forward (VR/ray_marcher.py:25-57), stand-alone ------------------ */
+/* colors [R,S,C], densities [R,S], depths [R,S] in the given (not re-sorted) order ->
+ * rgb [R,C], depth [R], weights [R,S-1].  depth_range is FOUR floats: [0..1] receive
+ * min/max(depths), [2..3] are scratch; the clamp is applied when clamp_depth != 0. */
+int tpr_ray_march(const float* colors, const float* densities, const float* depths,
+                  int64_t n_rays, int32_t n_samples, int32_t n_channels, int32_t white_back,
+                  float* rgb, float* depth, float* weights, float* depth_range, int32_t clamp_depth,
+                  void* stream);
+
+/* ---- a10/a11: sample_importance / sample_pdf (VR/renderer.py:194-253), stand-alone ------- */
+/* z_vals [R,S], weights [R,S-1] (coarse march weights), u [R,K] -> samples [R,K], inds [R,K]. */
+int tpr_sample_importance(const float* z_vals, const float* weights, const float* u,
+                          int64_t n_rays, int32_t n_samples, int32_t n_importance,
+                          float* samples, int32_t* inds, void* stream);
+/* bins [R,B+2] (only the first B+1 entries of each row are read, like the reference's call at
+ * :209-210), weights [R,B], u [R,K] -> samples [R,K], inds [R,K]. */
+int tpr_sample_pdf(const float* bins, int32_t bins_stride, const float* weights, const float* u,
+                   int64_t n_rays, int32_t n_weights, int32_t n_importance,
+                   float* samples, int32_t* inds, void* stream);
+
+/* ---- a14: math_utils.get_ray_limits_box (VR/math_utils.py:46-98) ------------------------ */
+int tpr_ray_limits_box(const float* origins, const float* dirs, int64_t n_rays,
+                       float box_side_length, float* t_min, float* t_max, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRIPLANE_B200_H_ */
