@@ -5,7 +5,7 @@ shared object is missing or fails to load, importing this module's ``lib()`` rai
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int32, c_int64, c_size_t, c_void_p
 
 from .build import LIB_PATH
 
@@ -14,10 +14,10 @@ MLP_FP32, MLP_BF16 = 0, 1
 
 
 class TprOptions(ctypes.Structure):
-    _fields_ = [('ray_start', c_float), ('ray_end', c_float), ('box_warp', c_float),
+    _fields_ = [('ray_start', c_double), ('ray_end', c_double), ('box_warp', c_double),
                 ('depth_resolution', c_int32), ('depth_resolution_importance', c_int32),
                 ('disparity_space_sampling', c_int32), ('white_back', c_int32),
-                ('flags', c_int32), ('tile_width', c_int32), ('reserved', c_int32 * 3)]
+                ('flags', c_int32), ('tile_width', c_int32), ('reserved', c_int32 * 5)]
 
 
 _P = c_void_p
@@ -29,7 +29,7 @@ _SIGNATURES = {
     'tpr_packed_decoder_bytes': (c_size_t, []),
     'tpr_pack_decoder': (ctypes.c_int, [_P, _P, _P, _P, c_float, c_float, c_float, c_float, _P, _P]),
     'tpr_ray_sample': (ctypes.c_int, [_P, _P, c_int64, c_int32, _P, _P, _P]),
-    'tpr_run_model': (ctypes.c_int, [_P, c_int64, c_int32, c_int32, _P, _P, c_int64, c_float, _P, _P, c_int32, _P]),
+    'tpr_run_model': (ctypes.c_int, [_P, c_int64, c_int32, c_int32, _P, _P, c_int64, c_double, _P, _P, c_int32, _P]),
     'tpr_decode': (ctypes.c_int, [_P, c_int64, c_int64, _P, _P, _P, c_int32, _P]),
     'tpr_render_scratch_bytes': (c_size_t, [c_int64, c_int64, ctypes.POINTER(TprOptions)]),
     'tpr_render': (ctypes.c_int, [_P, c_int64, c_int32, c_int32, _P, _P, _P, c_int64, _P, _P, _P, _P,

@@ -210,7 +210,7 @@ struct RenderArgs {
   const float* jitter; const float* u;
   const float* rs; const float* re;      // optional per-ray limits
   long long n_rays_total, rays_per_img, n_tiles, tiles_per_img;
-  float ray_start, ray_end, box_scale, lin_step, jitter_scale;
+  float ray_start, ray_end, box_scale, lin_step, jitter_scale, inv_start, inv_end;
   int Dc, Df, disparity, white_back, R;
   float* rgb; float* depth; float* wsum; float* fine_depths; int* fine_inds;
   unsigned* range_enc;                   // [2]: ordered-uint encoded (min, max) of all depths
@@ -225,8 +225,8 @@ __device__ __forceinline__ float coarse_depth(const RenderArgs& a, int k, float 
     const float step = 1.0f / (float)(D - 1);
     float t = (k < D / 2) ? __fmul_rn(step, (float)k) : __fsub_rn(1.0f, __fmul_rn(step, (float)(D - 1 - k)));
     t = __fadd_rn(t, __fmul_rn(jit, step));
-    float lo = __fmul_rn(__fdiv_rn(1.0f, a.ray_start), __fsub_rn(1.0f, t));
-    float hi = __fmul_rn(__fdiv_rn(1.0f, a.ray_end), t);
+    float lo = __fmul_rn(a.inv_start, __fsub_rn(1.0f, t));
+    float hi = __fmul_rn(a.inv_end, t);
     return __fdiv_rn(1.0f, __fadd_rn(lo, hi));
   }
   if (per_ray) {                          // :183-186 with math_utils.linspace (math_utils.py:101-118)
@@ -676,13 +676,13 @@ int tpr_ray_limits_box(const float* origins, const float* dirs, int64_t n_rays, 
 }
 
 static int launch_run_model(bool from_features, const float* planes, int64_t n_img, int32_t H, int32_t W,
-                            const float* dec, const float* in, int64_t n_pts, float box_warp, float* rgb, float* sigma,
+                            const float* dec, const float* in, int64_t n_pts, double box_warp, float* rgb, float* sigma,
                             int32_t flags, void* stream) {
   if (!dec || !in || !sigma) return fail(TPR_E_NULL, "run_model: NULL pointer");
   if (!from_features && !planes) return fail(TPR_E_NULL, "run_model: NULL planes");
   if (n_img <= 0 || n_pts <= 0) return fail(TPR_E_SHAPE, "run_model: empty input");
   if (!from_features && (H <= 0 || W <= 0 || (int64_t)H * W > (1 << 24))) return fail(TPR_E_SHAPE, "run_model: bad plane size");
-  if (!from_features && !(box_warp > 0.0f)) return fail(TPR_E_OPTION, "run_model: box_warp must be > 0");
+  if (!from_features && !(box_warp > 0.0)) return fail(TPR_E_OPTION, "run_model: box_warp must be > 0");
   if (flags != TPR_MLP_FP32) return fail(TPR_E_OPTION, "run_model: only TPR_MLP_FP32 is implemented in this build");
   DeviceInfo di = device_info();
   if (!di.ok) return fail(TPR_E_DEVICE, "run_model: no CUDA device");
@@ -697,7 +697,7 @@ static int launch_run_model(bool from_features, const float* planes, int64_t n_i
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(run_model_kernel)");
   const long long total = (long long)n_img * n_pts;
   const int grid = grid_for(total, kRmThreads, di.sms, env_int("TPR_RM_WAVES", 3));
-  const float box_scale = (float)(2.0 / (double)box_warp);
+  const float box_scale = (float)(2.0 / box_warp);      // python float (VR/renderer.py:61)
   if (from_features)
     run_model_kernel<true><<<grid, kRmThreads, smem, (cudaStream_t)stream>>>(nullptr, 0, 0, dec, in, n_img, n_pts, 0.f, rgb, sigma);
   else
@@ -707,7 +707,7 @@ static int launch_run_model(bool from_features, const float* planes, int64_t n_i
 }
 
 int tpr_run_model(const float* planes_packed, int64_t n_img, int32_t height, int32_t width, const float* decoder_packed,
-                  const float* xyz, int64_t n_pts, float box_warp, float* rgb, float* sigma, int32_t flags, void* stream) {
+                  const float* xyz, int64_t n_pts, double box_warp, float* rgb, float* sigma, int32_t flags, void* stream) {
   return launch_run_model(false, planes_packed, n_img, height, width, decoder_packed, xyz, n_pts, box_warp, rgb, sigma,
                           flags, stream);
 }
@@ -715,7 +715,7 @@ int tpr_run_model(const float* planes_packed, int64_t n_img, int32_t height, int
 int tpr_decode(const float* features, int64_t n_img, int64_t n_pts, const float* decoder_packed, float* rgb, float* sigma,
                int32_t flags, void* stream) {
   if (!rgb) return fail(TPR_E_NULL, "tpr_decode: NULL rgb");
-  return launch_run_model(true, nullptr, n_img, 0, 0, decoder_packed, features, n_pts, 1.0f, rgb, sigma, flags, stream);
+  return launch_run_model(true, nullptr, n_img, 0, 0, decoder_packed, features, n_pts, 1.0, rgb, sigma, flags, stream);
 }
 
 size_t tpr_render_scratch_bytes(int64_t, int64_t, const TprOptions*) { return 256; }
@@ -758,7 +758,7 @@ int tpr_render(const float* planes_packed, int64_t n_img, int32_t height, int32_
   if (Dc < 2 || Df < 0 || Dc + Df > TPR_MAX_SAMPLES) return fail(TPR_E_SHAPE, "tpr_render: depth resolutions out of range");
   if (Df > 0 && Dc < 4) return fail(TPR_E_SHAPE, "tpr_render: importance sampling needs depth_resolution >= 4");
   if (Df > 0 && !u) return fail(TPR_E_NULL, "tpr_render: NULL u with depth_resolution_importance > 0");
-  if (!(opt->box_warp > 0.0f)) return fail(TPR_E_OPTION, "tpr_render: box_warp must be > 0");
+  if (!(opt->box_warp > 0.0)) return fail(TPR_E_OPTION, "tpr_render: box_warp must be > 0");
   if (opt->flags != TPR_MLP_FP32) return fail(TPR_E_OPTION, "tpr_render: only TPR_MLP_FP32 is implemented in this build");
   if (scratch_bytes < tpr_render_scratch_bytes(n_img, n_rays, opt)) return fail(TPR_E_SCRATCH, "tpr_render: scratch too small");
   DeviceInfo di = device_info();
@@ -781,10 +781,11 @@ int tpr_render(const float* planes_packed, int64_t n_img, int32_t height, int32_
   a.n_rays_total = (long long)n_img * n_rays; a.rays_per_img = n_rays;
   a.tiles_per_img = (n_rays + R - 1) / R;
   a.n_tiles = a.tiles_per_img * n_img;
-  a.ray_start = opt->ray_start; a.ray_end = opt->ray_end;
-  a.box_scale = (float)(2.0 / (double)opt->box_warp);
-  a.lin_step = (opt->ray_end - opt->ray_start) / (float)(Dc - 1);                       // torch.linspace, float32
-  a.jitter_scale = (float)(((double)opt->ray_end - (double)opt->ray_start) / (Dc - 1)); // python float (VR/renderer.py:189)
+  a.ray_start = (float)opt->ray_start; a.ray_end = (float)opt->ray_end;                 // torch.linspace casts to float32
+  a.box_scale = (float)(2.0 / opt->box_warp);                                           // python float (VR/renderer.py:61)
+  a.lin_step = (a.ray_end - a.ray_start) / (float)(Dc - 1);                             // torch.linspace step, float32
+  a.jitter_scale = (float)((opt->ray_end - opt->ray_start) / (Dc - 1));                 // python float (VR/renderer.py:189)
+  a.inv_start = (float)(1.0 / opt->ray_start); a.inv_end = (float)(1.0 / opt->ray_end); // python floats (:181)
   a.Dc = Dc; a.Df = Df; a.disparity = opt->disparity_space_sampling; a.white_back = opt->white_back; a.R = R;
   a.rgb = rgb; a.depth = depth; a.wsum = weight_sum; a.fine_depths = fine_depths; a.fine_inds = fine_inds;
   a.range_enc = reinterpret_cast<unsigned*>(scratch);

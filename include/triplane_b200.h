@@ -55,16 +55,18 @@ enum {
 /* The subset of `rendering_options` the hot path reads (option table;
  * VR/renderer.py:91-100,116,143-146; VR/ray_marcher.py:32,52). */
 typedef struct TprOptions {
-  float ray_start;               /* scalar limits (VR/renderer.py:100); ignored if per-ray limits given */
-  float ray_end;
-  float box_warp;                /* VR/renderer.py:61 */
+  /* Python floats in the reference, so doubles here: the kernels reproduce the exact float32
+   * constants torch derives from them ((end-start)/(D-1), 1/start, 2/box_warp ...). */
+  double ray_start;              /* scalar limits (VR/renderer.py:100); ignored if per-ray limits given */
+  double ray_end;
+  double box_warp;               /* VR/renderer.py:61 */
   int32_t depth_resolution;      /* Dc >= 2 */
   int32_t depth_resolution_importance; /* Df >= 0; 0 = coarse pass only (VR/renderer.py:116,136-137) */
   int32_t disparity_space_sampling;    /* VR/renderer.py:174-181 */
   int32_t white_back;            /* VR/ray_marcher.py:52-53 */
   int32_t flags;                 /* TPR_MLP_* */
   int32_t tile_width;            /* perf hint only: rays form an image this many pixels wide (0 = unknown) */
-  int32_t reserved[3];
+  int32_t reserved[5];
 } TprOptions;
 
 int tpr_abi_version(void);
@@ -97,7 +99,7 @@ int tpr_ray_sample(const float* cam2world /*[N,4,4]*/, const float* intrinsics /
  * gen_videos.py:206). */
 int tpr_run_model(const float* planes_packed, int64_t n_img, int32_t height, int32_t width,
                   const float* decoder_packed, const float* xyz /*[N,P,3]*/, int64_t n_pts,
-                  float box_warp, float* rgb /*[N,P,32] or NULL*/, float* sigma /*[N,P,1]*/,
+                  double box_warp, float* rgb /*[N,P,32] or NULL*/, float* sigma /*[N,P,1]*/,
                   int32_t flags, void* stream);
 
 /* ---- a5: OSGDecoder.forward on already gathered features (training/triplane.py:124-136) - */

@@ -31,8 +31,8 @@ def test_library_exports_every_declared_symbol(pkg):
 
 
 def test_options_struct_layout_matches_header(pkg):
-    # 3 floats + 6 int32 + 3 reserved int32 = 48 bytes, no padding
-    assert ctypes.sizeof(pkg._lib.TprOptions) == 48
+    # 3 doubles + 6 int32 + 5 reserved int32 = 68 -> padded to 72 (8-byte alignment)
+    assert ctypes.sizeof(pkg._lib.TprOptions) == 72
 
 
 def test_argument_errors_are_reported_without_a_device(pkg):
