@@ -571,6 +571,7 @@ static thread_local std::string g_err;
 static int fail(int code, const char* msg) { g_err = msg; return code; }
 static int cuda_fail(cudaError_t e, const char* what) {
   g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  (void)cudaGetLastError();                 // clear the (non-sticky) error so later calls start clean
   return (int)e > 0 ? (int)e : 999;
 }
 #define TPR_CHECK_LAUNCH(what)                                   \
@@ -764,13 +765,19 @@ int tpr_render(const float* planes_packed, int64_t n_img, int32_t height, int32_
   DeviceInfo di = device_info();
   if (!di.ok) return fail(TPR_E_DEVICE, "tpr_render: no CUDA device");
 
-  int R, threads; size_t smem;
-  render_config(Dc, Df, di.smem_optin, R, threads, smem);
-  if ((int)smem > di.smem_optin) return fail(TPR_E_SHAPE, "tpr_render: sample count does not fit shared memory");
   void (*kern)(const RenderArgs) = (Dc + Df <= 64) ? render_kernel<2> : (Dc + Df <= 128) ? render_kernel<4> : render_kernel<8>;
+  cudaFuncAttributes fa;
   {
-    // cudaFuncSetAttribute is per device and cheap; set it on every call rather than caching per device
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin);
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncGetAttributes(render_kernel): no sm_100a image for this device?");
+  }
+  const int smem_cap = di.smem_optin - (int)fa.sharedSizeBytes;      // static smem counts against the opt-in limit
+  int R, threads; size_t smem;
+  render_config(Dc, Df, smem_cap, R, threads, smem);
+  if ((int)smem > smem_cap) return fail(TPR_E_SHAPE, "tpr_render: sample count does not fit shared memory");
+  {
+    // per device and cheap; set on every call rather than caching per device
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(render_kernel)");
   }
   RenderArgs a;

@@ -155,11 +155,20 @@ def test_ray_limits_box_and_auto_limits(pkg):
     t0, t1 = (-0.5 - o[0]) * inv, (0.5 - o[0]) * inv
     near, far = np.minimum(t0, t1).max(-1), np.maximum(t0, t1).min(-1)
     hit = near <= far
-    assert ((tmin > -1) == hit).mean() > 0.99
-    sel = hit & (tmin > -1)
-    np.testing.assert_allclose(tmin[sel], near[sel], atol=1e-4)
-    np.testing.assert_allclose(tmax[sel], far[sel], atol=1e-4)
-    assert (tmin[~hit & (tmin == -1)] == -1).all() and (tmax[tmin == -1] == -2).all()
+    missed = (tmin == -1) & (tmax == -2)                   # the reference's marker for "no intersection"
+    assert (missed == ~hit).mean() > 0.99                  # float32 vs float64 may disagree on grazing rays
+    sel = hit & ~missed
+    np.testing.assert_allclose(tmin[sel], near[sel], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(tmax[sel], far[sel], rtol=1e-4, atol=1e-4)
+    # 'auto' limits drive the per-ray branch of sample_stratified (VR/renderer.py:91-97,183-186)
+    scene, opts, _ = load_case('ragged')
+    o2 = dict(opts, ray_start='auto', ray_end='auto', box_warp=1)
+    R = pkg.ImportanceRenderer()
+    rgb, depth, wsum = R(T(scene['planes']), make_decoder(pkg, scene['dec']), T(scene['origins']), T(scene['dirs']), o2,
+                         noise=(T(scene['jitter']), T(scene['u'])))
+    assert torch.isfinite(rgb).all() and torch.isfinite(depth).all()
+    lo, hi = R.last_depth_range.tolist()
+    assert 2.0 < lo < hi < 3.6 and depth.min() >= lo and depth.max() <= hi
 
 
 def test_empty_space_rays_clamp_to_global_max_depth(pkg):
