@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_double, c_float, c_int32, c_int64, c_size_t, c_vo
 from .build import LIB_PATH
 
 ABI_VERSION = 1
-MLP_FP32, MLP_BF16 = 0, 1
+MLP_FP32, MLP_BF16, MLP_FFMA = 0, 1, 2
 
 
 class TprOptions(ctypes.Structure):

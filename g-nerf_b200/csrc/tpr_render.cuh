@@ -1,0 +1,141 @@
+// Pieces shared by the two fused render kernels (FFMA decoder: triplane_b200.cu, tensor-core
+// decoder: tpr_render_tc.cu).  Citations relative to /root/reference/g_nerf/ (VR/ = training/volumetric_rendering/).
+#pragma once
+#include "tpr_device.cuh"
+
+namespace tpr {
+
+struct RenderArgs {
+  const float* planes; int H, W;
+  const float* dec;
+  const float* origins; const float* dirs;
+  const float* jitter; const float* u;
+  const float* rs; const float* re;      // optional per-ray limits
+  long long n_rays_total, rays_per_img, n_tiles, tiles_per_img;
+  float ray_start, ray_end, box_scale, lin_step, jitter_scale, inv_start, inv_end;
+  int Dc, Df, disparity, white_back, R;
+  float* rgb; float* depth; float* wsum; float* fine_depths; int* fine_inds;
+  unsigned* range_enc;                   // [2]: ordered-uint encoded (min, max) of all depths
+};
+
+constexpr int kRenderMaxThreads = 512;
+
+// coarse depth k of a ray (VR/renderer.py:169-192)
+__device__ __forceinline__ float coarse_depth(const RenderArgs& a, int k, float jit, float rs, float re, bool per_ray) {
+  const int D = a.Dc;
+  if (a.disparity) {                      // :174-181
+    const float step = 1.0f / (float)(D - 1);
+    float t = (k < D / 2) ? __fmul_rn(step, (float)k) : __fsub_rn(1.0f, __fmul_rn(step, (float)(D - 1 - k)));
+    t = __fadd_rn(t, __fmul_rn(jit, step));
+    float lo = __fmul_rn(a.inv_start, __fsub_rn(1.0f, t));
+    float hi = __fmul_rn(a.inv_end, t);
+    return __fdiv_rn(1.0f, __fadd_rn(lo, hi));
+  }
+  if (per_ray) {                          // :183-186 with math_utils.linspace (math_utils.py:101-118)
+    float steps = __fdiv_rn((float)k, (float)(D - 1));
+    float base = __fadd_rn(rs, __fmul_rn(steps, __fsub_rn(re, rs)));
+    float delta = __fdiv_rn(__fsub_rn(re, rs), (float)(D - 1));
+    return __fadd_rn(base, __fmul_rn(jit, delta));
+  }
+  // :188-190 with torch.linspace's two-sided formula
+  float base = (k < D / 2) ? __fadd_rn(a.ray_start, __fmul_rn(a.lin_step, (float)k))
+                           : __fsub_rn(a.ray_end, __fmul_rn(a.lin_step, (float)(D - 1 - k)));
+  return __fadd_rn(base, __fmul_rn(jit, a.jitter_scale));
+}
+
+
+
+
+// a12 + a9 for the final pass: sort a ray's S samples by depth (VR/renderer.py:157-167), run the
+// march (VR/ray_marcher.py:26-46) and emit, per sample, the weight its colour carries in the composite:
+//   rgb = sum_i w_i (c_i + c_{i+1})/2 = sum_p c_p * omega_p,  omega_p = (w_{p-1} + w_p)/2.
+// kScatter = false: om[p], oi[p] by sorted position p (oi = original index);
+// kScatter = true : om[original index] = omega (oi unused).
+// Also returns sum(w), sum(w * mid depth) and folds the ray's depth range into (mn, mx).
+template <int E, bool kScatter>
+__device__ __forceinline__ void warp_sort_and_weights(const float* z, const float* sg, float* om, int* oi, int S, int lane,
+                                                      float& wsum_out, float& dnum_out, float& mn, float& mx) {
+  float key[E]; int idx[E];
+  bool sorted = true;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    int p = lane * E + e;
+    key[e] = p < S ? z[p] : __int_as_float(0x7f800000);
+    idx[e] = p;
+    if (e > 0) sorted &= !(key[e] < key[e - 1]);
+  }
+  {
+    float prev = __shfl_up_sync(kFull, key[E - 1], 1);
+    if (lane > 0) sorted &= !(key[0] < prev);
+  }
+  if (!__all_sync(kFull, sorted)) warp_bitonic_sort<E>(key, idx, lane);
+  // sorted, blocked: position p = lane*E + e
+  float sgm[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) sgm[e] = (lane * E + e) < S ? sg[idx[e]] : 0.0f;
+  const float nk = __shfl_down_sync(kFull, key[0], 1), ns = __shfl_down_sync(kFull, sgm[0], 1);
+  float al[E], dm[E];
+  float prod = 1.0f;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int p = lane * E + e;
+    const float d1 = e + 1 < E ? key[(e + 1) % E] : nk, s1 = e + 1 < E ? sgm[(e + 1) % E] : ns;
+    if (p + 1 < S) {
+      al[e] = interval_alpha(key[e], d1, sgm[e], s1);
+      dm[e] = (key[e] + d1) * 0.5f;
+      prod *= (1.0f - al[e] + 1e-10f);
+    } else { al[e] = 0.0f; dm[e] = 0.0f; }
+  }
+  float T = warp_excl_prod(prod, lane);
+  float wsum = 0.f, dnum = 0.f, w[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    w[e] = al[e] * T;
+    T *= (1.0f - al[e] + 1e-10f);
+    wsum += w[e];
+    dnum = fmaf(w[e], dm[e], dnum);
+  }
+  wsum_out = warp_sum(wsum);
+  dnum_out = warp_sum(dnum);
+  float wprev = __shfl_up_sync(kFull, w[E - 1], 1);
+  if (lane == 0) wprev = 0.0f;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int p = lane * E + e;
+    if (p < S) {
+      const float omega = 0.5f * ((e == 0 ? wprev : w[(e + E - 1) % E]) + w[e]);
+      if (kScatter) om[idx[e]] = omega;
+      else { om[p] = omega; oi[p] = idx[e]; }
+    }
+  }
+  // min / max of this ray's depths for the global clamp (VR/ray_marcher.py:50)
+  float lmn = key[0], lmx = -__int_as_float(0x7f800000);
+#pragma unroll
+  for (int e = 0; e < E; ++e) if (lane * E + e < S) lmx = key[e];
+  lmn = warp_min((lane * E) < S ? lmn : __int_as_float(0x7f800000));
+  lmx = warp_max(lmx);
+  mn = fminf(mn, lmn); mx = fmaxf(mx, lmx);
+}
+
+// one warp: coarse weights -> smoothed pdf -> CDF -> Df inverse-CDF draws (VR/renderer.py:194-253).
+// z, sg: the ray's coarse depths / densities (S-strided row); w, pw, cdf: scratch rows; fine: output row.
+__device__ __forceinline__ void warp_resample_ray(const RenderArgs& a, const float* z, const float* sg, float* w, float* pw,
+                                                  float* cdf, float* fine, long long g, int lane) {
+  const int Dc = a.Dc, Df = a.Df, nb = Dc - 3;
+  warp_march_weights(z, sg, w, Dc, lane);
+  __syncwarp();
+  warp_smooth_weights(w, pw, nb, lane);
+  __syncwarp();
+  warp_cdf(pw, cdf, nb, lane);
+  __syncwarp();
+  for (int j = lane; j < Df; j += 32) {
+    int inds;
+    float smp = invert_cdf(cdf, nb, __ldg(a.u + g * Df + j),
+                           [&](int i) { return __fmul_rn(0.5f, __fadd_rn(z[i], z[i + 1])); }, inds);
+    fine[j] = smp;
+    if (a.fine_depths) a.fine_depths[g * Df + j] = smp;
+    if (a.fine_inds) a.fine_inds[g * Df + j] = inds;
+  }
+}
+
+}  // namespace tpr

@@ -12,8 +12,13 @@
 
 #include "triplane_b200.h"
 #include "tpr_device.cuh"
+#include "tpr_render.cuh"
 
 namespace tpr {
+
+// tensor-core render path (tpr_render_tc.cu)
+int tc_rays_per_group(int Dc, int Df);
+int launch_render_tc(RenderArgs a, int bf16, int sms, int smem_optin, long long n_img, long long n_rays, cudaStream_t st);
 
 // =======================================================================================
 // layout preparation
@@ -203,44 +208,6 @@ __global__ void __launch_bounds__(kRmThreads) run_model_kernel(
 //                    D  sort 2D samples, final march, colour sum    (warp per ray)
 // Per-sample features and colours live only in shared memory (one 128-byte row per sample).
 // =======================================================================================
-struct RenderArgs {
-  const float* planes; int H, W;
-  const float* dec;
-  const float* origins; const float* dirs;
-  const float* jitter; const float* u;
-  const float* rs; const float* re;      // optional per-ray limits
-  long long n_rays_total, rays_per_img, n_tiles, tiles_per_img;
-  float ray_start, ray_end, box_scale, lin_step, jitter_scale, inv_start, inv_end;
-  int Dc, Df, disparity, white_back, R;
-  float* rgb; float* depth; float* wsum; float* fine_depths; int* fine_inds;
-  unsigned* range_enc;                   // [2]: ordered-uint encoded (min, max) of all depths
-};
-
-constexpr int kRenderMaxThreads = 512;
-
-// coarse depth k of a ray (VR/renderer.py:169-192)
-__device__ __forceinline__ float coarse_depth(const RenderArgs& a, int k, float jit, float rs, float re, bool per_ray) {
-  const int D = a.Dc;
-  if (a.disparity) {                      // :174-181
-    const float step = 1.0f / (float)(D - 1);
-    float t = (k < D / 2) ? __fmul_rn(step, (float)k) : __fsub_rn(1.0f, __fmul_rn(step, (float)(D - 1 - k)));
-    t = __fadd_rn(t, __fmul_rn(jit, step));
-    float lo = __fmul_rn(a.inv_start, __fsub_rn(1.0f, t));
-    float hi = __fmul_rn(a.inv_end, t);
-    return __fdiv_rn(1.0f, __fadd_rn(lo, hi));
-  }
-  if (per_ray) {                          // :183-186 with math_utils.linspace (math_utils.py:101-118)
-    float steps = __fdiv_rn((float)k, (float)(D - 1));
-    float base = __fadd_rn(rs, __fmul_rn(steps, __fsub_rn(re, rs)));
-    float delta = __fdiv_rn(__fsub_rn(re, rs), (float)(D - 1));
-    return __fadd_rn(base, __fmul_rn(jit, delta));
-  }
-  // :188-190 with torch.linspace's two-sided formula
-  float base = (k < D / 2) ? __fadd_rn(a.ray_start, __fmul_rn(a.lin_step, (float)k))
-                           : __fsub_rn(a.ray_end, __fmul_rn(a.lin_step, (float)(D - 1 - k)));
-  return __fadd_rn(base, __fmul_rn(jit, a.jitter_scale));
-}
-
 struct TileSmem {
   float* wsm;     // packed decoder
   float* col;     // [R*S][32]  features, then colours
@@ -281,67 +248,10 @@ template <int E>
 __device__ __forceinline__ void ray_composite(const RenderArgs& a, const TileSmem& sm, int r, long long g, int S,
                                               float& mn, float& mx) {
   const int lane = threadIdx.x & 31;
-  const float* z = sm.dep + r * S;
-  const float* sg = sm.sig + r * S;
   float* om = sm.wa + r * S;
   int* oi = reinterpret_cast<int*>(sm.wb + r * S);
-  float key[E]; int idx[E];
-  bool sorted = true;
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    int p = lane * E + e;
-    key[e] = p < S ? z[p] : __int_as_float(0x7f800000);
-    idx[e] = p;
-    if (e > 0) sorted &= !(key[e] < key[e - 1]);
-  }
-  {
-    float prev = __shfl_up_sync(kFull, key[E - 1], 1);
-    if (lane > 0) sorted &= !(key[0] < prev);
-  }
-  if (!__all_sync(kFull, sorted)) warp_bitonic_sort<E>(key, idx, lane);
-  // sorted, blocked: position p = lane*E + e
-  float sgm[E];
-#pragma unroll
-  for (int e = 0; e < E; ++e) sgm[e] = (lane * E + e) < S ? sg[idx[e]] : 0.0f;
-  const float nk = __shfl_down_sync(kFull, key[0], 1), ns = __shfl_down_sync(kFull, sgm[0], 1);
-  float al[E], dm[E];
-  float prod = 1.0f;
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    const int p = lane * E + e;
-    const float d1 = e + 1 < E ? key[(e + 1) % E] : nk, s1 = e + 1 < E ? sgm[(e + 1) % E] : ns;
-    if (p + 1 < S) {
-      al[e] = interval_alpha(key[e], d1, sgm[e], s1);
-      dm[e] = (key[e] + d1) * 0.5f;
-      prod *= (1.0f - al[e] + 1e-10f);
-    } else { al[e] = 0.0f; dm[e] = 0.0f; }
-  }
-  float T = warp_excl_prod(prod, lane);
-  float wsum = 0.f, dnum = 0.f, w[E];
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    w[e] = al[e] * T;
-    T *= (1.0f - al[e] + 1e-10f);
-    wsum += w[e];
-    dnum = fmaf(w[e], dm[e], dnum);
-  }
-  wsum = warp_sum(wsum);
-  dnum = warp_sum(dnum);
-  // rgb = sum_i w_i (c_i + c_{i+1})/2 = sum_p c_p (w_{p-1} + w_p)/2     (VR/ray_marcher.py:27,44)
-  float wprev = __shfl_up_sync(kFull, w[E - 1], 1);
-  if (lane == 0) wprev = 0.0f;
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    const int p = lane * E + e;
-    if (p < S) { om[p] = 0.5f * ((e == 0 ? wprev : w[(e + E - 1) % E]) + w[e]); oi[p] = idx[e]; }
-  }
-  // min / max of this ray's depths for the global clamp (VR/ray_marcher.py:50)
-  float lmn = key[0], lmx = -__int_as_float(0x7f800000);
-#pragma unroll
-  for (int e = 0; e < E; ++e) if (lane * E + e < S) lmx = key[e];
-  lmn = warp_min((lane * E) < S ? lmn : __int_as_float(0x7f800000));
-  lmx = warp_max(lmx);
-  mn = fminf(mn, lmn); mx = fmaxf(mx, lmx);
+  float wsum, dnum;
+  warp_sort_and_weights<E, false>(sm.dep + r * S, sm.sig + r * S, om, oi, S, lane, wsum, dnum, mn, mx);
   __syncwarp();
   // colour sum: lane = channel
   const int rowbase = r * S;
@@ -417,26 +327,9 @@ __global__ void __launch_bounds__(kRenderMaxThreads, 1) render_kernel(const Rend
     for (int pass = 0; pass < n_pass; ++pass) {
       if (pass == 1) {
         // ---- B: importance resampling, one warp per ray
-        const int nb = Dc - 3;
-        for (int r = warp; r < nr; r += nwarps) {
-          const float* z = sm.dep + r * S;
-          float* w = sm.wa + r * S; float* pw = sm.wb + r * S; float* cdf = sm.wc + r * S;
-          warp_march_weights(z, sm.sig + r * S, w, Dc, lane);
-          __syncwarp();
-          warp_smooth_weights(w, pw, nb, lane);
-          __syncwarp();
-          warp_cdf(pw, cdf, nb, lane);
-          __syncwarp();
-          const long long g = g0 + r;
-          for (int j = lane; j < Df; j += 32) {
-            int inds;
-            float smp = invert_cdf(cdf, nb, __ldg(a.u + g * Df + j),
-                                   [&](int i) { return __fmul_rn(0.5f, __fadd_rn(z[i], z[i + 1])); }, inds);
-            sm.dep[r * S + Dc + j] = smp;
-            if (a.fine_depths) a.fine_depths[g * Df + j] = smp;
-            if (a.fine_inds) a.fine_inds[g * Df + j] = inds;
-          }
-        }
+        for (int r = warp; r < nr; r += nwarps)
+          warp_resample_ray(a, sm.dep + r * S, sm.sig + r * S, sm.wa + r * S, sm.wb + r * S, sm.wc + r * S,
+                            sm.dep + r * S + Dc, g0 + r, lane);
         __syncthreads();
       }
       // ---- A / C: gather + decode the coarse (pass 0) or fine (pass 1) samples
@@ -684,7 +577,9 @@ static int launch_run_model(bool from_features, const float* planes, int64_t n_i
   if (n_img <= 0 || n_pts <= 0) return fail(TPR_E_SHAPE, "run_model: empty input");
   if (!from_features && (H <= 0 || W <= 0 || (int64_t)H * W > (1 << 24))) return fail(TPR_E_SHAPE, "run_model: bad plane size");
   if (!from_features && !(box_warp > 0.0)) return fail(TPR_E_OPTION, "run_model: box_warp must be > 0");
-  if (flags != TPR_MLP_FP32) return fail(TPR_E_OPTION, "run_model: only TPR_MLP_FP32 is implemented in this build");
+  if (flags != TPR_MLP_FP32 && flags != TPR_MLP_BF16 && flags != TPR_MLP_FFMA)
+    return fail(TPR_E_OPTION, "run_model: unknown decoder flag");
+  // point queries always run the fp32 FFMA decoder (at least as accurate as any requested mode)
   DeviceInfo di = device_info();
   if (!di.ok) return fail(TPR_E_DEVICE, "run_model: no CUDA device");
   const size_t smem = sizeof(float) * (kDecFloats + kRmWarps * 32 * kC);
@@ -760,53 +655,62 @@ int tpr_render(const float* planes_packed, int64_t n_img, int32_t height, int32_
   if (Df > 0 && Dc < 4) return fail(TPR_E_SHAPE, "tpr_render: importance sampling needs depth_resolution >= 4");
   if (Df > 0 && !u) return fail(TPR_E_NULL, "tpr_render: NULL u with depth_resolution_importance > 0");
   if (!(opt->box_warp > 0.0)) return fail(TPR_E_OPTION, "tpr_render: box_warp must be > 0");
-  if (opt->flags != TPR_MLP_FP32) return fail(TPR_E_OPTION, "tpr_render: only TPR_MLP_FP32 is implemented in this build");
+  if (opt->flags != TPR_MLP_FP32 && opt->flags != TPR_MLP_BF16 && opt->flags != TPR_MLP_FFMA)
+    return fail(TPR_E_OPTION, "tpr_render: unknown decoder flag");
   if (scratch_bytes < tpr_render_scratch_bytes(n_img, n_rays, opt)) return fail(TPR_E_SCRATCH, "tpr_render: scratch too small");
   DeviceInfo di = device_info();
   if (!di.ok) return fail(TPR_E_DEVICE, "tpr_render: no CUDA device");
 
-  void (*kern)(const RenderArgs) = (Dc + Df <= 64) ? render_kernel<2> : (Dc + Df <= 128) ? render_kernel<4> : render_kernel<8>;
-  cudaFuncAttributes fa;
-  {
-    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncGetAttributes(render_kernel): no sm_100a image for this device?");
-  }
-  const int smem_cap = di.smem_optin - (int)fa.sharedSizeBytes;      // static smem counts against the opt-in limit
-  int R, threads; size_t smem;
-  render_config(Dc, Df, smem_cap, R, threads, smem);
-  if ((int)smem > smem_cap) return fail(TPR_E_SHAPE, "tpr_render: sample count does not fit shared memory");
-  {
-    // per device and cheap; set on every call rather than caching per device
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(render_kernel)");
-  }
   RenderArgs a;
   memset(&a, 0, sizeof(a));
   a.planes = planes_packed; a.H = height; a.W = width; a.dec = decoder_packed;
   a.origins = origins; a.dirs = dirs; a.jitter = jitter; a.u = u;
   a.rs = ray_start_per_ray; a.re = ray_end_per_ray;
   a.n_rays_total = (long long)n_img * n_rays; a.rays_per_img = n_rays;
-  a.tiles_per_img = (n_rays + R - 1) / R;
-  a.n_tiles = a.tiles_per_img * n_img;
   a.ray_start = (float)opt->ray_start; a.ray_end = (float)opt->ray_end;                 // torch.linspace casts to float32
   a.box_scale = (float)(2.0 / opt->box_warp);                                           // python float (VR/renderer.py:61)
   a.lin_step = (a.ray_end - a.ray_start) / (float)(Dc - 1);                             // torch.linspace step, float32
   a.jitter_scale = (float)((opt->ray_end - opt->ray_start) / (Dc - 1));                 // python float (VR/renderer.py:189)
   a.inv_start = (float)(1.0 / opt->ray_start); a.inv_end = (float)(1.0 / opt->ray_end); // python floats (:181)
-  a.Dc = Dc; a.Df = Df; a.disparity = opt->disparity_space_sampling; a.white_back = opt->white_back; a.R = R;
+  a.Dc = Dc; a.Df = Df; a.disparity = opt->disparity_space_sampling; a.white_back = opt->white_back;
   a.rgb = rgb; a.depth = depth; a.wsum = weight_sum; a.fine_depths = fine_depths; a.fine_inds = fine_inds;
   a.range_enc = reinterpret_cast<unsigned*>(scratch);
-
-  int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
-  if (occ < 1) occ = 1;
-  long long grid = (long long)di.sms * occ;
-  if (grid > a.n_tiles) grid = a.n_tiles;
   cudaStream_t st = (cudaStream_t)stream;
   range_init_kernel<<<1, 1, 0, st>>>(a.range_enc);
   TPR_CHECK_LAUNCH("range_init_kernel");
-  kern<<<(unsigned)grid, threads, smem, st>>>(a);
-  TPR_CHECK_LAUNCH("render_kernel");
+
+  const bool use_tc = opt->flags != TPR_MLP_FFMA && tc_rays_per_group(Dc, Df) > 0 && !env_int("TPR_FORCE_FFMA", 0);
+  if (use_tc) {
+    // decoder on the tensor cores: 3xTF32 for the fp32 parity mode, bf16 operands for the PSNR mode
+    int rc = launch_render_tc(a, opt->flags == TPR_MLP_BF16, di.sms, di.smem_optin, n_img, n_rays, st);
+    if (rc != 0) return cuda_fail((cudaError_t)rc, "render_tc_kernel");
+  } else {
+    void (*kern)(const RenderArgs) = (Dc + Df <= 64) ? render_kernel<2> : (Dc + Df <= 128) ? render_kernel<4> : render_kernel<8>;
+    cudaFuncAttributes fa;
+    {
+      cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncGetAttributes(render_kernel): no sm_100a image for this device?");
+    }
+    const int smem_cap = di.smem_optin - (int)fa.sharedSizeBytes;      // static smem counts against the opt-in limit
+    int R, threads; size_t smem;
+    render_config(Dc, Df, smem_cap, R, threads, smem);
+    if ((int)smem > smem_cap) return fail(TPR_E_SHAPE, "tpr_render: sample count does not fit shared memory");
+    {
+      // per device and cheap; set on every call rather than caching per device
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(render_kernel)");
+    }
+    a.R = R;
+    a.tiles_per_img = (n_rays + R - 1) / R;
+    a.n_tiles = a.tiles_per_img * n_img;
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+    if (occ < 1) occ = 1;
+    long long grid = (long long)di.sms * occ;
+    if (grid > a.n_tiles) grid = a.n_tiles;
+    kern<<<(unsigned)grid, threads, smem, st>>>(a);
+    TPR_CHECK_LAUNCH("render_kernel");
+  }
   finish_kernel<<<grid_for(a.n_rays_total, 256, di.sms, 4), 256, 0, st>>>(a.range_enc, depth_range_io, depth, a.n_rays_total,
                                                                           clamp_depth);
   TPR_CHECK_LAUNCH("finish_kernel");

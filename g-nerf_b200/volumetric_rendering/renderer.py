@@ -114,7 +114,9 @@ def _mlp_flag(options):
         return _lib.MLP_FP32
     if mode == 'bf16':
         return _lib.MLP_BF16
-    raise RuntimeError(f"rendering_options['decoder_precision'] must be 'fp32' or 'bf16', got {mode!r}")
+    if mode == 'fp32_ffma':
+        return _lib.MLP_FFMA
+    raise RuntimeError(f"rendering_options['decoder_precision'] must be 'fp32', 'bf16' or 'fp32_ffma', got {mode!r}")
 
 
 class ImportanceRenderer(torch.nn.Module):

@@ -78,9 +78,33 @@ def test_decoder_on_gathered_features(pkg, name):
     assert np.abs(out['sigma'].cpu().numpy() - sig_o).max() < 2e-5
 
 
+def psnr(got, want, peak):
+    mse = float(np.mean((got.astype(np.float64) - want.astype(np.float64)) ** 2))
+    return float('inf') if mse == 0 else 10.0 * np.log10(peak * peak / mse)
+
+
 @pytest.mark.parametrize('name', list(CASES))
-def test_render_against_oracle_and_reference_fixture(pkg, name):
+def test_render_bf16_decoder_psnr(pkg, name):
+    """bf16-MLP mode (tcgen05 kind::f16 with bf16 operands): >= 50 dB PSNR against the oracle, peak 2.0 for
+    rgb/features and ray_end - ray_start for depth (BASELINE.json north_star)."""
     scene, opts, gold = load_case(name)
+    o = dict(opts, decoder_precision='bf16')
+    rgb, depth, wsum = pkg.ImportanceRenderer()(T(scene['planes']), make_decoder(pkg, scene['dec']), T(scene['origins']),
+                                                T(scene['dirs']), o, noise=(T(scene['jitter']), T(scene['u'])))
+    assert torch.isfinite(rgb).all() and torch.isfinite(depth).all()
+    p_rgb = psnr(rgb.cpu().numpy(), gold['rgb'], 2.0)
+    p_d = psnr(depth.cpu().numpy(), gold['depth'], opts['ray_end'] - opts['ray_start'])
+    p_w = psnr(wsum.cpu().numpy(), gold['wsum'], 1.0)
+    print(f'{name}: bf16 PSNR rgb {p_rgb:.1f} dB, depth {p_d:.1f} dB, wsum {p_w:.1f} dB')
+    assert p_rgb >= 50 and p_d >= 50 and p_w >= 50
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'fp32_ffma'])
+@pytest.mark.parametrize('name', list(CASES))
+def test_render_against_oracle_and_reference_fixture(pkg, name, mode):
+    """'fp32' = decoder on tcgen05 with 3xTF32 operands; 'fp32_ffma' = decoder in fp32 FFMA.  Same 1e-4 gate."""
+    scene, opts, gold = load_case(name)
+    opts = dict(opts, decoder_precision=mode)
     R = pkg.ImportanceRenderer()
     R.debug_outputs = True
     rgb, depth, wsum = R(T(scene['planes']), make_decoder(pkg, scene['dec']), T(scene['origins']), T(scene['dirs']),
