@@ -49,26 +49,32 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          '-lms', '20', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.time(), [c.strip() for c in line.split(',')]))
+
+    def window(self, t0, t1):
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        t0, t1 = getattr(self, 't0', 0.0), getattr(self, 't1', float('inf'))
+        rows = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.03] or [r for _, r in self.rows[-3:]]
+        sm = [float(r[0]) for r in rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        pw = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith('active')})
+        reasons = sorted({names[i] for r in rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith('active')})
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(sm)}
+                'power_w_max': max(pw) if pw else None, 'reasons': reasons, 'samples': len(sm)}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -160,10 +166,10 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--mode', default='fp32', choices=['fp32', 'bf16'])
+    ap.add_argument('--mode', default='fp32', choices=['fp32', 'bf16', 'fp32_ffma'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -229,19 +235,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler_clk = ClockSampler(local)
+    if rank == 0:
+        sampler_clk.start()              # nvidia-smi needs ~100 ms to start: begin before the warm-up
     for _ in range(warmup):
         step()
     barrier()
-    sampler_clk = ClockSampler(local)
-    if rank == 0:
-        sampler_clk.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_wall0 = time.time()
     ev0.record()
     for _ in range(args.steps):
         step(record=True)
     ev1.record()
     barrier()
+    sampler_clk.window(t_wall0, time.time())
     ms = ev0.elapsed_time(ev1) / args.steps
     clocks = sampler_clk.stop() if rank == 0 else None
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
@@ -289,7 +297,7 @@ def main():
         line = {
             'metric': METRIC, 'value': value, 'unit': METRIC, 'n_gpus': world, 'steps': args.steps, 'warmup': warmup,
             'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32' if args.mode == 'fp32' else 'bf16-mlp', 'data': 'synthetic',
+            'dtype': 'bf16-mlp' if args.mode == 'bf16' else 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'per_gpu_batch': N_IMG, 'rays_per_image': m, 'samples_per_ray': DC + DF,
                        'decoder_precision': args.mode, 'parallelism': f'image-batch sharding x{world}, all-gather of outputs'
                        if world > 1 else 'single GPU',
@@ -297,7 +305,7 @@ def main():
                        'step': 'ImportanceRenderer.forward incl. plane repack, decoder pack, both torch.rand draws'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                          'frac': achieved / pk['hbm_gbs'], 'traffic': None, 'peak_kind': pk_kind,
-                         'kernel': 'render_kernel (tpr_render: +2 helper launches of ~2 us)', 'kernel_ms': kern_ms,
+                         'kernel': ('render_kernel' if args.mode == 'fp32_ffma' else 'render_tc_kernel') + ' (tpr_render: +2 helper launches of ~2 us)', 'kernel_ms': kern_ms,
                          'algorithmic_bytes_per_launch': samples_per_step * BYTES_PER_SAMPLE},
             'e2e': {'value': world * samples_per_step / (e2e_ms * 1e-3), 'unit': METRIC, 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},

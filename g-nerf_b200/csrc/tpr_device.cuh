@@ -176,6 +176,35 @@ __device__ __forceinline__ float4 gather_point(const float* __restrict__ img, in
   return make_float4(a0.x + a1.x + a2.x, a0.y + a1.y + a2.y, a0.z + a1.z + a2.z, a0.w + a1.w + a2.w);
 }
 
+// Tap table entry for one (sample, plane): element offsets (plane offset included) and weights.
+struct __align__(16) TapEntry { int off[4]; float w[4]; };
+
+// Same as gather_point, but the 12 (offset, weight) pairs come from a shared-memory tap table that one
+// lane per (sample, plane) filled beforehand -- the eight lanes of a sample no longer redo that arithmetic.
+__device__ __forceinline__ float4 gather_point_taps(const float* __restrict__ img_sub, const TapEntry* __restrict__ te) {
+  int4 o[3]; float4 w[3];
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    o[p] = *reinterpret_cast<const int4*>(te[p].off);
+    w[p] = *reinterpret_cast<const float4*>(te[p].w);
+  }
+  float4 v[12];
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    v[4 * p + 0] = ldg128(img_sub + (unsigned)o[p].x);
+    v[4 * p + 1] = ldg128(img_sub + (unsigned)o[p].y);
+    v[4 * p + 2] = ldg128(img_sub + (unsigned)o[p].z);
+    v[4 * p + 3] = ldg128(img_sub + (unsigned)o[p].w);
+  }
+  float4 a[3];
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    a[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    fma4(a[p], w[p].x, v[4 * p]); fma4(a[p], w[p].y, v[4 * p + 1]); fma4(a[p], w[p].z, v[4 * p + 2]); fma4(a[p], w[p].w, v[4 * p + 3]);
+  }
+  return make_float4(a[0].x + a[1].x + a[2].x, a[0].y + a[1].y + a[2].y, a[0].z + a[1].z + a[2].z, a[0].w + a[1].w + a[2].w);
+}
+
 // One warp gathers the plane features of its 32 samples into shared-memory rows.
 // Lane L supplies sample L (point, destination row, validity); `img` (this image's
 // [3][H][W][32] block) is warp-uniform.  Eight lanes cooperate on one sample so every load

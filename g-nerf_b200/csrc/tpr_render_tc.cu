@@ -66,13 +66,15 @@ __device__ void tc_stage_weights(const float* __restrict__ dec, TcTiles<MODE>& t
   __syncthreads();
   for (int i = tid; i < kN1 * 32; i += kTcThreads) {
     const int n = i >> 5, k = i & 31;
-    const float w = dec[kW1tOff + k * kHid + n];
+    const float w = dec[kW1tOff + k * kHid + n] * kLog2e;          // layer-1 output in the log2 domain
     if (MODE == 1) st_swz_bf16(tl.b1[0], n, k, w);
     else { float hi, lo; split_tf32(w, hi, lo); st_swz_f32(tl.b1[0], n, k, hi); st_swz_f32(tl.b1[MODE == 0 ? 1 : 0], n, k, lo); }
   }
   for (int i = tid; i < kN2 * 64; i += kTcThreads) {
     const int n = i >> 6, k = i & 63;
-    const float w = n < kOutPad ? dec[kW2tOff + k * kOutPad + n] : 0.0f;
+    // hidden activations arrive as softplus/ln2; colour rows (n >= 1) produce logits times -log2(e)
+    const float w0 = n < kOutPad ? dec[kW2tOff + k * kOutPad + n] : 0.0f;
+    const float w = n == 0 ? w0 * kLn2 : -w0;
     if (MODE == 1) st_swz_bf16(tl.b2[0][0], n, k, w);
     else {
       float hi, lo; split_tf32(w, hi, lo);
@@ -83,7 +85,8 @@ __device__ void tc_stage_weights(const float* __restrict__ dec, TcTiles<MODE>& t
   for (int n = tid; n < kN1 + kN2; n += kTcThreads) {
     const bool l1 = n < kN1;
     const int r = l1 ? n : n - kN1;
-    const float b = l1 ? dec[kB1Off + r] : (r < kOutPad ? dec[kB2Off + r] : 0.0f);
+    const float b = l1 ? dec[kB1Off + r] * kLog2e
+                       : (r < kOutPad ? (r == 0 ? dec[kB2Off] : -kLog2e * dec[kB2Off + r]) : 0.0f);
     float* tile = l1 ? tl.bias1 : tl.bias2;
     if (MODE == 1) {
       const float hi = __bfloat162float(__float2bfloat16_rn(b));
@@ -99,28 +102,47 @@ struct TcRaySmem {
   float* dep; float* sig; float* wa; float* wb; float* wc; float* ray; float* rayw;
 };
 
-// G: gather one tile (rows = R rays x DPT depths) into A1[buf]
+// G: gather one tile (rows = R rays x DPT depths) into A1[buf].  Warp w owns rows [8w, 8w+8).
+// Step 1: lane 3s+p computes the bilinear taps of (sample s, plane p) once into the warp's tap table.
+// Step 2: eight lanes per sample fetch whole 128-byte texels (four channels per lane) and blend.
 template <int MODE>
 __device__ __forceinline__ void tc_gather_tile(const RenderArgs& a, TcTiles<MODE>& tl, int buf, const float* __restrict__ img,
-                                               const TcRaySmem& rs, int nr, int Dx, int off, int S, int t, int dpt_shift) {
+                                               const TcRaySmem& rs, TapEntry* taps_all, int nr, int Dx, int off, int S,
+                                               int t, int dpt_shift) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & 7;
   const int dpt = 1 << dpt_shift;
-#pragma unroll
-  for (int rd = 0; rd < 2; ++rd) {
-    const int row = warp * 8 + rd * 4 + grp;
+  TapEntry* tw = taps_all + warp * 24;
+  {
+    const int s = lane / 3, p = lane - s * 3;
+    const int row = warp * 8 + s;
     const int r = row >> dpt_shift, di = t * dpt + (row & (dpt - 1));
-    if (r < nr && di < Dx) {
+    if (lane < 24 && r < nr && di < Dx) {
       const float d = rs.dep[r * S + off + di];
       const float* ry = rs.ray + r * 8;
       // origin + depth * direction (VR/renderer.py:105,123), then * 2/box_warp (:61)
       const float px = __fmul_rn(__fadd_rn(ry[0], __fmul_rn(d, ry[3])), a.box_scale);
       const float py = __fmul_rn(__fadd_rn(ry[1], __fmul_rn(d, ry[4])), a.box_scale);
       const float pz = __fmul_rn(__fadd_rn(ry[2], __fmul_rn(d, ry[5])), a.box_scale);
-      const float4 f = gather_point(img, a.H, a.W, px, py, pz, sub);
+      Taps tp;
+      plane_taps(p == 2 ? pz : px, p == 0 ? py : (p == 1 ? pz : px), a.H, a.W, tp);   // (x,y) (x,z) (z,x)
+      const int po = p * a.H * a.W * kC;
+      *reinterpret_cast<int4*>(tw[lane].off) = make_int4(tp.off[0] + po, tp.off[1] + po, tp.off[2] + po, tp.off[3] + po);
+      *reinterpret_cast<float4*>(tw[lane].w) = make_float4(tp.w[0], tp.w[1], tp.w[2], tp.w[3]);
+    }
+  }
+  __syncwarp();
+  const float* img_sub = img + sub * 4;
+#pragma unroll
+  for (int rd = 0; rd < 2; ++rd) {
+    const int s = rd * 4 + grp;
+    const int row = warp * 8 + s;
+    const int r = row >> dpt_shift, di = t * dpt + (row & (dpt - 1));
+    if (r < nr && di < Dx) {
+      const float4 f = gather_point_taps(img_sub, tw + s * 3);
       if (MODE == 1) {
         uint2 pk = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
-        uint8_t* base = reinterpret_cast<uint8_t*>(tl.a1[buf][0]) + row * 128 + ((((sub >> 1) ^ (row & 7)) << 4) | ((sub & 1) << 3));
-        *reinterpret_cast<uint2*>(base) = pk;
+        uint8_t* dst = reinterpret_cast<uint8_t*>(tl.a1[buf][0]) + row * 128 + ((((sub >> 1) ^ (row & 7)) << 4) | ((sub & 1) << 3));
+        *reinterpret_cast<uint2*>(dst) = pk;
       } else {
         float4 hi, lo;
         split_tf32(f.x, hi.x, lo.x); split_tf32(f.y, hi.y, lo.y); split_tf32(f.z, hi.z, lo.z); split_tf32(f.w, hi.w, lo.w);
@@ -129,6 +151,7 @@ __device__ __forceinline__ void tc_gather_tile(const RenderArgs& a, TcTiles<MODE
       }
     }
   }
+  __syncwarp();           // the tap table is rewritten by the next tile
 }
 
 // M1: D1 = A1 . W1^T + b1      (one thread)
@@ -191,14 +214,14 @@ __device__ __forceinline__ void tc_epilogue1(uint32_t tmem) {
   if (MODE == 1) {
     uint32_t pk[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(softplus_f(__uint_as_float(r[2 * i])), softplus_f(__uint_as_float(r[2 * i + 1])));
+    for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(softplus_log2(__uint_as_float(r[2 * i])), softplus_log2(__uint_as_float(r[2 * i + 1])));
     tmem_st8(tmem + kColA2Hi + lane_base + 8 * j, pk);
   } else {
     uint32_t hi[16], lo[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       float a, b;
-      split_tf32(softplus_f(__uint_as_float(r[i])), a, b);
+      split_tf32(softplus_log2(__uint_as_float(r[i])), a, b);
       hi[i] = __float_as_uint(a); lo[i] = __float_as_uint(b);
     }
     tmem_st16(tmem + kColA2Hi + lane_base + 16 * j, hi);
@@ -210,9 +233,12 @@ __device__ __forceinline__ void tc_epilogue1(uint32_t tmem) {
 template <int MODE, int E>
 __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for the swizzled tiles; offsetting the __shared__ array (rather than round-tripping
+  // through an integer) keeps every access an LDS/STS instead of a generic LD/ST
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   TcTiles<MODE>& tl = *reinterpret_cast<TcTiles<MODE>*>(base);
-  float* fl = reinterpret_cast<float*>(base + sizeof(TcTiles<MODE>));
+  TapEntry* taps = reinterpret_cast<TapEntry*>(base + sizeof(TcTiles<MODE>));
+  float* fl = reinterpret_cast<float*>(base + sizeof(TcTiles<MODE>) + sizeof(TapEntry) * kTcWarps * 24);
   const int R = a.R, Dc = a.Dc, Df = a.Df, S = Dc + Df;
   const int dpt_shift = R == 8 ? 4 : 5, dpt = 1 << dpt_shift;
   TcRaySmem rs;
@@ -287,7 +313,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderAr
         __syncthreads();
       }
       // ---- tile pipeline
-      tc_gather_tile<MODE>(a, tl, 0, img, rs, nr, Dx, off, S, 0, dpt_shift);
+      tc_gather_tile<MODE>(a, tl, 0, img, rs, taps, nr, Dx, off, S, 0, dpt_shift);
       fence_proxy_async_smem();
       __syncthreads();
 #pragma unroll 1
@@ -298,7 +324,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderAr
           mma_commit(&bar1);
         }
         if (t + 1 < T) {
-          tc_gather_tile<MODE>(a, tl, (t + 1) & 1, img, rs, nr, Dx, off, S, t + 1, dpt_shift);
+          tc_gather_tile<MODE>(a, tl, (t + 1) & 1, img, rs, taps, nr, Dx, off, S, t + 1, dpt_shift);
           fence_proxy_async_smem();
         }
         mbar_wait(&bar1, p1); p1 ^= 1;
@@ -352,7 +378,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderAr
         tmem_ld8(tmem + kColSlots + sl * kSlotCols + lane_base + 1 + 8 * j, v);
         tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] = valid ? fmaf(om, colour_act(__uint_as_float(v[c])), acc[c]) : acc[c];
+        for (int c = 0; c < 8; ++c) acc[c] = valid ? fmaf(om, colour_act_neglog2(__uint_as_float(v[c])), acc[c]) : acc[c];
       }
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -404,7 +430,7 @@ int tc_rays_per_group(int Dc, int Df) {
 
 template <int MODE>
 static size_t tc_smem_bytes(int R, int S) {
-  return 1024 + sizeof(TcTiles<MODE>) + sizeof(float) * ((size_t)5 * R * S + (size_t)R * 8 + R);
+  return 1024 + sizeof(TcTiles<MODE>) + sizeof(TapEntry) * kTcWarps * 24 + sizeof(float) * ((size_t)5 * R * S + (size_t)R * 8 + R);
 }
 
 typedef void (*TcKernel)(const RenderArgs);

@@ -145,10 +145,28 @@ __device__ __forceinline__ float to_tf32(float x) {          // round-to-nearest
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-// x ~= hi + lo with hi, lo both exactly representable in tf32 (3xTF32 operand split)
+// x ~= hi + lo for the 3xTF32 scheme.  hi is x rounded to tf32 (round-half-up on the bit pattern: two
+// integer ops instead of cvt.rna's four), lo = x - hi is exact in fp32 and is handed to the tensor core
+// as is: the MMA reads only the upper 19 bits of a tf32 operand, so lo carries a relative error
+// <= 2^-10 on a term that is itself <= 2^-11 |x|, i.e. ~2^-21 |x| overall.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = to_tf32(x);
-  lo = to_tf32(x - hi);
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+  lo = x - hi;
+}
+// MUFU wrappers without the denormal range fix-ups __expf/__logf carry (inputs here are O(1))
+__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+// softplus in the log2 domain: input x' = x*log2(e), output softplus(x)/ln(2).  The two constants are
+// folded into W1/b1 and W2, so the activation itself is EX2, FADD, LG2 and the torch threshold select.
+__device__ __forceinline__ float softplus_log2(float xs) {
+  const float y = lg2_fast(1.0f + ex2_fast(xs));
+  return xs > 20.0f * kLog2e ? xs : y;
+}
+// colour activation on a logit pre-multiplied by -log2(e): sigmoid(x)*1.002 - 0.001 (training/triplane.py:134)
+__device__ __forceinline__ float colour_act_neglog2(float zs) {
+  return fmaf(rcp_fast(1.0f + ex2_fast(zs)), 1.002f, -0.001f);
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo_elem, float hi_elem) {   // low 16 bits = lower k
   uint32_t r;
