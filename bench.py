@@ -192,43 +192,27 @@ def main():
     planes_h, c2w_h, K_h = make_inputs(torch, dev, seed=100 + rank)
     decoder = make_decoder(torch, pkg, dev, seed=0)
     renderer, sampler = pkg.ImportanceRenderer(), pkg.RaySampler()
-    renderer.defer_depth_clamp = world > 1
     opts = dict(OPTS, decoder_precision=args.mode)
     planes = planes_h.to(dev)
     origins, dirs = sampler(c2w_h.to(dev), K_h.to(dev), RES)
     m = RES * RES
     samples_per_step = N_IMG * m * (DC + DF)
-    L = pkg._lib.lib()
-    import ctypes
-
-    gathered = None
-    if world > 1:
-        gathered = torch.empty((world, N_IMG, m, 34), device=dev, dtype=torch.float32)
 
     kernel_events = []
 
     def step(record=False):
-        """The hot path as a user calls it, inputs resident in HBM."""
+        """The hot path as a user calls it, inputs resident in HBM.  N > 1: every rank renders its batch into
+        its slice of the gather buffers, the depth range is all-reduced, outputs are all-gathered in place."""
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             renderer._timing_events = (e0, e1)
             kernel_events.append((e0, e1))
-        rgb, depth, wsum = renderer(planes, decoder, origins, dirs, opts)
-        renderer._timing_events = None
         if world > 1:
-            # the one non-local dependency: the global depth min/max (VR/ray_marcher.py:50)
-            rng = renderer.last_depth_range
-            lo, hi = rng[0:1].clone(), rng[1:2].clone()
-            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-            rr = torch.cat([lo, hi])
-            pkg._lib.check(L.tpr_clamp_depth(ctypes.c_void_p(depth.data_ptr()), depth.numel(),
-                                             ctypes.c_void_p(rr.data_ptr()),
-                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'tpr_clamp_depth')
-            mine = gathered[rank]
-            mine[..., :32].copy_(rgb); mine[..., 32:33].copy_(depth); mine[..., 33:34].copy_(wsum)
-            dist.all_gather_into_tensor(gathered.view(-1), mine.reshape(-1))
-        return rgb, depth, wsum
+            out = pkg.parallel.render_sharded(renderer, planes, decoder, origins, dirs, opts)
+        else:
+            out = renderer(planes, decoder, origins, dirs, opts)
+        renderer._timing_events = None
+        return out
 
     def barrier():
         if world > 1:
@@ -264,11 +248,10 @@ def main():
         p = planes_pin.to(dev, non_blocking=True)
         o = o_pin.to(dev, non_blocking=True)
         d = d_pin.to(dev, non_blocking=True)
-        outs = renderer(p, decoder, o, d, opts)
         if world > 1:
-            pkg._lib.check(L.tpr_clamp_depth(ctypes.c_void_p(outs[1].data_ptr()), outs[1].numel(),
-                                             ctypes.c_void_p(renderer.last_depth_range.data_ptr()),
-                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'tpr_clamp_depth')
+            outs = pkg.parallel.render_sharded(renderer, p, decoder, o, d, opts, gather=False)
+        else:
+            outs = renderer(p, decoder, o, d, opts)
         for dst, src in zip(out_pin, outs):
             dst.copy_(src, non_blocking=True)
 

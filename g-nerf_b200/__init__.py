@@ -9,6 +9,7 @@ from .volumetric_rendering import (ImportanceRenderer, RaySampler, MipRayMarcher
 from .triplane import OSGDecoder, FullyConnectedLayer  # noqa: F401
 from .install import install, uninstall  # noqa: F401
 from .build import build  # noqa: F401
+from . import parallel  # noqa: F401
 
 __all__ = ['ImportanceRenderer', 'RaySampler', 'MipRayMarcher2', 'OSGDecoder', 'FullyConnectedLayer',
            'PackedPlanes', 'pack_planes', 'pack_decoder', 'generate_planes', 'install', 'uninstall', 'build']

@@ -133,10 +133,12 @@ class ImportanceRenderer(torch.nn.Module):
         self.defer_depth_clamp = False
 
     # ------------------------------------------------------------------ forward (VR/renderer.py:88-140)
-    def forward(self, planes, decoder, ray_origins, ray_directions, rendering_options, *, noise=None):
+    def forward(self, planes, decoder, ray_origins, ray_directions, rendering_options, *, noise=None, out=None):
         """``noise=(jitter [N,M,Dc,1], u [N*M,Df])`` overrides the two uniform draws (used by parity
         tests, which must feed the oracle and the kernels the same numbers); by default they are drawn
-        with the reference's own torch calls in the reference's order (VR/renderer.py:190,237)."""
+        with the reference's own torch calls in the reference's order (VR/renderer.py:190,237).
+        ``out=(rgb, depth, weight_sum)`` renders into caller-owned contiguous tensors (the multi-GPU path
+        passes slices of its all-gather buffers)."""
         opts = rendering_options
         ray_origins = _require_cuda_f32(ray_origins, 'ray_origins', (3,))
         ray_directions = _require_cuda_f32(ray_directions, 'ray_directions', (3,))
@@ -182,9 +184,15 @@ class ImportanceRenderer(torch.nn.Module):
                                 disparity_space_sampling=int(bool(opts.get('disparity_space_sampling', False))),
                                 white_back=int(bool(opts.get('white_back', False))), flags=_mlp_flag(opts),
                                 tile_width=0)
-            rgb = torch.empty((n, m, 32), device=dev, dtype=torch.float32)
-            depth = torch.empty((n, m, 1), device=dev, dtype=torch.float32)
-            wsum = torch.empty((n, m, 1), device=dev, dtype=torch.float32)
+            if out is None:
+                rgb = torch.empty((n, m, 32), device=dev, dtype=torch.float32)
+                depth = torch.empty((n, m, 1), device=dev, dtype=torch.float32)
+                wsum = torch.empty((n, m, 1), device=dev, dtype=torch.float32)
+            else:
+                rgb, depth, wsum = out
+                for t, c in ((rgb, 32), (depth, 1), (wsum, 1)):
+                    if (tuple(t.shape) != (n, m, c) or t.dtype != torch.float32 or t.device != dev or not t.is_contiguous()):
+                        raise RuntimeError(f'out tensors must be contiguous float32 [{n},{m},{c}] on {dev}')
             rng = torch.empty(2, device=dev, dtype=torch.float32)
             nscratch = L.tpr_render_scratch_bytes(n, m, ctypes.byref(o))
             scratch = torch.empty(nscratch, device=dev, dtype=torch.uint8)
