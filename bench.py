@@ -112,7 +112,7 @@ def cpu_baseline(sample_res, repeats=1):
     scene = O.synthetic_scene(3, 1, sample_res, PLANE_RES, DC, DF)
     n_samples = sample_res * sample_res * (DC + DF)
     if have_c:
-        cores = c_oracle.num_threads()
+        cores = c_oracle.use_all_cores()
         c_oracle.render(scene, dict(O.FFHQ_OPTIONS))          # warm-up (page-in, thread pool)
         t0 = time.perf_counter()
         for _ in range(repeats):

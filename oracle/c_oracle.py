@@ -36,6 +36,13 @@ def num_threads() -> int:
     return int(_load().oracle_num_threads())
 
 
+def use_all_cores() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline is supposed to use every host core it may."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    _load().oracle_set_num_threads(int(n))
+    return num_threads()
+
+
 def render(scene: dict, opts: dict, want_stages: bool = False):
     """scene as produced by triplane_oracle.synthetic_scene; returns (rgb, depth, wsum[, stages])."""
     lib = _load()
