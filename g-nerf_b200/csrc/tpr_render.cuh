@@ -16,6 +16,8 @@ struct RenderArgs {
   int Dc, Df, disparity, white_back, R;
   float* rgb; float* depth; float* wsum; float* fine_depths; int* fine_inds;
   unsigned* range_enc;                   // [2]: ordered-uint encoded (min, max) of all depths
+  int col_w;                             // > 0: rays form an image col_w pixels wide and a group is R rays of one image COLUMN
+  long long* dbg;                        // optional [16] per-phase cycle counters of CTA 0 (TPR_PHASE_TIMING=1)
 };
 
 constexpr int kRenderMaxThreads = 512;

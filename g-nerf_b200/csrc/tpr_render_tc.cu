@@ -27,8 +27,9 @@
 namespace tpr {
 using namespace tc;
 
-constexpr int kTcThreads = 512;
-constexpr int kTcWarps = kTcThreads / 32;
+constexpr int kTcWorkers = 512;                  // 16 worker warps: gather, activations, per-ray phases
+constexpr int kTcWarps = kTcWorkers / 32;
+constexpr int kTcThreads = kTcWorkers + 32;      // + one warp that only issues tcgen05.mma
 constexpr int kRows = 128;
 constexpr int kN1 = 64, kN2 = 48;
 // TMEM column map (512 columns allocated)
@@ -230,6 +231,14 @@ __device__ __forceinline__ void tc_epilogue1(uint32_t tmem) {
   tmem_wait_st();
 }
 
+// mbarriers shared by the worker warps and the MMA warp
+struct TcBarriers {
+  uint64_t a1_full[2];     // 16 worker arrivals: A1[b] gathered (and published to the async proxy)
+  uint64_t d1_full;        // tcgen05.commit: layer 1 of the current tile is in TMEM
+  uint64_t a2_full;        // 16 worker arrivals: activations written back to TMEM
+  uint64_t m2_done;        // tcgen05.commit: layer 2 of the current tile has consumed A2 / filled its slot
+};
+
 template <int MODE, int E>
 __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -244,16 +253,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderAr
   TcRaySmem rs;
   rs.dep = fl; rs.sig = rs.dep + R * S; rs.wa = rs.sig + R * S; rs.wb = rs.wa + R * S; rs.wc = rs.wb + R * S;
   rs.ray = rs.wc + R * S; rs.rayw = rs.ray + R * 8;
-  __shared__ uint64_t bar1, bar2;
+  __shared__ TcBarriers bars;
   __shared__ uint32_t tmem_base_sm;
   __shared__ unsigned range_sm[2];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, j = warp >> 2;
+  const int q = warp & 3, j = (warp >> 2) & 3;
   const uint32_t lane_base = (uint32_t)(q * 32) << 16;
 
   if (tid == 0) {
     range_sm[0] = 0xffffffffu; range_sm[1] = 0u;
-    mbar_init(&bar1, 1); mbar_init(&bar2, 1); fence_mbar_init();
+    mbar_init(&bars.a1_full[0], kTcWarps); mbar_init(&bars.a1_full[1], kTcWarps);
+    mbar_init(&bars.d1_full, 1); mbar_init(&bars.a2_full, kTcWarps); mbar_init(&bars.m2_done, 1);
+    fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(&tmem_base_sm, 512); tmem_relinquish(); }
   tc_stage_weights<MODE>(a.dec, tl);
@@ -262,7 +273,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderAr
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_base_sm;
-  if (j == 0) {                                 // the ones block (A operand of the bias MMAs): k0 = k1 = 1
+  if (warp < 4) {                               // the ones block (A operand of the bias MMAs): k0 = k1 = 1
     uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (MODE == 1) v[0] = 0x3f803f80u; else { v[0] = 0x3f800000u; v[1] = 0x3f800000u; }
     tmem_st8(tmem + kColOnes + lane_base, v);
@@ -271,149 +282,194 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderAr
   tcgen05_fence_before();
   __syncthreads();
 
-  uint32_t p1 = 0, p2 = 0;                      // mbarrier phase parities
-  const bool per_ray = a.rs != nullptr;
-  const size_t img_stride = (size_t)3 * a.H * a.W * kC;
   const int nsl_c = (Dc + dpt - 1) >> dpt_shift, nsl_f = (Df + dpt - 1) >> dpt_shift;
-  float mn = __int_as_float(0x7f800000), mx = -__int_as_float(0x7f800000);
+  const int n_pass = Df > 0 ? 2 : 1;
 
-  for (long long grp = blockIdx.x; grp < a.n_tiles; grp += gridDim.x) {
-    const long long n = grp / a.tiles_per_img;
-    const long long m0 = (grp - n * a.tiles_per_img) * R;
-    const long long g0 = n * a.rays_per_img + m0;
-    const int nr = (int)min((long long)R, a.rays_per_img - m0);
-    const float* img = a.planes + (size_t)n * img_stride;
-    // ---- rays + coarse depths
-    if (tid < nr * 6) {
-      const int r = tid / 6, c = tid - r * 6;
-      const long long g = g0 + r;
-      rs.ray[r * 8 + c] = c < 3 ? a.origins[g * 3 + c] : a.dirs[g * 3 + c - 3];
-      if (c == 0) {
-        rs.ray[r * 8 + 6] = per_ray ? a.rs[g] : a.ray_start;
-        rs.ray[r * 8 + 7] = per_ray ? a.re[g] : a.ray_end;
-      }
-    }
-    __syncthreads();
-    for (int s = tid; s < nr * Dc; s += kTcThreads) {
-      const int r = s / Dc, k = s - r * Dc;
-      rs.dep[r * S + k] = coarse_depth(a, k, __ldg(a.jitter + g0 * Dc + s), rs.ray[r * 8 + 6], rs.ray[r * 8 + 7], per_ray);
-    }
-    __syncthreads();
-
-    const int n_pass = Df > 0 ? 2 : 1;
+  if (warp == kTcWarps) {
+    // =========================== MMA warp: waits for operands, issues, commits ===========================
+    uint32_t pa[2] = {0, 0}, pa2 = 0;
+    tcgen05_fence_after();
+    for (long long grp = blockIdx.x; grp < a.n_tiles; grp += gridDim.x) {
 #pragma unroll 1
-    for (int pass = 0; pass < n_pass; ++pass) {
-      const int Dx = pass == 0 ? Dc : Df, off = pass == 0 ? 0 : Dc;
-      const int T = pass == 0 ? nsl_c : nsl_f, slot0 = pass == 0 ? 0 : nsl_c;
-      if (pass == 1) {
-        // ---- importance resampling, one warp per ray
-        for (int r = warp; r < nr; r += kTcWarps)
-          warp_resample_ray(a, rs.dep + r * S, rs.sig + r * S, rs.wa + r * S, rs.wb + r * S, rs.wc + r * S,
-                            rs.dep + r * S + Dc, g0 + r, lane);
-        __syncthreads();
-      }
-      // ---- tile pipeline
-      tc_gather_tile<MODE>(a, tl, 0, img, rs, taps, nr, Dx, off, S, 0, dpt_shift);
-      fence_proxy_async_smem();
-      __syncthreads();
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const int T = pass == 0 ? nsl_c : nsl_f, slot0 = pass == 0 ? 0 : nsl_c;
 #pragma unroll 1
-      for (int t = 0; t < T; ++t) {
-        if (tid == 0) {
+        for (int t = 0; t < T; ++t) {
+          const int b = t & 1;
+          mbar_wait(&bars.a1_full[b], pa[b]); pa[b] ^= 1;
           tcgen05_fence_after();
-          tc_issue_layer1<MODE>(tl, t & 1, tmem);
-          mma_commit(&bar1);
+          if (elect_one_sync()) {
+            tc_issue_layer1<MODE>(tl, b, tmem);
+            mma_commit(&bars.d1_full);
+          }
+          __syncwarp();
+          mbar_wait(&bars.a2_full, pa2); pa2 ^= 1;
+          tcgen05_fence_after();
+          if (elect_one_sync()) {
+            tc_issue_layer2<MODE>(tl, tmem, slot0 + t);
+            mma_commit(&bars.m2_done);
+          }
+          __syncwarp();
         }
-        if (t + 1 < T) {
-          tc_gather_tile<MODE>(a, tl, (t + 1) & 1, img, rs, taps, nr, Dx, off, S, t + 1, dpt_shift);
-          fence_proxy_async_smem();
+      }
+    }
+  } else {
+    // =========================== worker warps ===========================
+    uint32_t pd1 = 0, pm2 = 0;                    // mbarrier phase parities
+    const bool per_ray = a.rs != nullptr;
+    const size_t img_stride = (size_t)3 * a.H * a.W * kC;
+    float mn = __int_as_float(0x7f800000), mx = -__int_as_float(0x7f800000);
+    long long tprev = clock64();
+#define TPR_MARK(i) do { if (a.dbg != nullptr && blockIdx.x == 0 && tid == 0) { long long now_ = clock64(); a.dbg[i] += now_ - tprev; tprev = now_; } } while (0)
+#define WORKER_SYNC() named_bar_sync(1, kTcWorkers)
+
+    for (long long grp = blockIdx.x; grp < a.n_tiles; grp += gridDim.x) {
+      const long long n = grp / a.tiles_per_img;
+      const long long gi = grp - n * a.tiles_per_img;
+      // Which rays form the group.  Column mode (rays are a col_w-wide image, x fastest, VR/ray_sampler.py:44):
+      // R vertically adjacent pixels of one image column -- they share their (x,z) footprint, i.e. their taps on
+      // two of the three planes (plane 1 and 2 are both functions of (x,z), VR/renderer.py:29-37), which cuts the
+      // L2->L1 traffic of the gather several-fold.  Otherwise R consecutive rays.
+      const bool colm = a.col_w > 0;
+      const long long ray0 = n * a.rays_per_img + (colm ? (gi / a.col_w) * R * a.col_w + gi % a.col_w : gi * R);
+      const long long rstride = colm ? a.col_w : 1;
+      const int nr = colm ? R : (int)min((long long)R, a.rays_per_img - gi * R);
+#define RAY_G(r) (ray0 + (long long)(r) * rstride)
+      const float* img = a.planes + (size_t)n * img_stride;
+      // ---- rays + coarse depths
+      if (tid < nr * 6) {
+        const int r = tid / 6, c = tid - r * 6;
+        const long long g = RAY_G(r);
+        rs.ray[r * 8 + c] = c < 3 ? a.origins[g * 3 + c] : a.dirs[g * 3 + c - 3];
+        if (c == 0) {
+          rs.ray[r * 8 + 6] = per_ray ? a.rs[g] : a.ray_start;
+          rs.ray[r * 8 + 7] = per_ray ? a.re[g] : a.ray_end;
         }
-        mbar_wait(&bar1, p1); p1 ^= 1;
-        if (t > 0) { mbar_wait(&bar2, p2); p2 ^= 1; }      // layer 2 of the previous tile has consumed A2
+      }
+      WORKER_SYNC();
+      for (int s = tid; s < nr * Dc; s += kTcWorkers) {
+        const int r = s / Dc, k = s - r * Dc;
+        rs.dep[r * S + k] = coarse_depth(a, k, __ldg(a.jitter + RAY_G(r) * Dc + k), rs.ray[r * 8 + 6], rs.ray[r * 8 + 7], per_ray);
+      }
+      WORKER_SYNC();
+      TPR_MARK(0);
+
+#pragma unroll 1
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const int Dx = pass == 0 ? Dc : Df, off = pass == 0 ? 0 : Dc;
+        const int T = pass == 0 ? nsl_c : nsl_f, slot0 = pass == 0 ? 0 : nsl_c;
+        if (pass == 1) {
+          // ---- importance resampling, one warp per ray
+          for (int r = warp; r < nr; r += kTcWarps)
+            warp_resample_ray(a, rs.dep + r * S, rs.sig + r * S, rs.wa + r * S, rs.wb + r * S, rs.wc + r * S,
+                              rs.dep + r * S + Dc, RAY_G(r), lane);
+          WORKER_SYNC();
+          TPR_MARK(8);
+        }
+        // ---- tile pipeline
+        tc_gather_tile<MODE>(a, tl, 0, img, rs, taps, nr, Dx, off, S, 0, dpt_shift);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.a1_full[0]);
+        TPR_MARK(1);
+#pragma unroll 1
+        for (int t = 0; t < T; ++t) {
+          if (t + 1 < T) {
+            tc_gather_tile<MODE>(a, tl, (t + 1) & 1, img, rs, taps, nr, Dx, off, S, t + 1, dpt_shift);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars.a1_full[(t + 1) & 1]);
+          }
+          TPR_MARK(3);
+          mbar_wait(&bars.d1_full, pd1); pd1 ^= 1;
+          if (t > 0) { mbar_wait(&bars.m2_done, pm2); pm2 ^= 1; }   // layer 2 of the previous tile has consumed A2
+          tcgen05_fence_after();
+          TPR_MARK(4);
+          tc_epilogue1<MODE>(tmem);
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.a2_full);
+          TPR_MARK(5);
+        }
+        mbar_wait(&bars.m2_done, pm2); pm2 ^= 1;
         tcgen05_fence_after();
-        tc_epilogue1<MODE>(tmem);
+        // ---- sigma = column 0 of every slot of this pass
+        for (int sl = j; sl < T; sl += 4) {
+          const float sg = __uint_as_float(tmem_ld1(tmem + kColSlots + (slot0 + sl) * kSlotCols + lane_base));
+          tmem_wait_ld();
+          const int row = q * 32 + lane, r = row >> dpt_shift, di = sl * dpt + (row & (dpt - 1));
+          if (r < nr && di < Dx) rs.sig[r * S + off + di] = sg;
+        }
         tcgen05_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-          tcgen05_fence_after();
-          tc_issue_layer2<MODE>(tl, tmem, slot0 + t);
-          mma_commit(&bar2);
+        WORKER_SYNC();
+        TPR_MARK(7);
+      }
+      // ---- sort + final march: omega per sample (scattered to original order), depth, weight sum
+      for (int r = warp; r < nr; r += kTcWarps) {
+        float wsum, dnum;
+        warp_sort_and_weights<E, true>(rs.dep + r * S, rs.sig + r * S, rs.wa + r * S, nullptr, S, lane, wsum, dnum, mn, mx);
+        if (lane == 0) {
+          rs.rayw[r] = wsum;
+          a.depth[RAY_G(r)] = dnum / wsum;            // NaN -> inf and the clamp happen in finish_kernel
+          a.wsum[RAY_G(r)] = wsum;
         }
       }
-      mbar_wait(&bar2, p2); p2 ^= 1;
-      tcgen05_fence_after();
-      // ---- sigma = column 0 of every slot of this pass
-      for (int sl = j; sl < T; sl += 4) {
-        const float sg = __uint_as_float(tmem_ld1(tmem + kColSlots + (slot0 + sl) * kSlotCols + lane_base));
-        tmem_wait_ld();
-        const int row = q * 32 + lane, r = row >> dpt_shift, di = sl * dpt + (row & (dpt - 1));
-        if (r < nr && di < Dx) rs.sig[r * S + off + di] = sg;
-      }
-      tcgen05_fence_before();
-      __syncthreads();
-    }
-    // ---- sort + final march: omega per sample (scattered to original order), depth, weight sum
-    for (int r = warp; r < nr; r += kTcWarps) {
-      float wsum, dnum;
-      warp_sort_and_weights<E, true>(rs.dep + r * S, rs.sig + r * S, rs.wa + r * S, nullptr, S, lane, wsum, dnum, mn, mx);
-      if (lane == 0) {
-        rs.rayw[r] = wsum;
-        a.depth[g0 + r] = dnum / wsum;              // NaN -> inf and the clamp happen in finish_kernel
-        a.wsum[g0 + r] = wsum;
-      }
-    }
-    __syncthreads();
-    // ---- composite: warp (q, j) sums channels [8j, 8j+8) over the samples held by its lanes
-    {
-      tcgen05_fence_after();
-      const int row = q * 32 + lane, r = row >> dpt_shift, i = row & (dpt - 1);
-      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      const int nsl = nsl_c + (Df > 0 ? nsl_f : 0);
+      WORKER_SYNC();
+      TPR_MARK(9);
+      // ---- composite: warp (q, j) sums channels [8j, 8j+8) over the samples held by its lanes
+      {
+        tcgen05_fence_after();
+        const int row = q * 32 + lane, r = row >> dpt_shift, i = row & (dpt - 1);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const int nsl = nsl_c + (Df > 0 ? nsl_f : 0);
 #pragma unroll 1
-      for (int sl = 0; sl < nsl; ++sl) {
-        const bool fine = sl >= nsl_c;
-        const int di = (fine ? sl - nsl_c : sl) * dpt + i;
-        const bool valid = r < nr && di < (fine ? Df : Dc);
-        const float om = valid ? rs.wa[r * S + (fine ? Dc : 0) + di] : 0.0f;
-        uint32_t v[8];
-        tmem_ld8(tmem + kColSlots + sl * kSlotCols + lane_base + 1 + 8 * j, v);
-        tmem_wait_ld();
+        for (int sl = 0; sl < nsl; ++sl) {
+          const bool fine = sl >= nsl_c;
+          const int di = (fine ? sl - nsl_c : sl) * dpt + i;
+          const bool valid = r < nr && di < (fine ? Df : Dc);
+          const float om = valid ? rs.wa[r * S + (fine ? Dc : 0) + di] : 0.0f;
+          uint32_t v[8];
+          tmem_ld8(tmem + kColSlots + sl * kSlotCols + lane_base + 1 + 8 * j, v);
+          tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] = valid ? fmaf(om, colour_act_neglog2(__uint_as_float(v[c])), acc[c]) : acc[c];
-      }
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        if (o < dpt) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(kFull, acc[c], o);
+          for (int c = 0; c < 8; ++c) acc[c] = valid ? fmaf(om, colour_act_neglog2(__uint_as_float(v[c])), acc[c]) : acc[c];
         }
-      }
-      if (i == 0 && r < nr) {
-        const float ws = rs.rayw[r];
-        float o8[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float v = acc[c];
-          if (a.white_back) v = v + 1.0f - ws;         // VR/ray_marcher.py:52-53
-          o8[c] = v * 2.0f - 1.0f;                     // :55
+        for (int o = 1; o < 32; o <<= 1) {
+          if (o < dpt) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(kFull, acc[c], o);
+          }
         }
-        float4* dst = reinterpret_cast<float4*>(a.rgb + (g0 + r) * kC + 8 * j);
-        dst[0] = make_float4(o8[0], o8[1], o8[2], o8[3]);
-        dst[1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
+        if (i == 0 && r < nr) {
+          const float ws = rs.rayw[r];
+          float o8[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float v = acc[c];
+            if (a.white_back) v = v + 1.0f - ws;         // VR/ray_marcher.py:52-53
+            o8[c] = v * 2.0f - 1.0f;                     // :55
+          }
+          float4* dst = reinterpret_cast<float4*>(a.rgb + RAY_G(r) * kC + 8 * j);
+          dst[0] = make_float4(o8[0], o8[1], o8[2], o8[3]);
+          dst[1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
+        }
+        tcgen05_fence_before();
       }
-      tcgen05_fence_before();
+      WORKER_SYNC();                                     // slots, ray arrays free for the next group
+      TPR_MARK(10);
     }
-    __syncthreads();                                   // slots, ray arrays free for the next group
-  }
-  if (lane == 0 && mn <= mx) {
-    atomicMin(&range_sm[0], float_to_ordered(mn));
-    atomicMax(&range_sm[1], float_to_ordered(mx));
+    if (lane == 0 && mn <= mx) {
+      atomicMin(&range_sm[0], float_to_ordered(mn));
+      atomicMax(&range_sm[1], float_to_ordered(mx));
+    }
   }
   __syncthreads();
   if (tid == 0 && range_sm[0] <= range_sm[1]) {
     atomicMin(a.range_enc + 0, range_sm[0]);
     atomicMax(a.range_enc + 1, range_sm[1]);
   }
-  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (warp == 0) { tcgen05_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 // ---- host-side selection ---------------------------------------------------------------------
@@ -443,6 +499,7 @@ static TcKernel pick_kernel(int S) {
 int launch_render_tc(RenderArgs a, int bf16, int sms, int smem_optin, long long n_img, long long n_rays, cudaStream_t st) {
   const int S = a.Dc + a.Df;
   a.R = tc_rays_per_group(a.Dc, a.Df);
+  if (a.col_w > 0 && (a.col_w % a.R != 0 || (long long)a.col_w * a.col_w != n_rays)) a.col_w = 0;
   a.tiles_per_img = (n_rays + a.R - 1) / a.R;
   a.n_tiles = a.tiles_per_img * n_img;
   TcKernel k = bf16 ? pick_kernel<1>(S) : pick_kernel<0>(S);

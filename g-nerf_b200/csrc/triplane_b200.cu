@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(kRenderMaxThreads, 1) render_kernel(const Rend
 
 __global__ void range_init_kernel(unsigned* enc) {
   enc[0] = 0xffffffffu; enc[1] = 0u;
+  for (int i = 0; i < 16; ++i) reinterpret_cast<long long*>(reinterpret_cast<char*>(enc) + 64)[i] = 0;   // phase counters
 }
 
 // decode the (min,max) and optionally apply nan_to_num(inf) + clamp (VR/ray_marcher.py:49-50)
@@ -675,6 +676,15 @@ int tpr_render(const float* planes_packed, int64_t n_img, int32_t height, int32_
   a.Dc = Dc; a.Df = Df; a.disparity = opt->disparity_space_sampling; a.white_back = opt->white_back;
   a.rgb = rgb; a.depth = depth; a.wsum = weight_sum; a.fine_depths = fine_depths; a.fine_inds = fine_inds;
   a.range_enc = reinterpret_cast<unsigned*>(scratch);
+  {
+    // column grouping needs the rays to be a square image with x fastest (what RaySampler produces); the caller
+    // can say so through tile_width, otherwise it is inferred from a perfect-square ray count
+    int w = opt->tile_width;
+    if (w == 0) { w = (int)llround(sqrt((double)n_rays)); if ((long long)w * w != n_rays) w = 0; }
+    if (w < 0 || env_int("TPR_NO_COLUMN_TILES", 0)) w = 0;
+    a.col_w = w;
+  }
+  a.dbg = env_int("TPR_PHASE_TIMING", 0) ? reinterpret_cast<long long*>(reinterpret_cast<char*>(scratch) + 64) : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   range_init_kernel<<<1, 1, 0, st>>>(a.range_enc);
   TPR_CHECK_LAUNCH("range_init_kernel");

@@ -211,6 +211,7 @@ class ImportanceRenderer(torch.nn.Module):
             if ev is not None:
                 ev[1].record()
         self.last_depth_range = rng
+        self.last_scratch = scratch                    # TPR_PHASE_TIMING=1: int64 phase counters at byte 64
         self.last_fine = (fine_d, fine_i)
         return rgb, depth, wsum
 

@@ -67,7 +67,8 @@ typedef struct TprOptions {
   int32_t disparity_space_sampling;    /* VR/renderer.py:174-181 */
   int32_t white_back;            /* VR/ray_marcher.py:52-53 */
   int32_t flags;                 /* TPR_MLP_* */
-  int32_t tile_width;            /* perf hint only: rays form an image this many pixels wide (0 = unknown) */
+  int32_t tile_width;            /* perf hint only, never changes results: rays form a square image this many pixels
+                                    wide with x fastest (0 = infer from a perfect-square ray count, < 0 = no image) */
   int32_t reserved[5];
 } TprOptions;
 
