@@ -158,6 +158,19 @@ int tpr_sample_pdf(const float* bins, int32_t bins_stride, const float* weights,
 int tpr_ray_limits_box(const float* origins, const float* dirs, int64_t n_rays,
                        float box_side_length, float* t_min, float* t_max, void* stream);
 
+/* ---- measurement aid: the gather roofline ------------------------- */
+/* Fetches random 128-byte lines of buf[n_lines*32 floats] with the render kernels' access shape (8 lanes x
+ * 16 bytes per line, 12 lines in flight per thread) from `ctas` CTAs of 512 threads, `iters` rounds each.
+ * sink: 65536 floats.  Returns the number of lines fetched (> 0) or a negative error.  The caller times
+ * it with CUDA events; lines * 128 B / time is the L2 (small buffer) or DRAM (large buffer) gather bandwidth
+ * bench.py reports beside the HBM copy peak. */
+int64_t tpr_gather_microbench(const float* buf, int64_t n_lines, int32_t ctas, int32_t iters, float* sink,
+                              void* stream);
+/* same with the CTA size (multiple of 32, <= 1024) and the lines in flight per thread (4, 6, 12 or 24) chosen
+ * by the caller; sink: 65536 floats */
+int64_t tpr_gather_microbench_ex(const float* buf, int64_t n_lines, int32_t ctas, int32_t threads,
+                                 int32_t in_flight, int32_t iters, float* sink, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
