@@ -40,6 +40,7 @@ _SIGNATURES = {
     'tpr_sample_pdf': (ctypes.c_int, [_P, c_int32, _P, _P, c_int64, c_int32, c_int32, _P, _P, _P]),
     'tpr_ray_limits_box': (ctypes.c_int, [_P, _P, c_int64, c_float, _P, _P, _P]),
     'tpr_gather_microbench': (c_int64, [_P, c_int64, c_int32, c_int32, _P, _P]),
+    'tpr_mma_microbench': (ctypes.c_int, [c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     'tpr_gather_microbench_ex': (c_int64, [_P, c_int64, c_int32, c_int32, c_int32, c_int32, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

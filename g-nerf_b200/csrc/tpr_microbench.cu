@@ -61,3 +61,89 @@ extern "C" int64_t tpr_gather_microbench_ex(const float* buf, int64_t n_lines, i
   if (e != cudaSuccess) return -(int64_t)e - 1000;
   return (int64_t)ctas * (threads / 8) * in_flight * iters;          // lines fetched
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// tcgen05.mma cost for the small shapes of the decoder: `count` back-to-back MMAs of M = 128, N = n, one K step
+// each (tf32: K = 8, bf16: K = 16), A from shared memory (SS) or TMEM (TS), issued by one thread.  Reports
+// cycles from the first issue to the commit's arrival, and the issue-only cycles.
+// ---------------------------------------------------------------------------------------------------------
+#include "tpr_tc.cuh"
+namespace tpr {
+using namespace tc;
+__global__ void __launch_bounds__(128, 1) mma_bench_kernel(int n, int bf16, int ts, int count, int layout, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* a_tile = reinterpret_cast<float*>(base);                 // 128 rows x 128 B
+  float* b_tile = reinterpret_cast<float*>(base + 16384);         // up to 256 rows x 128 B
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_sm;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<float*>(base)[i] = 0.0f;
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(&tmem_base_sm, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_base_sm;
+  if (warp == 0) {
+    const uint32_t idesc = instr_desc(bf16 ? kFmtBF16 : kFmtTF32, 128, n);
+    const uint32_t d = tmem + 256;
+    const uint64_t a0 = smem_desc_sw128(smem_u32(a_tile), 0), b0 = smem_desc_sw128(smem_u32(b_tile), 0);
+    long long t0 = 0, t1 = 0, t2 = 0;
+    if (elect_one_sync()) {
+      t0 = clock64();
+      if (layout == 0) {
+        // as the render kernels issue them: descriptors rebuilt per MMA
+        for (int i = 0; i < count; ++i) {
+          const uint32_t koff = (i & 3) * 32;
+          if (ts) {
+            if (bf16) mma_f16_ts(d, tmem + (i & 3) * 8, smem_desc_sw128(smem_u32(b_tile), koff), idesc, true);
+            else mma_tf32_ts(d, tmem + (i & 3) * 8, smem_desc_sw128(smem_u32(b_tile), koff), idesc, true);
+          } else {
+            if (bf16) mma_f16_ss(d, smem_desc_sw128(smem_u32(a_tile), koff), smem_desc_sw128(smem_u32(b_tile), koff), idesc, true);
+            else mma_tf32_ss(d, smem_desc_sw128(smem_u32(a_tile), koff), smem_desc_sw128(smem_u32(b_tile), koff), idesc, true);
+          }
+        }
+      } else {
+        // tight: precomputed descriptors, four K steps unrolled with constant increments (+2 = 32 bytes)
+        if (ts) {
+          for (int i = 0; i < count; i += 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (bf16) mma_f16_ts(d, tmem + k * 8, b0 + 2 * k, idesc, true);
+              else mma_tf32_ts(d, tmem + k * 8, b0 + 2 * k, idesc, true);
+            }
+          }
+        } else {
+          for (int i = 0; i < count; i += 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (bf16) mma_f16_ss(d, a0 + 2 * k, b0 + 2 * k, idesc, true);
+              else mma_tf32_ss(d, a0 + 2 * k, b0 + 2 * k, idesc, true);
+            }
+          }
+        }
+      }
+      t1 = clock64();
+      mma_commit(&bar);
+      mbar_wait(&bar, 0);
+      t2 = clock64();
+      out[0] = t1 - t0; out[1] = t2 - t0;
+    }
+    __syncwarp();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) { tcgen05_fence_after(); tmem_dealloc(tmem, 512); }
+}
+}  // namespace tpr
+
+extern "C" int tpr_mma_microbench(int32_t n, int32_t bf16, int32_t ts, int32_t count, int32_t tight, long long* out_dev, void* stream) {
+  if (!out_dev || n < 16 || n > 256 || (n & 15) || count <= 0) return TPR_E_SHAPE;
+  const int smem = 1024 + 16384 + 32768;
+  cudaError_t e = cudaFuncSetAttribute(tpr::mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;
+  tpr::mma_bench_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(n, bf16, ts, count, tight, out_dev);
+  return (int)cudaGetLastError();
+}

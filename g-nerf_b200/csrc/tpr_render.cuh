@@ -16,6 +16,7 @@ struct RenderArgs {
   int Dc, Df, disparity, white_back, R;
   float* rgb; float* depth; float* wsum; float* fine_depths; int* fine_inds;
   unsigned* range_enc;                   // [2]: ordered-uint encoded (min, max) of all depths
+  int variant;                           // debug: A/B switches (TPR_WS_VARIANT)
   int col_w;                             // > 0: rays form an image col_w pixels wide and a group is R rays of one image COLUMN
   long long* dbg;                        // optional [16] per-phase cycle counters of CTA 0 (TPR_PHASE_TIMING=1)
 };
@@ -54,27 +55,80 @@ __device__ __forceinline__ float coarse_depth(const RenderArgs& a, int k, float 
 // kScatter = false: om[p], oi[p] by sorted position p (oi = original index);
 // kScatter = true : om[original index] = omega (oi unused).
 // Also returns sum(w), sum(w * mid depth) and folds the ray's depth range into (mn, mx).
+// Sorting: with `tmp` (2*S floats of scratch; `om` serves as a third scratch row) each lane counts, for its elements,
+// how many of the ray's S depths are smaller -- S warp-broadcast shared-memory reads and S*E independent compares,
+// no shuffles, so it overlaps with itself far better than the bitonic network's dependent compare-exchange chain
+// (the ray warps are latency bound) -- and scatters (depth, sigma, index) to that rank.  Two equal depths would
+// get the same rank; a rank-sum check detects that and falls back to the network with its index tie-break.
 template <int E, bool kScatter>
 __device__ __forceinline__ void warp_sort_and_weights(const float* z, const float* sg, float* om, int* oi, int S, int lane,
-                                                      float& wsum_out, float& dnum_out, float& mn, float& mx) {
+                                                      float& wsum_out, float& dnum_out, float& mn, float& mx,
+                                                      float* tmp = nullptr) {
   float key[E]; int idx[E];
-  bool sorted = true;
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    int p = lane * E + e;
-    key[e] = p < S ? z[p] : __int_as_float(0x7f800000);
-    idx[e] = p;
-    if (e > 0) sorted &= !(key[e] < key[e - 1]);
-  }
-  {
-    float prev = __shfl_up_sync(kFull, key[E - 1], 1);
-    if (lane > 0) sorted &= !(key[0] < prev);
-  }
-  if (!__all_sync(kFull, sorted)) warp_bitonic_sort<E>(key, idx, lane);
-  // sorted, blocked: position p = lane*E + e
   float sgm[E];
+  bool ranked = false;
+  if (tmp != nullptr) {
+    // element p = e*32 + lane (strided: conflict-free reads and writes)
+    float ze[E]; int cnt[E];
 #pragma unroll
-  for (int e = 0; e < E; ++e) sgm[e] = (lane * E + e) < S ? sg[idx[e]] : 0.0f;
+    for (int e = 0; e < E; ++e) { const int p = e * 32 + lane; ze[e] = p < S ? z[p] : __int_as_float(0x7f800000); cnt[e] = 0; }
+    int j = 0;
+    if ((reinterpret_cast<uintptr_t>(z) & 15) == 0) {
+#pragma unroll 2
+      for (; j + 4 <= S; j += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(z + j);
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+          cnt[e] += (int)(v.x < ze[e]) + (int)(v.y < ze[e]) + (int)(v.z < ze[e]) + (int)(v.w < ze[e]);
+      }
+    }
+    for (; j < S; ++j) {
+      const float v = z[j];
+#pragma unroll
+      for (int e = 0; e < E; ++e) cnt[e] += (int)(v < ze[e]);
+    }
+    int rsum = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) if (e * 32 + lane < S) rsum += cnt[e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(kFull, rsum, o);
+    ranked = rsum == S * (S - 1) / 2;            // a tie (or a NaN) makes the sum fall short
+    if (ranked) {
+      float* zs = tmp; float* ss = tmp + S; int* is = reinterpret_cast<int*>(om);
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int p = e * 32 + lane;
+        if (p < S) { zs[cnt[e]] = ze[e]; ss[cnt[e]] = sg[p]; is[cnt[e]] = p; }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int p = lane * E + e;
+        key[e] = p < S ? zs[p] : __int_as_float(0x7f800000);
+        sgm[e] = p < S ? ss[p] : 0.0f;
+        idx[e] = p < S ? is[p] : p;
+      }
+      __syncwarp();                              // `om` is rewritten below
+    }
+  }
+  if (!ranked) {
+    bool sorted = true;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      int p = lane * E + e;
+      key[e] = p < S ? z[p] : __int_as_float(0x7f800000);
+      idx[e] = p;
+      if (e > 0) sorted &= !(key[e] < key[e - 1]);
+    }
+    {
+      float prev = __shfl_up_sync(kFull, key[E - 1], 1);
+      if (lane > 0) sorted &= !(key[0] < prev);
+    }
+    if (!__all_sync(kFull, sorted)) warp_bitonic_sort<E>(key, idx, lane);
+    // sorted, blocked: position p = lane*E + e
+#pragma unroll
+    for (int e = 0; e < E; ++e) sgm[e] = (lane * E + e) < S ? sg[idx[e]] : 0.0f;
+  }
   const float nk = __shfl_down_sync(kFull, key[0], 1), ns = __shfl_down_sync(kFull, sgm[0], 1);
   float al[E], dm[E];
   float prod = 1.0f;
@@ -120,9 +174,10 @@ __device__ __forceinline__ void warp_sort_and_weights(const float* z, const floa
 }
 
 // one warp: coarse weights -> smoothed pdf -> CDF -> Df inverse-CDF draws (VR/renderer.py:194-253).
-// z, sg: the ray's coarse depths / densities (S-strided row); w, pw, cdf: scratch rows; fine: output row.
+// z, sg: the ray's coarse depths / densities (S-strided row); w, pw, cdf: scratch rows; fine: output row;
+// urow: the ray's Df uniform draws (global or shared memory).
 __device__ __forceinline__ void warp_resample_ray(const RenderArgs& a, const float* z, const float* sg, float* w, float* pw,
-                                                  float* cdf, float* fine, long long g, int lane) {
+                                                  float* cdf, float* fine, long long g, int lane, const float* urow) {
   const int Dc = a.Dc, Df = a.Df, nb = Dc - 3;
   warp_march_weights(z, sg, w, Dc, lane);
   __syncwarp();
@@ -132,7 +187,7 @@ __device__ __forceinline__ void warp_resample_ray(const RenderArgs& a, const flo
   __syncwarp();
   for (int j = lane; j < Df; j += 32) {
     int inds;
-    float smp = invert_cdf(cdf, nb, __ldg(a.u + g * Df + j),
+    float smp = invert_cdf(cdf, nb, urow[j],
                            [&](int i) { return __fmul_rn(0.5f, __fadd_rn(z[i], z[i + 1])); }, inds);
     fine[j] = smp;
     if (a.fine_depths) a.fine_depths[g * Df + j] = smp;

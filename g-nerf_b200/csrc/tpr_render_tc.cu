@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderAr
           // ---- importance resampling, one warp per ray
           for (int r = warp; r < nr; r += kTcWarps)
             warp_resample_ray(a, rs.dep + r * S, rs.sig + r * S, rs.wa + r * S, rs.wb + r * S, rs.wc + r * S,
-                              rs.dep + r * S + Dc, RAY_G(r), lane);
+                              rs.dep + r * S + Dc, RAY_G(r), lane, a.u + RAY_G(r) * Df);
           WORKER_SYNC();
           TPR_MARK(8);
         }

@@ -1,0 +1,696 @@
+// Warp-specialised fused ImportanceRenderer.forward (VR/renderer.py:88-140) for sm_100a.
+//
+// Same arithmetic as render_tc_kernel (tpr_render_tc.cu) -- plane gather, OSGDecoder on tcgen05 (3xTF32 or
+// bf16), in-register ray march / CDF / sort -- but the three kinds of work run CONCURRENTLY on one SM instead
+// of taking turns, because each of them alone leaves the SM mostly idle (ncu on the turn-taking kernel: 36 %
+// issue utilisation; the gather is bound by L2 latency, the per-ray phases by dependent-instruction latency):
+//
+//   warps  0-15  GATHER    per tile of 128 samples: bilinear taps -> 12 x 128-byte texel reads per sample -> A1
+//                          operand tile in shared memory (SWIZZLE_128B), three tiles deep
+//   warps 16-23  DECODE    warp 16 lane 0 issues the tcgen05.mma; all eight run the softplus epilogue
+//                          (tcgen05.ld D1 -> EX2/LG2 -> tcgen05.st A2) and read sigma back after layer 2
+//   warps 24-31  RAYS      one warp per ray: coarse depths, coarse march + pdf + CDF + inverse-CDF draws,
+//                          depth sort + final march, then the colour composite straight out of TMEM
+//
+// The roles are decoupled by a software pipeline over ray groups (a group = R rays of one image):
+//   GATHER/DECODE job order:  C(0) C(1) F(0) C(2) F(1) ...    (C = coarse pass, F = fine pass of a group)
+//   RAYS step g:              resample(g)  setup(g+2)  sort+composite(g-1)
+// so the importance resampling of group g hides behind the coarse gather of group g+1 and its sort/composite
+// behind the next jobs.  Layer-2 colour outputs stay in TMEM until the group's composite: a pool of 32-column
+// slots (11 in 3xTF32 mode, 12 in bf16 mode) with flow control (a slot is reused only after the composite of
+// the group that owned it); sigma goes through its own 16-column block and is copied to shared memory per tile.
+// mbarriers carry every hand-off; nothing per-sample ever touches HBM.
+//
+// Citations relative to /root/reference/g_nerf/ (VR/ = training/volumetric_rendering/).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string.h>
+#include <cuda_bf16.h>
+#include "triplane_b200.h"
+#include "tpr_render.cuh"
+#include "tpr_tc.cuh"
+
+namespace tpr {
+using namespace tc;
+
+namespace ws {
+
+constexpr int kGatherWarps = 16, kDecodeWarps = 8, kRayWarps = 8;
+constexpr int kThreads = 32 * (kGatherWarps + kDecodeWarps + kRayWarps);      // 1024
+constexpr int kFirstDecodeWarp = kGatherWarps, kFirstRayWarp = kGatherWarps + kDecodeWarps;
+constexpr int kRows = 128;                  // samples per tile = TMEM lanes
+constexpr int kN1 = 64, kNc = 32;           // layer 1 width, colour outputs
+constexpr int kBufs = 3;                    // A1 operand tiles in flight
+constexpr int kCtx = 4;                     // ray-group contexts in flight
+constexpr int kSlotCols = 32;
+
+// TMEM column maps.  3xTF32: the hi half of the layer-2 A operand overwrites D1 in place (layer 1 of the next
+// tile is issued after layer 2 of this one, and the tensor pipe executes in issue order).
+template <int MODE> struct Cols;
+template <> struct Cols<0> { static constexpr uint32_t d1 = 0, a2hi = 0, a2lo = 64, slots = 128; static constexpr int ns = 12; };
+template <> struct Cols<1> { static constexpr uint32_t d1 = 0, a2hi = 64, a2lo = 64, slots = 96; static constexpr int ns = 13; };
+
+// Only the two dense contractions run on the tensor cores: hidden = A1.W1^T (N = 64) and colours = A2.W2c^T
+// (N = 32).  Biases and the single sigma row of layer 2 are applied by the epilogue in fp32 FFMA: a tcgen05.mma
+// costs ~75 cycles of issue time whatever its N (measured, profiles/), so 1-row and bias MMAs are poor value.
+template <int MODE> struct Tiles;           // every MMA operand member is a multiple of 1024 B: tiles stay swizzle-aligned
+template <> struct Tiles<0> {               // 3xTF32: [hi, lo] copies
+  float a1[kBufs][2][kRows * 32];
+  float b1[2][kN1 * 32];
+  float b2c[2][2][kNc * 32];                // [hi, lo][k block]
+  float bias1[kN1];                         // b1 * log2e
+  float w2s[kN1];                           // sigma row of W2, * ln2 (hidden activations are softplus/ln2)
+  float bias2[kNc + 4];                     // [0..31] = -log2e * colour bias, [32] = sigma bias
+  float psig[kRows];                        // sigma partial sums of hidden units 32..63
+};
+template <> struct Tiles<1> {               // bf16 (rows are still 128 B; layer 1 uses the first 64 B)
+  float a1[kBufs][1][kRows * 32];
+  float b1[1][kN1 * 32];
+  float b2c[1][1][kNc * 32];
+  float bias1[kN1];
+  float w2s[kN1];
+  float bias2[kNc + 4];
+  float psig[kRows];
+};
+
+struct Barriers {
+  uint64_t a1_full[kBufs];      // 16 gather-warp arrivals: tile gathered and published to the async proxy
+  uint64_t a1_free[kBufs];      // tcgen05.commit: layer 1 has consumed the tile
+  uint64_t d1_full;             // tcgen05.commit: layer 1 of the current tile is in TMEM
+  uint64_t a2_full;             // 8 decode-warp arrivals: activations are back in TMEM
+  uint64_t m2_done;             // tcgen05.commit: layer 2 of the current tile is in its slot / sigma block
+  uint64_t coarse_ready[kCtx];  // 8 ray-warp arrivals: coarse depths of the group are in shared memory
+  uint64_t fine_ready[kCtx];    // 8 ray-warp arrivals: importance depths are in shared memory
+  uint64_t csig_ready[kCtx];    // 4 decode-warp arrivals: every coarse sigma of the group is in shared memory
+  uint64_t fsig_ready[kCtx];    // 4 decode-warp arrivals: every fine sigma, and every colour slot of the group is final
+};
+
+__device__ __forceinline__ void st_swz_f32(float* tile, int row, int k, float v) {
+  tile[row * 32 + ((((k >> 2) ^ (row & 7)) << 2) | (k & 3))] = v;
+}
+__device__ __forceinline__ void st_swz_bf16(float* tile, int row, int k, float v) {     // 64 bf16 per 128-byte row
+  reinterpret_cast<__nv_bfloat16*>(tile)[row * 64 + ((((k >> 3) ^ (row & 7)) << 3) | (k & 7))] = __float2bfloat16_rn(v);
+}
+
+// Packed decoder (tpr_device.cuh) -> MMA B operands.  Layer-1 outputs are produced in the log2 domain (log2e
+// folded into W1/b1), the activation returns softplus/ln2, so sigma weights carry ln2 and colour weights a minus
+// sign: the colour slot holds -logit*log2e, which colour_act_neglog2 turns into the sigmoid with one EX2.
+template <int MODE>
+__device__ void stage_weights(const float* __restrict__ dec, Tiles<MODE>& tl) {
+  const int tid = threadIdx.x;
+  constexpr int L = MODE == 0 ? 1 : 0;      // index of the lo copy (aliases hi in bf16 mode, never written there)
+  for (int i = tid; i < kN1 * 32; i += kThreads) {
+    const int n = i >> 5, k = i & 31;
+    const float w = dec[kW1tOff + k * kHid + n] * kLog2e;
+    if (MODE == 1) st_swz_bf16(tl.b1[0], n, k, w);
+    else { float hi, lo; split_tf32(w, hi, lo); st_swz_f32(tl.b1[0], n, k, hi); st_swz_f32(tl.b1[L], n, k, lo); }
+  }
+  for (int i = tid; i < kNc * 64; i += kThreads) {
+    const int n = i >> 6, k = i & 63;                       // colour n = decoder output n + 1
+    const float w = -dec[kW2tOff + k * kOutPad + n + 1];
+    if (MODE == 1) st_swz_bf16(tl.b2c[0][0], n, k, w);
+    else {
+      float hi, lo; split_tf32(w, hi, lo);
+      st_swz_f32(tl.b2c[0][k >> 5], n, k & 31, hi);
+      st_swz_f32(tl.b2c[L][k >> 5], n, k & 31, lo);
+    }
+  }
+  for (int i = tid; i < kN1; i += kThreads) {
+    tl.bias1[i] = dec[kB1Off + i] * kLog2e;
+    tl.w2s[i] = dec[kW2tOff + i * kOutPad] * kLn2;
+  }
+  for (int i = tid; i < kNc + 1; i += kThreads) tl.bias2[i] = i < kNc ? -kLog2e * dec[kB2Off + 1 + i] : dec[kB2Off];
+}
+
+// per-group shared-memory context
+struct Ctx { float* dep; float* sig; float* u; float* ray; };
+
+struct Geom { long long n, ray0, rstride; int nr; };
+// Which rays form group `grp`.  Column mode (rays are a col_w-wide image, x fastest, VR/ray_sampler.py:44):
+// R vertically adjacent pixels of one image column -- they nearly share their (x,z) footprint, i.e. their taps on
+// two of the three planes (VR/renderer.py:29-37).  Otherwise R consecutive rays.
+__device__ __forceinline__ Geom group_geom(const RenderArgs& a, long long grp, int R) {
+  Geom g;
+  g.n = grp / a.tiles_per_img;
+  const long long gi = grp - g.n * a.tiles_per_img;
+  const bool colm = a.col_w > 0;
+  g.ray0 = g.n * a.rays_per_img + (colm ? (gi / a.col_w) * R * a.col_w + gi % a.col_w : gi * R);
+  g.rstride = colm ? a.col_w : 1;
+  g.nr = colm ? R : (int)min((long long)R, a.rays_per_img - gi * R);
+  return g;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GATHER: one tile (rows = R rays x DPT depths) into an A1 buffer.  Warp w owns rows [8w, 8w+8).
+// Step 1: lane 3s+p computes the bilinear taps of (sample s, plane p) into the warp's tap table.
+// Step 2: eight lanes per sample fetch whole 128-byte texels (four channels per lane), one plane (four texels)
+//         at a time: tpr_gather_microbench (profiles/) shows that on B200 a shallow queue per thread and many
+//         warps sustains more random-line bandwidth than twelve loads in flight per thread.
+// ---------------------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void gather_tile(const RenderArgs& a, float* a1_hi, float* a1_lo, const float* __restrict__ img,
+                                            const Ctx& cx, TapEntry* tw, int nr, int Dx, int off, int S, int t, int dpt_shift,
+                                            int warp, int lane) {
+  const int grp = lane >> 3, sub = lane & 7;
+  const int dpt = 1 << dpt_shift;
+  {
+    const int s = lane / 3, p = lane - s * 3;
+    const int row = warp * 8 + s;
+    const int r = row >> dpt_shift, di = t * dpt + (row & (dpt - 1));
+    if (lane < 24 && r < nr && di < Dx) {
+      const float d = cx.dep[r * S + off + di];
+      const float* ry = cx.ray + r * 8;
+      // origin + depth * direction (VR/renderer.py:105,123), then * 2/box_warp (:61)
+      const float px = __fmul_rn(__fadd_rn(ry[0], __fmul_rn(d, ry[3])), a.box_scale);
+      const float py = __fmul_rn(__fadd_rn(ry[1], __fmul_rn(d, ry[4])), a.box_scale);
+      const float pz = __fmul_rn(__fadd_rn(ry[2], __fmul_rn(d, ry[5])), a.box_scale);
+      Taps tp;
+      plane_taps(p == 2 ? pz : px, p == 0 ? py : (p == 1 ? pz : px), a.H, a.W, tp);   // (x,y) (x,z) (z,x)
+      const int po = p * a.H * a.W * kC;
+      *reinterpret_cast<int4*>(tw[lane].off) = make_int4(tp.off[0] + po, tp.off[1] + po, tp.off[2] + po, tp.off[3] + po);
+      *reinterpret_cast<float4*>(tw[lane].w) = make_float4(tp.w[0], tp.w[1], tp.w[2], tp.w[3]);
+    }
+  }
+  __syncwarp();
+  const float* img_sub = img + sub * 4;
+#pragma unroll 1
+  for (int rd = 0; rd < 2; ++rd) {
+    const int s = rd * 4 + grp;
+    const int row = warp * 8 + s;
+    const int r = row >> dpt_shift, di = t * dpt + (row & (dpt - 1));
+    if (r < nr && di < Dx) {
+      const TapEntry* te = tw + s * 3;
+      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+      for (int p = 0; p < 3; ++p) {
+        const int4 o = *reinterpret_cast<const int4*>(te[p].off);
+        const float4 w = *reinterpret_cast<const float4*>(te[p].w);
+        const float4 v0 = ldg128(img_sub + (unsigned)o.x), v1 = ldg128(img_sub + (unsigned)o.y);
+        const float4 v2 = ldg128(img_sub + (unsigned)o.z), v3 = ldg128(img_sub + (unsigned)o.w);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        fma4(acc, w.x, v0); fma4(acc, w.y, v1); fma4(acc, w.z, v2); fma4(acc, w.w, v3);
+        f.x += acc.x; f.y += acc.y; f.z += acc.z; f.w += acc.w;
+      }
+      if (MODE == 1) {
+        uint2 pk = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
+        uint8_t* dst = reinterpret_cast<uint8_t*>(a1_hi) + row * 128 + ((((sub >> 1) ^ (row & 7)) << 4) | ((sub & 1) << 3));
+        *reinterpret_cast<uint2*>(dst) = pk;
+      } else {
+        float4 hi, lo;
+        split_tf32(f.x, hi.x, lo.x); split_tf32(f.y, hi.y, lo.y); split_tf32(f.z, hi.z, lo.z); split_tf32(f.w, hi.w, lo.w);
+        *reinterpret_cast<float4*>(a1_hi + row_chunk_off(row, sub)) = hi;
+        *reinterpret_cast<float4*>(a1_lo + row_chunk_off(row, sub)) = lo;
+      }
+    }
+  }
+  __syncwarp();           // the tap table is rewritten by the next tile
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// DECODE: MMA issue (one thread)
+// ---------------------------------------------------------------------------------------------------------
+// The issuing thread's own instruction stream bounds the MMA rate for these small shapes (tpr_mma_microbench,
+// profiles/: ~70-100 cycles per tcgen05.mma when the descriptors are rebuilt each time, 28 (TS, N = 32) to 76
+// (SS, N = 64) when they are not), so every descriptor is the tile block's base descriptor plus a compile-time
+// constant: the start-address field counts 16-byte units and all operand tiles live in one Tiles<> block.
+#define TPR_OFF16(member) ((uint32_t)(offsetof(Tiles<MODE>, member) >> 4))
+#define TPR_D(lo) desc_sw128_from_lo(lo)
+template <int MODE>
+__device__ __forceinline__ void issue_layer1(uint32_t dlo, int buf, uint32_t tmem) {
+  const uint32_t d1 = tmem + Cols<MODE>::d1;
+  constexpr uint32_t kTile16 = (kRows * 32 * 4) >> 4;                       // one 16 KB A1 tile
+  const uint32_t ah = dlo + TPR_OFF16(a1) + (uint32_t)buf * ((MODE == 0 ? 2 : 1) * kTile16);
+  const uint32_t bh = dlo + TPR_OFF16(b1);
+  if (MODE == 1) {
+    const uint32_t idesc = instr_desc(kFmtBF16, 128, kN1);
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) mma_f16_ss(d1, TPR_D(ah + 2 * ks), TPR_D(bh + 2 * ks), idesc, ks > 0);
+  } else {
+    const uint32_t idesc = instr_desc(kFmtTF32, 128, kN1);
+    const uint32_t al = ah + kTile16, bl = bh + ((kN1 * 32 * 4) >> 4);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      mma_tf32_ss(d1, TPR_D(ah + 2 * ks), TPR_D(bh + 2 * ks), idesc, ks > 0);
+      mma_tf32_ss(d1, TPR_D(al + 2 * ks), TPR_D(bh + 2 * ks), idesc, true);
+      mma_tf32_ss(d1, TPR_D(ah + 2 * ks), TPR_D(bl + 2 * ks), idesc, true);
+    }
+  }
+}
+
+// layer 2, colour rows only (N = 32), into slot `slot`
+template <int MODE>
+__device__ __forceinline__ void issue_layer2(uint32_t dlo, uint32_t tmem, int slot) {
+  const uint32_t dc = tmem + Cols<MODE>::slots + slot * kSlotCols;
+  const uint32_t bh = dlo + TPR_OFF16(b2c);
+  constexpr uint32_t kB16 = (kNc * 32 * 4) >> 4;                            // one 4 KB W2 block
+  if (MODE == 1) {
+    const uint32_t ic = instr_desc(kFmtBF16, 128, kNc);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) mma_f16_ts(dc, tmem + Cols<MODE>::a2hi + ks * 8, TPR_D(bh + 2 * ks), ic, ks > 0);
+  } else {
+    const uint32_t ic = instr_desc(kFmtTF32, 128, kNc);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const uint32_t bhk = bh + (ks >> 2) * kB16 + 2 * (ks & 3), blk = bhk + 2 * kB16;   // [hi, lo][k block]
+      mma_tf32_ts(dc, tmem + Cols<MODE>::a2hi + ks * 8, TPR_D(bhk), ic, ks > 0);
+      mma_tf32_ts(dc, tmem + Cols<MODE>::a2lo + ks * 8, TPR_D(bhk), ic, true);
+      mma_tf32_ts(dc, tmem + Cols<MODE>::a2hi + ks * 8, TPR_D(blk), ic, true);
+    }
+  }
+}
+
+// E1: D1 + b1 -> softplus -> A2 (TMEM).  Decode warp (q, h) owns lane quarter q and hidden columns [32h, 32h+32).
+// Returns this thread's part of sigma = w2s . hidden over those columns (fp32 FFMA, training/triplane.py:135).
+template <int MODE>
+__device__ __forceinline__ float epilogue1(const Tiles<MODE>& tl, uint32_t tmem, uint32_t lane_base, int h) {
+  float sg = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int col = 32 * h + 16 * c;
+    uint32_t r[16];
+    tmem_ld16(tmem + Cols<MODE>::d1 + lane_base + col, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float act[8];
+#pragma unroll
+      for (int i4 = 0; i4 < 2; ++i4) {
+        const int o = 8 * half + 4 * i4;
+        const float4 b = *reinterpret_cast<const float4*>(tl.bias1 + col + o);
+        const float4 w = *reinterpret_cast<const float4*>(tl.w2s + col + o);
+        act[4 * i4 + 0] = softplus_log2(__uint_as_float(r[o + 0]) + b.x); sg = fmaf(act[4 * i4 + 0], w.x, sg);
+        act[4 * i4 + 1] = softplus_log2(__uint_as_float(r[o + 1]) + b.y); sg = fmaf(act[4 * i4 + 1], w.y, sg);
+        act[4 * i4 + 2] = softplus_log2(__uint_as_float(r[o + 2]) + b.z); sg = fmaf(act[4 * i4 + 2], w.z, sg);
+        act[4 * i4 + 3] = softplus_log2(__uint_as_float(r[o + 3]) + b.w); sg = fmaf(act[4 * i4 + 3], w.w, sg);
+      }
+      if (MODE == 1) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pk[i] = pack_bf16(act[2 * i], act[2 * i + 1]);
+        tmem_st4(tmem + Cols<MODE>::a2hi + lane_base + ((col + 8 * half) >> 1), pk);
+      } else {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float x, y;
+          split_tf32(act[i], x, y);
+          hi[i] = __float_as_uint(x); lo[i] = __float_as_uint(y);
+        }
+        tmem_st8(tmem + Cols<MODE>::a2hi + lane_base + col + 8 * half, hi);
+        tmem_st8(tmem + Cols<MODE>::a2lo + lane_base + col + 8 * half, lo);
+      }
+    }
+  }
+  tmem_wait_st();
+  return sg;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------------
+template <int MODE, int E>
+__global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  Tiles<MODE>& tl = *reinterpret_cast<Tiles<MODE>*>(base);
+  TapEntry* taps = reinterpret_cast<TapEntry*>(base + sizeof(Tiles<MODE>));
+  float* fl = reinterpret_cast<float*>(base + sizeof(Tiles<MODE>) + sizeof(TapEntry) * kGatherWarps * 24);
+  const int R = a.R, Dc = a.Dc, Df = a.Df, S = Dc + Df;
+  const int dpt_shift = R == 8 ? 4 : 5, dpt = 1 << dpt_shift;
+  // contexts: dep [R*S], sig [R*S], u [R*Df], ray [R*8]
+  const int ctx_floats = 2 * R * S + R * Df + R * 8;
+  float* scratch = fl + kCtx * ctx_floats;            // ray-warp scratch: wa, wb, wc [R*S] each, rayw [R]
+  auto ctx_of = [&](int gi) {
+    float* p = fl + (gi & (kCtx - 1)) * ctx_floats;
+    Ctx c; c.dep = p; c.sig = p + R * S; c.u = c.sig + R * S; c.ray = c.u + R * Df;
+    return c;
+  };
+  __shared__ Barriers bars;
+  __shared__ uint32_t tmem_base_sm;
+  __shared__ unsigned range_sm[2];
+  // Colour-slot allocation.  Slot lifetimes are not FIFO (job order C(g+1) F(g): the coarse slots of group g+1 are
+  // handed out before the fine slots of group g but released after them), so the MMA issuer keeps a free mask,
+  // records the slot of every tile of a group in slot_tab[ctx] (read by the ray warps for the composite) and takes
+  // a group's slots back once all eight ray warps have added 1 to freed_warps after their last read of them.
+  // A counter rather than an mbarrier: several groups may be released between two looks of the issuer.
+  __shared__ unsigned freed_warps;
+  __shared__ int slot_tab[kCtx][16];
+  // TPR_PHASE_TIMING=1: cycles CTA 0 spends in each wait / work section of each role (one lane per role)
+  __shared__ long long prof[24];
+  const bool profiling = a.dbg != nullptr && blockIdx.x == 0;
+#define PROF_T0() long long pt0_ = profiling ? clock64() : 0
+#define PROF_ADD(i, cond) do { if (profiling && (cond)) { const long long now_ = clock64(); prof[i] += now_ - pt0_; pt0_ = now_; } } while (0)
+  // the warp index goes through a shuffle so that the compiler knows it is warp-uniform: everything the MMA issuer
+  // derives from role-dependent control flow (buffer index, slot, descriptors) then lives in uniform registers and a
+  // tcgen05.mma costs one or two instructions instead of an elect/broadcast loop
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+
+  if (tid == 0) {
+    range_sm[0] = 0xffffffffu; range_sm[1] = 0u;
+    for (int b = 0; b < kBufs; ++b) { mbar_init(&bars.a1_full[b], kGatherWarps); mbar_init(&bars.a1_free[b], 1); }
+    mbar_init(&bars.d1_full, 1); mbar_init(&bars.a2_full, kDecodeWarps); mbar_init(&bars.m2_done, 1);
+    for (int c = 0; c < kCtx; ++c) {
+      mbar_init(&bars.coarse_ready[c], kRayWarps); mbar_init(&bars.fine_ready[c], kRayWarps);
+      mbar_init(&bars.csig_ready[c], 4); mbar_init(&bars.fsig_ready[c], 4);
+    }
+    freed_warps = 0u;
+    for (int i = 0; i < 24; ++i) prof[i] = 0;
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(&tmem_base_sm, 512); tmem_relinquish(); }
+  stage_weights<MODE>(a.dec, tl);
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_sm, 0);
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+
+  const int nc = (Dc + dpt - 1) >> dpt_shift, nf = Df > 0 ? (Df + dpt - 1) >> dpt_shift : 0;
+  // groups of this CTA: blockIdx.x + gi * gridDim.x, gi = 0 .. G-1
+  const int G = (int)((a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const size_t img_stride = (size_t)3 * a.H * a.W * kC;
+  const bool per_ray = a.rs != nullptr;
+
+  if (warp < kGatherWarps) {
+    // ====================================== GATHER ======================================
+    TapEntry* tw = taps + warp * 24;
+    int b = 0; uint32_t ph = 0;                      // A1 buffer ring position / phase
+    for (int step = 0; step <= G; ++step) {
+#pragma unroll 1
+      for (int jb = 0; jb < 2; ++jb) {
+        const int pass = jb;
+        int gi;
+        if (pass == 0) { if (step >= G) continue; gi = step; }
+        else { if (step < 1 || nf == 0) continue; gi = step - 1; }
+        const Geom gg = group_geom(a, blockIdx.x + (long long)gi * gridDim.x, R);
+        const Ctx cx = ctx_of(gi);
+        const uint32_t cpar = (uint32_t)(gi >> 2) & 1u;
+        PROF_T0();
+        mbar_wait_parked(pass == 0 ? &bars.coarse_ready[gi & 3] : &bars.fine_ready[gi & 3], cpar);
+        PROF_ADD(pass, tid == 0);
+        const float* img = a.planes + (size_t)gg.n * img_stride;
+        const int T = pass == 0 ? nc : nf, Dx = pass == 0 ? Dc : Df, off = pass == 0 ? 0 : Dc;
+#pragma unroll 1
+        for (int t = 0; t < T; ++t) {
+          mbar_wait_parked(&bars.a1_free[b], ph ^ 1u);      // passes immediately the first time round
+          PROF_ADD(2, tid == 0);
+          gather_tile<MODE>(a, tl.a1[b][0], tl.a1[b][MODE == 0 ? 1 : 0], img, cx, tw, gg.nr, Dx, off, S, t, dpt_shift, warp, lane);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.a1_full[b]);
+          PROF_ADD(3, tid == 0);
+          if (++b == kBufs) { b = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp < kFirstRayWarp) {
+    // ====================================== DECODE ======================================
+    const int dw = warp - kFirstDecodeWarp, q = dw & 3, h = dw >> 2;
+    const bool issuer = dw == 0;
+    int b = 0; uint32_t ph = 0;                      // A1 buffer ring
+    uint32_t pt = 0;                                 // per-tile phase of d1_full / a2_full / m2_done
+    const uint32_t dbase = smem_desc_lo(smem_u32(&tl));
+    uint32_t free_mask = (1u << Cols<MODE>::ns) - 1u;  // issuer only (warp-uniform): free colour slots
+    int freed_groups = 0;                              // groups whose slots have been taken back
+    for (int step = 0; step <= G; ++step) {
+#pragma unroll 1
+      for (int jb = 0; jb < 2; ++jb) {
+        const int pass = jb;
+        int gi;
+        if (pass == 0) { if (step >= G) continue; gi = step; }
+        else { if (step < 1 || nf == 0) continue; gi = step - 1; }
+        const Geom gg = group_geom(a, blockIdx.x + (long long)gi * gridDim.x, R);
+        const Ctx cx = ctx_of(gi);
+        const int T = pass == 0 ? nc : nf, Dx = pass == 0 ? Dc : Df, off = pass == 0 ? 0 : Dc;
+#pragma unroll 1
+        for (int t = 0; t < T; ++t) {
+          PROF_T0();
+          const bool pl = dw == 0 && lane == 0;
+          if (issuer) {
+            mbar_wait_parked(&bars.a1_full[b], ph);
+            PROF_ADD(4, pl);
+            tcgen05_fence_after();
+            const int bu = __shfl_sync(0xffffffffu, b, 0);     // uniform register for the descriptor arithmetic
+            if (elect_one_sync()) {
+              issue_layer1<MODE>(dbase, bu, tmem);
+              mma_commit(&bars.a1_free[b]);
+              mma_commit(&bars.d1_full);
+            }
+            __syncwarp();
+          }
+          if (++b == kBufs) { b = 0; ph ^= 1u; }
+          int slot = 0;
+          if (issuer) {
+            // take back the slots of every group composited since the last look (eagerly: slot_tab[ctx] is rewritten
+            // four groups later); spin only while every slot holds colours of a group that is not composited yet
+            do {
+              const int fg = (int)(*reinterpret_cast<volatile unsigned*>(&freed_warps) / kRayWarps);
+              for (; freed_groups < fg; ++freed_groups)
+                for (int i = 0; i < nc + nf; ++i) free_mask |= 1u << slot_tab[freed_groups & (kCtx - 1)][i];
+            } while (free_mask == 0u);
+            __threadfence_block();
+            slot = __shfl_sync(0xffffffffu, __ffs(free_mask) - 1, 0);        // (warp-uniform by construction)
+            free_mask &= ~(1u << slot);
+            if (lane == 0) slot_tab[gi & (kCtx - 1)][(pass == 0 ? 0 : nc) + t] = slot;
+          }
+          PROF_ADD(5, pl);
+          mbar_wait_parked(&bars.d1_full, pt);               // also: layer 2 of the previous tile has consumed A2
+          PROF_ADD(6, pl);
+          tcgen05_fence_after();
+          const float sgp = epilogue1<MODE>(tl, tmem, lane_base, h);
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.a2_full);
+          PROF_ADD(7, pl);
+          if (issuer) {
+            mbar_wait_parked(&bars.a2_full, pt);
+            PROF_ADD(8, pl);
+            tcgen05_fence_after();
+            if (elect_one_sync()) {
+              issue_layer2<MODE>(dbase, tmem, slot);
+              mma_commit(&bars.m2_done);
+            }
+            __syncwarp();
+          }
+          PROF_ADD(9, pl);
+          // sigma of this tile -> shared memory: the two warps of a lane quarter add their halves
+          if (h == 1) tl.psig[q * 32 + lane] = sgp;
+          named_bar_sync(3 + q, 64);
+          if (h == 0) {
+            const int row = q * 32 + lane, r = row >> dpt_shift, di = t * dpt + (row & (dpt - 1));
+            if (r < gg.nr && di < Dx) cx.sig[r * S + off + di] = sgp + tl.psig[row] + tl.bias2[kNc];
+          }
+          named_bar_sync(3 + q, 64);                  // psig is rewritten by the next tile
+          PROF_ADD(10, pl);
+          if (h == 0 && t == T - 1) {
+            // coarse pass: the resampling only needs sigma.  Last pass of the group: the composite also needs every
+            // colour slot of the group, i.e. this tile's layer 2 (and with it all earlier MMAs) complete.
+            if (pass == 1 || nf == 0) { mbar_wait_parked(&bars.m2_done, pt); }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pass == 0 ? &bars.csig_ready[gi & 3] : &bars.fsig_ready[gi & 3]);
+          }
+          pt ^= 1u;
+          PROF_ADD(11, pl);
+        }
+      }
+    }
+  } else {
+    // ====================================== RAYS ======================================
+    const int rw = warp - kFirstRayWarp, rtid = tid - kFirstRayWarp * 32;
+    const int q = rw & 3, hc = rw >> 2;               // composite: lane quarter, channel half
+    constexpr int kRayThreads = kRayWarps * 32;
+    float* wa = scratch; float* wb = wa + R * S; float* wc = wb + R * S; float* rayw = wc + R * S;
+    float mn = __int_as_float(0x7f800000), mx = -__int_as_float(0x7f800000);
+#define RAY_SYNC() named_bar_sync(2, kRayThreads)
+
+    const bool pl = rtid == 0;
+    auto setup = [&](int gi) {
+      // rays, coarse depths (VR/renderer.py:169-192) and the group's uniform draws into its context
+      PROF_T0();
+      const Geom gg = group_geom(a, blockIdx.x + (long long)gi * gridDim.x, R);
+      const Ctx cx = ctx_of(gi);
+      if (rtid < gg.nr * 6) {
+        const int r = rtid / 6, c = rtid - r * 6;
+        const long long g = gg.ray0 + (long long)r * gg.rstride;
+        cx.ray[r * 8 + c] = c < 3 ? __ldg(a.origins + g * 3 + c) : __ldg(a.dirs + g * 3 + c - 3);
+      }
+      for (int s = rtid; s < gg.nr * Dc; s += kRayThreads) {
+        const int r = s / Dc, k = s - r * Dc;
+        const long long g = gg.ray0 + (long long)r * gg.rstride;
+        const float lo = per_ray ? __ldg(a.rs + g) : a.ray_start, hi = per_ray ? __ldg(a.re + g) : a.ray_end;
+        cx.dep[r * S + k] = coarse_depth(a, k, __ldg(a.jitter + g * Dc + k), lo, hi, per_ray);
+      }
+      for (int s = rtid; s < gg.nr * Df; s += kRayThreads) {
+        const int r = s / Df, k = s - r * Df;
+        cx.u[s] = __ldg(a.u + (gg.ray0 + (long long)r * gg.rstride) * Df + k);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.coarse_ready[gi & 3]);
+      PROF_ADD(12, pl);
+    };
+
+    auto resample = [&](int gi) {
+      const Geom gg = group_geom(a, blockIdx.x + (long long)gi * gridDim.x, R);
+      const Ctx cx = ctx_of(gi);
+      PROF_T0();
+      mbar_wait_parked(&bars.csig_ready[gi & 3], (uint32_t)(gi >> 2) & 1u);
+      PROF_ADD(13, pl);
+      // the uniform draws were staged by other warps in setup(); coarse_ready has completed (the coarse pass ran)
+      for (int r = rw; r < gg.nr; r += kRayWarps)
+        warp_resample_ray(a, cx.dep + r * S, cx.sig + r * S, wa + r * S, wb + r * S, wc + r * S, cx.dep + r * S + Dc,
+                          gg.ray0 + (long long)r * gg.rstride, lane, cx.u + r * Df);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.fine_ready[gi & 3]);
+      PROF_ADD(14, pl);
+    };
+
+    auto sort_composite = [&](int gi) {
+      const Geom gg = group_geom(a, blockIdx.x + (long long)gi * gridDim.x, R);
+      const Ctx cx = ctx_of(gi);
+      PROF_T0();
+      mbar_wait_parked(nf > 0 ? &bars.fsig_ready[gi & 3] : &bars.csig_ready[gi & 3], (uint32_t)(gi >> 2) & 1u);
+      PROF_ADD(15, pl);
+      // ---- sort + final march: omega per sample (scattered to original order), depth, weight sum
+      for (int r = rw; r < gg.nr; r += kRayWarps) {
+        float wsum, dnum;
+        warp_sort_and_weights<E, true>(cx.dep + r * S, cx.sig + r * S, wa + r * S, nullptr, S, lane, wsum, dnum, mn, mx,
+                                       wb + r * 2 * S);          // wb and wc are contiguous: 2*S floats per ray
+        if (lane == 0) {
+          const long long g = gg.ray0 + (long long)r * gg.rstride;
+          rayw[r] = wsum;
+          a.depth[g] = dnum / wsum;                   // NaN -> inf and the clamp happen in finish_kernel
+          a.wsum[g] = wsum;
+        }
+      }
+      RAY_SYNC();
+      PROF_ADD(16, pl);
+      // ---- composite: ray warp (q, hc) sums channels [16hc, 16hc+16) over the samples held by its lanes
+      tcgen05_fence_after();
+      const int row = q * 32 + lane, r = row >> dpt_shift, i = row & (dpt - 1);
+      float acc[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
+#pragma unroll 1
+      for (int sl = 0; sl < nc + nf; ++sl) {
+        const bool fine = sl >= nc;
+        const int tl_i = fine ? sl - nc : sl;
+        const int slot = slot_tab[gi & (kCtx - 1)][sl];
+        const int di = tl_i * dpt + i;
+        const bool valid = r < gg.nr && di < (fine ? Df : Dc);
+        const float om = valid ? wa[r * S + (fine ? Dc : 0) + di] : 0.0f;
+        uint32_t v[16];
+        tmem_ld16(tmem + Cols<MODE>::slots + slot * kSlotCols + lane_base + 16 * hc, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float4 bz = *reinterpret_cast<const float4*>(tl.bias2 + 16 * hc + 4 * c4);
+          const float bb[4] = {bz.x, bz.y, bz.z, bz.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            acc[4 * c4 + c] = valid ? fmaf(om, colour_act_neglog2(__uint_as_float(v[4 * c4 + c]) + bb[c]), acc[4 * c4 + c]) : acc[4 * c4 + c];
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) { __threadfence_block(); atomicAdd(&freed_warps, 1u); }   // this warp is done with the group's slots
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        if (o < dpt) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) acc[c] += __shfl_xor_sync(kFull, acc[c], o);
+        }
+      }
+      if (i == 0 && r < gg.nr) {
+        const float wsr = rayw[r];
+        float4* dst = reinterpret_cast<float4*>(a.rgb + (gg.ray0 + (long long)r * gg.rstride) * kC + 16 * hc);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          float o4[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float v = acc[4 * c4 + c];
+            if (a.white_back) v = v + 1.0f - wsr;      // VR/ray_marcher.py:52-53
+            o4[c] = v * 2.0f - 1.0f;                   // :55
+          }
+          dst[c4] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        }
+      }
+      RAY_SYNC();                                      // wa / rayw are reused by the next resample / sort
+      PROF_ADD(17, pl);
+    };
+
+    setup(0);
+    if (G > 1) setup(1);
+    for (int g = 0; g < G; ++g) {
+      if (nf > 0) resample(g);
+      if (g + 2 < G) setup(g + 2);
+      if (nf > 0) { if (g >= 1) sort_composite(g - 1); }
+      else sort_composite(g);
+    }
+    if (nf > 0) sort_composite(G - 1);
+    mn = warp_min(mn); mx = warp_max(mx);
+    if (lane == 0 && mn <= mx) {
+      atomicMin(&range_sm[0], float_to_ordered(mn));
+      atomicMax(&range_sm[1], float_to_ordered(mx));
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (tid == 0 && range_sm[0] <= range_sm[1]) {
+    atomicMin(a.range_enc + 0, range_sm[0]);
+    atomicMax(a.range_enc + 1, range_sm[1]);
+  }
+  if (warp == 0) { tcgen05_fence_after(); tmem_dealloc(tmem, 512); }
+  if (profiling && tid < 24) a.dbg[tid] = prof[tid];
+}
+
+template <int MODE>
+static size_t smem_bytes(int R, int S, int Df) {
+  return 1024 + sizeof(Tiles<MODE>) + sizeof(TapEntry) * kGatherWarps * 24 +
+         sizeof(float) * ((size_t)kCtx * (2 * R * S + R * Df + R * 8) + (size_t)3 * R * S + R + 8);
+}
+
+typedef void (*Kernel)(const RenderArgs);
+template <int MODE>
+static Kernel pick_kernel(int S) {
+  return S <= 64 ? render_ws_kernel<MODE, 2> : S <= 128 ? render_ws_kernel<MODE, 4> : render_ws_kernel<MODE, 8>;
+}
+
+}  // namespace ws
+
+// Rays per group (8 or 4) the warp-specialised kernel would use, or 0 if (Dc, Df) does not fit its slot ring:
+// the pipelined job order keeps the coarse slots of two groups and the fine slots of one alive at once.
+int ws_rays_per_group(int Dc, int Df, int bf16) {
+  const int ns = bf16 ? ws::Cols<1>::ns : ws::Cols<0>::ns;
+  for (int R = 8; R >= 4; R >>= 1) {
+    const int dpt = ws::kRows / R;
+    const int nc = (Dc + dpt - 1) / dpt, nf = Df > 0 ? (Df + dpt - 1) / dpt : 0;
+    if (2 * nc + nf <= ns) return R;
+  }
+  return 0;
+}
+
+// Launch; returns cudaError_t (0 = ok), or -1 if the configuration does not fit (the caller falls back).
+int launch_render_ws(RenderArgs a, int bf16, int sms, int smem_optin, long long n_img, long long n_rays, cudaStream_t st) {
+  const int S = a.Dc + a.Df;
+  a.R = ws_rays_per_group(a.Dc, a.Df, bf16);
+  if (a.R == 0) return -1;
+  if (a.col_w > 0 && (a.col_w % a.R != 0 || (long long)a.col_w * a.col_w != n_rays)) a.col_w = 0;
+  a.tiles_per_img = (n_rays + a.R - 1) / a.R;
+  a.n_tiles = a.tiles_per_img * n_img;
+  ws::Kernel k = bf16 ? ws::pick_kernel<1>(S) : ws::pick_kernel<0>(S);
+  const size_t smem = bf16 ? ws::smem_bytes<1>(a.R, S, a.Df) : ws::smem_bytes<0>(a.R, S, a.Df);
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, k);
+  if (e != cudaSuccess) return (int)e;
+  if ((int)smem > smem_optin - (int)fa.sharedSizeBytes) return -1;
+  e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const long long grid = a.n_tiles < sms ? a.n_tiles : sms;      // one CTA per SM: each owns all 512 TMEM columns
+  k<<<(unsigned)grid, ws::kThreads, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace tpr

@@ -30,6 +30,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
+// Same, but the hardware may park the thread for up to `ns` nanoseconds per attempt (it is still woken when the phase
+// completes).  For waits that are long by design: a bare try_wait loop re-issues every ~20 cycles, and in a kernel
+// where three roles share the issue slots of one SM those polling instructions are not free (ncu: 16 % of all
+// instructions of render_ws_kernel were mbarrier polling before this).
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t ns = 20000u) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+  } while (ok == 0);
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -79,6 +93,18 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t tile_smem_addr, uin
   d |= (uint64_t)(1024 >> 4) << 32;                                       // stride byte offset
   d |= (uint64_t)1 << 46;                                                 // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;                                                 // SWIZZLE_128B
+  return d;
+}
+
+// The same descriptor split into its words: the high word is a constant, the low word is the start address in
+// 16-byte units (14 bits) plus the LBO field, so descriptors of tiles in one block differ by small constants.
+constexpr uint32_t kDescHiSw128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t tile_smem_addr) {
+  return ((tile_smem_addr >> 4) & 0x3fffu) | (1u << 16);
+}
+__device__ __forceinline__ uint64_t desc_sw128_from_lo(uint32_t lo) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(kDescHiSw128));
   return d;
 }
 
@@ -146,6 +172,10 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }

@@ -19,6 +19,9 @@ namespace tpr {
 // tensor-core render path (tpr_render_tc.cu)
 int tc_rays_per_group(int Dc, int Df);
 int launch_render_tc(RenderArgs a, int bf16, int sms, int smem_optin, long long n_img, long long n_rays, cudaStream_t st);
+// warp-specialised tensor-core render path (tpr_render_ws.cu)
+int ws_rays_per_group(int Dc, int Df, int bf16);
+int launch_render_ws(RenderArgs a, int bf16, int sms, int smem_optin, long long n_img, long long n_rays, cudaStream_t st);
 
 // =======================================================================================
 // layout preparation
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(kRenderMaxThreads, 1) render_kernel(const Rend
         // ---- B: importance resampling, one warp per ray
         for (int r = warp; r < nr; r += nwarps)
           warp_resample_ray(a, sm.dep + r * S, sm.sig + r * S, sm.wa + r * S, sm.wb + r * S, sm.wc + r * S,
-                            sm.dep + r * S + Dc, g0 + r, lane);
+                            sm.dep + r * S + Dc, g0 + r, lane, a.u + (g0 + r) * Df);
         __syncthreads();
       }
       // ---- A / C: gather + decode the coarse (pass 0) or fine (pass 1) samples
@@ -615,7 +618,7 @@ int tpr_decode(const float* features, int64_t n_img, int64_t n_pts, const float*
   return launch_run_model(true, nullptr, n_img, 0, 0, decoder_packed, features, n_pts, 1.0, rgb, sigma, flags, stream);
 }
 
-size_t tpr_render_scratch_bytes(int64_t, int64_t, const TprOptions*) { return 256; }
+size_t tpr_render_scratch_bytes(int64_t, int64_t, const TprOptions*) { return 512; }
 
 // pick rays-per-CTA and threads for render_kernel
 static void render_config(int Dc, int Df, int smem_optin, int& R, int& threads, size_t& smem) {
@@ -684,13 +687,24 @@ int tpr_render(const float* planes_packed, int64_t n_img, int32_t height, int32_
     if (w < 0 || env_int("TPR_NO_COLUMN_TILES", 0)) w = 0;
     a.col_w = w;
   }
+  a.variant = env_int("TPR_WS_VARIANT", 0);
   a.dbg = env_int("TPR_PHASE_TIMING", 0) ? reinterpret_cast<long long*>(reinterpret_cast<char*>(scratch) + 64) : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   range_init_kernel<<<1, 1, 0, st>>>(a.range_enc);
   TPR_CHECK_LAUNCH("range_init_kernel");
 
   const bool use_tc = opt->flags != TPR_MLP_FFMA && tc_rays_per_group(Dc, Df) > 0 && !env_int("TPR_FORCE_FFMA", 0);
-  if (use_tc) {
+  // TPR_RENDER_IMPL: 0 = pick (default), 1 = turn-taking tensor-core kernel, 2 = warp-specialised kernel (A/B runs)
+  const int impl = env_int("TPR_RENDER_IMPL", 0);
+  bool done = false;
+  if (opt->flags != TPR_MLP_FFMA && impl != 1 && !env_int("TPR_FORCE_FFMA", 0) &&
+      ws_rays_per_group(Dc, Df, opt->flags == TPR_MLP_BF16) > 0) {
+    int rc = launch_render_ws(a, opt->flags == TPR_MLP_BF16, di.sms, di.smem_optin, n_img, n_rays, st);
+    if (rc > 0) return cuda_fail((cudaError_t)rc, "render_ws_kernel");
+    done = rc == 0;                       // < 0: does not fit shared memory, fall through
+  }
+  if (done) {
+  } else if (use_tc) {
     // decoder on the tensor cores: 3xTF32 for the fp32 parity mode, bf16 operands for the PSNR mode
     int rc = launch_render_tc(a, opt->flags == TPR_MLP_BF16, di.sms, di.smem_optin, n_img, n_rays, st);
     if (rc != 0) return cuda_fail((cudaError_t)rc, "render_tc_kernel");

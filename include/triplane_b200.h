@@ -171,6 +171,12 @@ int64_t tpr_gather_microbench(const float* buf, int64_t n_lines, int32_t ctas, i
 int64_t tpr_gather_microbench_ex(const float* buf, int64_t n_lines, int32_t ctas, int32_t threads,
                                  int32_t in_flight, int32_t iters, float* sink, void* stream);
 
+/* Issues `count` tcgen05.mma (M = 128, N = n, one K step; tf32 or bf16 operands; A from shared memory or TMEM)
+ * from one thread of one CTA; tight != 0 issues them from precomputed descriptors (count % 4 == 0).
+ * out_dev[0] = cycles spent issuing, out_dev[1] = cycles until all have completed. */
+int tpr_mma_microbench(int32_t n, int32_t bf16, int32_t a_from_tmem, int32_t count, int32_t tight, long long* out_dev,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,6 +1,8 @@
+"""Per-role wait / work cycle breakdown of CTA 0 of the render kernels (TPR_PHASE_TIMING=1 makes the kernels
+write clock64 deltas into the scratch buffer).  Usage: python profiles/phase_timing.py [fp32] [bf16]"""
 import os, sys, importlib
 os.environ['TPR_PHASE_TIMING'] = '1'
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
 pkg = importlib.import_module('g-nerf_b200')
 import bench
@@ -9,12 +11,17 @@ planes_h, c2w, K = bench.make_inputs(torch, dev, 100)
 dec = bench.make_decoder(torch, pkg, dev, 0)
 R, S = pkg.ImportanceRenderer(), pkg.RaySampler()
 planes = planes_h.to(dev); o, d = S(c2w.to(dev), K.to(dev), 128)
-names = ['setup','G0+sync','issueM1','G(t+1)','wait bar1/2','E1+sync','issueM2','pass-end wait+sigma','resample','sort','composite']
+WS = ['GATHER wait coarse_ready', 'GATHER wait fine_ready', 'GATHER wait a1_free', 'GATHER gather+publish',
+      'DECODE wait a1_full (issuer)', 'DECODE issue M1 + slot', 'DECODE wait d1_full', 'DECODE epilogue1', 'DECODE wait a2_full (issuer)',
+      'DECODE issue M2', 'DECODE wait m2_done', 'DECODE sigma readback', 'RAYS setup', 'RAYS wait csig', 'RAYS resample',
+      'RAYS wait fsig', 'RAYS sort+march', 'RAYS composite']
+TC = ['setup', 'G0+sync', 'issueM1', 'G(t+1)', 'wait bar1/2', 'E1+sync', 'issueM2', 'pass-end wait+sigma', 'resample', 'sort', 'composite']
 for mode in sys.argv[1:] or ['fp32']:
     opts = dict(bench.OPTS, decoder_precision=mode)
     for _ in range(3): R(planes, dec, o, d, opts)
     torch.cuda.synchronize()
-    t = R.last_scratch[64:64+16*8].view(torch.int64).cpu().numpy()
-    tot = t.sum(); ngroups = 16384*8/8/148
-    print(mode, 'CTA0 total cycles', tot, 'per group', int(tot/ngroups))
-    for n, v in zip(names, t): print(f'  {n:22s} {v/tot*100:5.1f}%  {int(v/ngroups):6d} cyc/group')
+    t = R.last_scratch[64:64 + 24 * 8].view(torch.int64).cpu().numpy()
+    ngroups = 16384 * 8 / 8 / 148
+    names = TC if os.environ.get('TPR_RENDER_IMPL') == '1' else WS
+    print(mode, 'CTA0 cycles per group (', int(ngroups), 'groups )')
+    for n, v in zip(names, t): print(f'  {n:32s} {int(v / ngroups):7d}')
