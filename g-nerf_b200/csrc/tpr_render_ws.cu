@@ -148,9 +148,14 @@ __device__ __forceinline__ Geom group_geom(const RenderArgs& a, long long grp, i
 //         at a time: tpr_gather_microbench (profiles/) shows that on B200 a shallow queue per thread and many
 //         warps sustains more random-line bandwidth than twelve loads in flight per thread.
 // ---------------------------------------------------------------------------------------------------------
+// Tap table entry for one (sample, plane): the four texels as offsets in 16-byte units from the image's plane
+// block (plane offset included) and the four bilinear weights, each stored twice so that a weight is directly the
+// {w, w} operand of a packed FFMA2.
+struct __align__(16) Tap2 { uint32_t off[4]; float w2[8]; };
+
 template <int MODE>
 __device__ __forceinline__ void gather_tile(const RenderArgs& a, float* a1_hi, float* a1_lo, const float* __restrict__ img,
-                                            const Ctx& cx, TapEntry* tw, int nr, int Dx, int off, int S, int t, int dpt_shift,
+                                            const Ctx& cx, Tap2* tw, int nr, int Dx, int off, int S, int t, int dpt_shift,
                                             int warp, int lane) {
   const int grp = lane >> 3, sub = lane & 7;
   const int dpt = 1 << dpt_shift;
@@ -168,30 +173,40 @@ __device__ __forceinline__ void gather_tile(const RenderArgs& a, float* a1_hi, f
       Taps tp;
       plane_taps(p == 2 ? pz : px, p == 0 ? py : (p == 1 ? pz : px), a.H, a.W, tp);   // (x,y) (x,z) (z,x)
       const int po = p * a.H * a.W * kC;
-      *reinterpret_cast<int4*>(tw[lane].off) = make_int4(tp.off[0] + po, tp.off[1] + po, tp.off[2] + po, tp.off[3] + po);
-      *reinterpret_cast<float4*>(tw[lane].w) = make_float4(tp.w[0], tp.w[1], tp.w[2], tp.w[3]);
+      // float offsets are multiples of 32: >> 2 gives 16-byte units
+      *reinterpret_cast<uint4*>(tw[lane].off) = make_uint4((unsigned)(tp.off[0] + po) >> 2, (unsigned)(tp.off[1] + po) >> 2,
+                                                           (unsigned)(tp.off[2] + po) >> 2, (unsigned)(tp.off[3] + po) >> 2);
+      *reinterpret_cast<float4*>(tw[lane].w2) = make_float4(tp.w[0], tp.w[0], tp.w[1], tp.w[1]);
+      *reinterpret_cast<float4*>(tw[lane].w2 + 4) = make_float4(tp.w[2], tp.w[2], tp.w[3], tp.w[3]);
     }
   }
   __syncwarp();
-  const float* img_sub = img + sub * 4;
+  // this lane's four channels of every texel; opaque to the compiler so that an address is one IMAD.WIDE
+  const ulonglong2* base = reinterpret_cast<const ulonglong2*>(img) + sub;
+  asm volatile("" : "+l"(base));
 #pragma unroll 1
   for (int rd = 0; rd < 2; ++rd) {
     const int s = rd * 4 + grp;
     const int row = warp * 8 + s;
     const int r = row >> dpt_shift, di = t * dpt + (row & (dpt - 1));
     if (r < nr && di < Dx) {
-      const TapEntry* te = tw + s * 3;
-      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+      const Tap2* te = tw + s * 3;
+      uint64_t f01 = 0ull, f23 = 0ull;           // channels (0,1) and (2,3) of this lane, summed over the planes
+      // one plane (four texels) at a time: tpr_gather_microbench shows that a shallow queue per thread and many
+      // warps sustains more random-line bandwidth than twelve loads in flight per thread
 #pragma unroll 1
       for (int p = 0; p < 3; ++p) {
-        const int4 o = *reinterpret_cast<const int4*>(te[p].off);
-        const float4 w = *reinterpret_cast<const float4*>(te[p].w);
-        const float4 v0 = ldg128(img_sub + (unsigned)o.x), v1 = ldg128(img_sub + (unsigned)o.y);
-        const float4 v2 = ldg128(img_sub + (unsigned)o.z), v3 = ldg128(img_sub + (unsigned)o.w);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        fma4(acc, w.x, v0); fma4(acc, w.y, v1); fma4(acc, w.z, v2); fma4(acc, w.w, v3);
-        f.x += acc.x; f.y += acc.y; f.z += acc.z; f.w += acc.w;
+        const uint4 o = *reinterpret_cast<const uint4*>(te[p].off);
+        const ulonglong2 wa = *reinterpret_cast<const ulonglong2*>(te[p].w2), wb = *reinterpret_cast<const ulonglong2*>(te[p].w2 + 4);
+        const ulonglong2 v0 = __ldg(base + o.x), v1 = __ldg(base + o.y), v2 = __ldg(base + o.z), v3 = __ldg(base + o.w);
+        uint64_t a01 = fma2(wa.x, v0.x, 0ull), a23 = fma2(wa.x, v0.y, 0ull);
+        a01 = fma2(wa.y, v1.x, a01); a23 = fma2(wa.y, v1.y, a23);
+        a01 = fma2(wb.x, v2.x, a01); a23 = fma2(wb.x, v2.y, a23);
+        a01 = fma2(wb.y, v3.x, a01); a23 = fma2(wb.y, v3.y, a23);
+        f01 = add2(f01, a01); f23 = add2(f23, a23);
       }
+      float4 f;
+      unpack2(f01, f.x, f.y); unpack2(f23, f.z, f.w);
       if (MODE == 1) {
         uint2 pk = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
         uint8_t* dst = reinterpret_cast<uint8_t*>(a1_hi) + row * 128 + ((((sub >> 1) ^ (row & 7)) << 4) | ((sub & 1) << 3));
@@ -309,13 +324,13 @@ __device__ __forceinline__ float epilogue1(const Tiles<MODE>& tl, uint32_t tmem,
 // ---------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
-template <int MODE, int E>
+template <int MODE, int E, bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   Tiles<MODE>& tl = *reinterpret_cast<Tiles<MODE>*>(base);
-  TapEntry* taps = reinterpret_cast<TapEntry*>(base + sizeof(Tiles<MODE>));
-  float* fl = reinterpret_cast<float*>(base + sizeof(Tiles<MODE>) + sizeof(TapEntry) * kGatherWarps * 24);
+  Tap2* taps = reinterpret_cast<Tap2*>(base + sizeof(Tiles<MODE>));
+  float* fl = reinterpret_cast<float*>(base + sizeof(Tiles<MODE>) + sizeof(Tap2) * kGatherWarps * 24);
   const int R = a.R, Dc = a.Dc, Df = a.Df, S = Dc + Df;
   const int dpt_shift = R == 8 ? 4 : 5, dpt = 1 << dpt_shift;
   // contexts: dep [R*S], sig [R*S], u [R*Df], ray [R*8]
@@ -338,9 +353,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
   __shared__ int slot_tab[kCtx][16];
   // TPR_PHASE_TIMING=1: cycles CTA 0 spends in each wait / work section of each role (one lane per role)
   __shared__ long long prof[24];
-  const bool profiling = a.dbg != nullptr && blockIdx.x == 0;
-#define PROF_T0() long long pt0_ = profiling ? clock64() : 0
-#define PROF_ADD(i, cond) do { if (profiling && (cond)) { const long long now_ = clock64(); prof[i] += now_ - pt0_; pt0_ = now_; } } while (0)
+  const bool profiling = PROF && a.dbg != nullptr && blockIdx.x == 0;
+#define PROF_T0() long long pt0_ = (PROF && profiling) ? clock64() : 0
+#define PROF_ADD(i, cond) do { if (PROF && profiling && (cond)) { const long long now_ = clock64(); prof[i] += now_ - pt0_; pt0_ = now_; } } while (0)
   // the warp index goes through a shuffle so that the compiler knows it is warp-uniform: everything the MMA issuer
   // derives from role-dependent control flow (buffer index, slot, descriptors) then lives in uniform registers and a
   // tcgen05.mma costs one or two instructions instead of an elect/broadcast loop
@@ -375,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
 
   if (warp < kGatherWarps) {
     // ====================================== GATHER ======================================
-    TapEntry* tw = taps + warp * 24;
+    Tap2* tw = taps + warp * 24;
     int b = 0; uint32_t ph = 0;                      // A1 buffer ring position / phase
     for (int step = 0; step <= G; ++step) {
 #pragma unroll 1
@@ -643,19 +658,20 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
     atomicMax(a.range_enc + 1, range_sm[1]);
   }
   if (warp == 0) { tcgen05_fence_after(); tmem_dealloc(tmem, 512); }
-  if (profiling && tid < 24) a.dbg[tid] = prof[tid];
+  if (PROF && profiling && tid < 24) a.dbg[tid] = prof[tid];
 }
 
 template <int MODE>
 static size_t smem_bytes(int R, int S, int Df) {
-  return 1024 + sizeof(Tiles<MODE>) + sizeof(TapEntry) * kGatherWarps * 24 +
+  return 1024 + sizeof(Tiles<MODE>) + sizeof(Tap2) * kGatherWarps * 24 +
          sizeof(float) * ((size_t)kCtx * (2 * R * S + R * Df + R * 8) + (size_t)3 * R * S + R + 8);
 }
 
 typedef void (*Kernel)(const RenderArgs);
 template <int MODE>
-static Kernel pick_kernel(int S) {
-  return S <= 64 ? render_ws_kernel<MODE, 2> : S <= 128 ? render_ws_kernel<MODE, 4> : render_ws_kernel<MODE, 8>;
+static Kernel pick_kernel(int S, bool prof) {
+  if (prof && S > 64 && S <= 128) return render_ws_kernel<MODE, 4, true>;      // TPR_PHASE_TIMING=1 (profiles/phase_timing.py)
+  return S <= 64 ? render_ws_kernel<MODE, 2, false> : S <= 128 ? render_ws_kernel<MODE, 4, false> : render_ws_kernel<MODE, 8, false>;
 }
 
 }  // namespace ws
@@ -680,7 +696,7 @@ int launch_render_ws(RenderArgs a, int bf16, int sms, int smem_optin, long long 
   if (a.col_w > 0 && (a.col_w % a.R != 0 || (long long)a.col_w * a.col_w != n_rays)) a.col_w = 0;
   a.tiles_per_img = (n_rays + a.R - 1) / a.R;
   a.n_tiles = a.tiles_per_img * n_img;
-  ws::Kernel k = bf16 ? ws::pick_kernel<1>(S) : ws::pick_kernel<0>(S);
+  ws::Kernel k = bf16 ? ws::pick_kernel<1>(S, a.dbg != nullptr) : ws::pick_kernel<0>(S, a.dbg != nullptr);
   const size_t smem = bf16 ? ws::smem_bytes<1>(a.R, S, a.Df) : ws::smem_bytes<0>(a.R, S, a.Df);
   cudaFuncAttributes fa;
   cudaError_t e = cudaFuncGetAttributes(&fa, k);
