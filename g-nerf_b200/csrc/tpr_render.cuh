@@ -60,7 +60,8 @@ __device__ __forceinline__ float coarse_depth(const RenderArgs& a, int k, float 
 // no shuffles, so it overlaps with itself far better than the bitonic network's dependent compare-exchange chain
 // (the ray warps are latency bound) -- and scatters (depth, sigma, index) to that rank.  Two equal depths would
 // get the same rank; a rank-sum check detects that and falls back to the network with its index tie-break.
-template <int E, bool kScatter>
+// ER: rows of 32 elements the rank count looks at (ceil(S/32) <= ER <= E; E itself must be a power of two for the network).
+template <int E, bool kScatter, int ER = E>
 __device__ __forceinline__ void warp_sort_and_weights(const float* z, const float* sg, float* om, int* oi, int S, int lane,
                                                       float& wsum_out, float& dnum_out, float& mn, float& mx,
                                                       float* tmp = nullptr) {
@@ -69,34 +70,34 @@ __device__ __forceinline__ void warp_sort_and_weights(const float* z, const floa
   bool ranked = false;
   if (tmp != nullptr) {
     // element p = e*32 + lane (strided: conflict-free reads and writes)
-    float ze[E]; int cnt[E];
+    float ze[ER]; int cnt[ER];
 #pragma unroll
-    for (int e = 0; e < E; ++e) { const int p = e * 32 + lane; ze[e] = p < S ? z[p] : __int_as_float(0x7f800000); cnt[e] = 0; }
+    for (int e = 0; e < ER; ++e) { const int p = e * 32 + lane; ze[e] = p < S ? z[p] : __int_as_float(0x7f800000); cnt[e] = 0; }
     int j = 0;
     if ((reinterpret_cast<uintptr_t>(z) & 15) == 0) {
 #pragma unroll 2
       for (; j + 4 <= S; j += 4) {
         const float4 v = *reinterpret_cast<const float4*>(z + j);
 #pragma unroll
-        for (int e = 0; e < E; ++e)
+        for (int e = 0; e < ER; ++e)
           cnt[e] += (int)(v.x < ze[e]) + (int)(v.y < ze[e]) + (int)(v.z < ze[e]) + (int)(v.w < ze[e]);
       }
     }
     for (; j < S; ++j) {
       const float v = z[j];
 #pragma unroll
-      for (int e = 0; e < E; ++e) cnt[e] += (int)(v < ze[e]);
+      for (int e = 0; e < ER; ++e) cnt[e] += (int)(v < ze[e]);
     }
     int rsum = 0;
 #pragma unroll
-    for (int e = 0; e < E; ++e) if (e * 32 + lane < S) rsum += cnt[e];
+    for (int e = 0; e < ER; ++e) if (e * 32 + lane < S) rsum += cnt[e];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(kFull, rsum, o);
     ranked = rsum == S * (S - 1) / 2;            // a tie (or a NaN) makes the sum fall short
     if (ranked) {
       float* zs = tmp; float* ss = tmp + S; int* is = reinterpret_cast<int*>(om);
 #pragma unroll
-      for (int e = 0; e < E; ++e) {
+      for (int e = 0; e < ER; ++e) {
         const int p = e * 32 + lane;
         if (p < S) { zs[cnt[e]] = ze[e]; ss[cnt[e]] = sg[p]; is[cnt[e]] = p; }
       }

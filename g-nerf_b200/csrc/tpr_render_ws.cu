@@ -126,18 +126,23 @@ __device__ void stage_weights(const float* __restrict__ dec, Tiles<MODE>& tl) {
 // per-group shared-memory context
 struct Ctx { float* dep; float* sig; float* u; float* ray; };
 
-struct Geom { long long n, ray0, rstride; int nr; };
+struct Geom { long long ray0; int n, rstride, nr; };
 // Which rays form group `grp`.  Column mode (rays are a col_w-wide image, x fastest, VR/ray_sampler.py:44):
 // R vertically adjacent pixels of one image column -- they nearly share their (x,z) footprint, i.e. their taps on
-// two of the three planes (VR/renderer.py:29-37).  Otherwise R consecutive rays.
-__device__ __forceinline__ Geom group_geom(const RenderArgs& a, long long grp, int R) {
+// two of the three planes (VR/renderer.py:29-37).  Otherwise R consecutive rays.  32-bit arithmetic: the launcher
+// checks that the group count and the rays per image fit an int (64-bit divisions cost ~100 instructions each and
+// every role calls this once per job).
+__device__ __forceinline__ Geom group_geom(const RenderArgs& a, unsigned grp, int R) {
   Geom g;
-  g.n = grp / a.tiles_per_img;
-  const long long gi = grp - g.n * a.tiles_per_img;
+  const unsigned tpi = (unsigned)a.tiles_per_img;
+  const unsigned n = grp / tpi, gi = grp - n * tpi;
   const bool colm = a.col_w > 0;
-  g.ray0 = g.n * a.rays_per_img + (colm ? (gi / a.col_w) * R * a.col_w + gi % a.col_w : gi * R);
-  g.rstride = colm ? a.col_w : 1;
-  g.nr = colm ? R : (int)min((long long)R, a.rays_per_img - gi * R);
+  const unsigned cw = colm ? (unsigned)a.col_w : 1u;
+  const unsigned gy = gi / cw, gx = gi - gy * cw;
+  g.n = (int)n;
+  g.ray0 = (long long)n * a.rays_per_img + (colm ? (long long)(gy * R * cw + gx) : (long long)gi * R);
+  g.rstride = (int)cw;
+  g.nr = colm ? R : (int)min((long long)R, a.rays_per_img - (long long)gi * R);
   return g;
 }
 
@@ -279,7 +284,8 @@ __device__ __forceinline__ void issue_layer2(uint32_t dlo, uint32_t tmem, int sl
 // Returns this thread's part of sigma = w2s . hidden over those columns (fp32 FFMA, training/triplane.py:135).
 template <int MODE>
 __device__ __forceinline__ float epilogue1(const Tiles<MODE>& tl, uint32_t tmem, uint32_t lane_base, int h) {
-  float sg = 0.0f;
+  uint64_t sg2 = 0ull;
+  const uint64_t kOne2 = pack2(1.0f, 1.0f);
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     const int col = 32 * h + 16 * c;
@@ -288,29 +294,40 @@ __device__ __forceinline__ float epilogue1(const Tiles<MODE>& tl, uint32_t tmem,
     tmem_wait_ld();
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      float act[8];
+      uint64_t act2[4];                        // four packed pairs of activations
 #pragma unroll
       for (int i4 = 0; i4 < 2; ++i4) {
         const int o = 8 * half + 4 * i4;
-        const float4 b = *reinterpret_cast<const float4*>(tl.bias1 + col + o);
-        const float4 w = *reinterpret_cast<const float4*>(tl.w2s + col + o);
-        act[4 * i4 + 0] = softplus_log2(__uint_as_float(r[o + 0]) + b.x); sg = fmaf(act[4 * i4 + 0], w.x, sg);
-        act[4 * i4 + 1] = softplus_log2(__uint_as_float(r[o + 1]) + b.y); sg = fmaf(act[4 * i4 + 1], w.y, sg);
-        act[4 * i4 + 2] = softplus_log2(__uint_as_float(r[o + 2]) + b.z); sg = fmaf(act[4 * i4 + 2], w.z, sg);
-        act[4 * i4 + 3] = softplus_log2(__uint_as_float(r[o + 3]) + b.w); sg = fmaf(act[4 * i4 + 3], w.w, sg);
+        const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(tl.bias1 + col + o);
+        const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(tl.w2s + col + o);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          // softplus in the log2 domain on a pair: x' = D1 + b1', y = x' > 20 log2e ? x' : lg2(1 + 2^x')
+          const uint64_t xs2 = add2(pack2(__uint_as_float(r[o + 2 * h2]), __uint_as_float(r[o + 2 * h2 + 1])), h2 == 0 ? b.x : b.y);
+          float x0, x1, y0, y1;
+          unpack2(xs2, x0, x1);
+          unpack2(add2(pack2(ex2_fast(x0), ex2_fast(x1)), kOne2), y0, y1);
+          y0 = x0 > 20.0f * kLog2e ? x0 : lg2_fast(y0);
+          y1 = x1 > 20.0f * kLog2e ? x1 : lg2_fast(y1);
+          act2[2 * i4 + h2] = pack2(y0, y1);
+          sg2 = fma2(act2[2 * i4 + h2], h2 == 0 ? w.x : w.y, sg2);
+        }
       }
       if (MODE == 1) {
         uint32_t pk[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) pk[i] = pack_bf16(act[2 * i], act[2 * i + 1]);
+        for (int i = 0; i < 4; ++i) { float y0, y1; unpack2(act2[i], y0, y1); pk[i] = pack_bf16(y0, y1); }
         tmem_st4(tmem + Cols<MODE>::a2hi + lane_base + ((col + 8 * half) >> 1), pk);
       } else {
         uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float x, y;
-          split_tf32(act[i], x, y);
-          hi[i] = __float_as_uint(x); lo[i] = __float_as_uint(y);
+        for (int i = 0; i < 4; ++i) {
+          float y0, y1, l0, l1;
+          unpack2(act2[i], y0, y1);
+          hi[2 * i] = (__float_as_uint(y0) + 0x1000u) & 0xffffe000u;          // split_tf32, the subtraction packed
+          hi[2 * i + 1] = (__float_as_uint(y1) + 0x1000u) & 0xffffe000u;
+          unpack2(sub2(act2[i], pack2(__uint_as_float(hi[2 * i]), __uint_as_float(hi[2 * i + 1]))), l0, l1);
+          lo[2 * i] = __float_as_uint(l0); lo[2 * i + 1] = __float_as_uint(l1);
         }
         tmem_st8(tmem + Cols<MODE>::a2hi + lane_base + col + 8 * half, hi);
         tmem_st8(tmem + Cols<MODE>::a2lo + lane_base + col + 8 * half, lo);
@@ -318,13 +335,15 @@ __device__ __forceinline__ float epilogue1(const Tiles<MODE>& tl, uint32_t tmem,
     }
   }
   tmem_wait_st();
-  return sg;
+  float s0, s1;
+  unpack2(sg2, s0, s1);
+  return s0 + s1;
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
-template <int MODE, int E, bool PROF>
+template <int MODE, int E, int ER, bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -374,6 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(&tmem_base_sm, 512); tmem_relinquish(); }
+  for (int i = tid; i < (int)(sizeof(tl.a1) / 16); i += kThreads) reinterpret_cast<float4*>(tl.a1)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   stage_weights<MODE>(a.dec, tl);
   fence_proxy_async_smem();
   tcgen05_fence_before();
@@ -399,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
         int gi;
         if (pass == 0) { if (step >= G) continue; gi = step; }
         else { if (step < 1 || nf == 0) continue; gi = step - 1; }
-        const Geom gg = group_geom(a, blockIdx.x + (long long)gi * gridDim.x, R);
+        const Geom gg = group_geom(a, blockIdx.x + (unsigned)gi * gridDim.x, R);
         const Ctx cx = ctx_of(gi);
         const uint32_t cpar = (uint32_t)(gi >> 2) & 1u;
         PROF_T0();
@@ -436,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
         int gi;
         if (pass == 0) { if (step >= G) continue; gi = step; }
         else { if (step < 1 || nf == 0) continue; gi = step - 1; }
-        const Geom gg = group_geom(a, blockIdx.x + (long long)gi * gridDim.x, R);
+        const Geom gg = group_geom(a, blockIdx.x + (unsigned)gi * gridDim.x, R);
         const Ctx cx = ctx_of(gi);
         const int T = pass == 0 ? nc : nf, Dx = pass == 0 ? Dc : Df, off = pass == 0 ? 0 : Dc;
 #pragma unroll 1
@@ -521,33 +541,48 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
 #define RAY_SYNC() named_bar_sync(2, kRayThreads)
 
     const bool pl = rtid == 0;
-    auto setup = [&](int gi) {
-      // rays, coarse depths (VR/renderer.py:169-192) and the group's uniform draws into its context
-      PROF_T0();
-      const Geom gg = group_geom(a, blockIdx.x + (long long)gi * gridDim.x, R);
-      const Ctx cx = ctx_of(gi);
+    // The group's per-ray inputs (6 ray floats, Dc jitter draws, Df uniform draws per ray) are DRAM reads with
+    // nothing to overlap them inside setup, so they are fetched with cp.async into a staging area one step ahead;
+    // each thread later converts exactly the elements it copied itself (no barrier needed, only wait_group).
+    float* stg_jit = rayw + R; float* stg_u = stg_jit + R * Dc; float* stg_ray = stg_u + R * Df;
+    auto prefetch = [&](int gi) {
+      const Geom gg = group_geom(a, blockIdx.x + (unsigned)gi * gridDim.x, R);
       if (rtid < gg.nr * 6) {
         const int r = rtid / 6, c = rtid - r * 6;
         const long long g = gg.ray0 + (long long)r * gg.rstride;
-        cx.ray[r * 8 + c] = c < 3 ? __ldg(a.origins + g * 3 + c) : __ldg(a.dirs + g * 3 + c - 3);
+        cp_async4(stg_ray + rtid, c < 3 ? a.origins + g * 3 + c : a.dirs + g * 3 + c - 3);
       }
+      for (int s = rtid; s < gg.nr * Dc; s += kRayThreads) {
+        const int r = s / Dc, k = s - r * Dc;
+        cp_async4(stg_jit + s, a.jitter + (gg.ray0 + (long long)r * gg.rstride) * Dc + k);
+      }
+      for (int s = rtid; s < gg.nr * Df; s += kRayThreads) {
+        const int r = s / Df, k = s - r * Df;
+        cp_async4(stg_u + s, a.u + (gg.ray0 + (long long)r * gg.rstride) * Df + k);
+      }
+      cp_async_commit();
+    };
+    auto setup = [&](int gi) {
+      // rays, coarse depths (VR/renderer.py:169-192) and the group's uniform draws into its context
+      PROF_T0();
+      const Geom gg = group_geom(a, blockIdx.x + (unsigned)gi * gridDim.x, R);
+      const Ctx cx = ctx_of(gi);
+      cp_async_wait_all();
+      if (rtid < gg.nr * 6) { const int r = rtid / 6; cx.ray[r * 8 + (rtid - r * 6)] = stg_ray[rtid]; }
       for (int s = rtid; s < gg.nr * Dc; s += kRayThreads) {
         const int r = s / Dc, k = s - r * Dc;
         const long long g = gg.ray0 + (long long)r * gg.rstride;
         const float lo = per_ray ? __ldg(a.rs + g) : a.ray_start, hi = per_ray ? __ldg(a.re + g) : a.ray_end;
-        cx.dep[r * S + k] = coarse_depth(a, k, __ldg(a.jitter + g * Dc + k), lo, hi, per_ray);
+        cx.dep[r * S + k] = coarse_depth(a, k, stg_jit[s], lo, hi, per_ray);
       }
-      for (int s = rtid; s < gg.nr * Df; s += kRayThreads) {
-        const int r = s / Df, k = s - r * Df;
-        cx.u[s] = __ldg(a.u + (gg.ray0 + (long long)r * gg.rstride) * Df + k);
-      }
+      for (int s = rtid; s < gg.nr * Df; s += kRayThreads) cx.u[s] = stg_u[s];
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.coarse_ready[gi & 3]);
       PROF_ADD(12, pl);
     };
 
     auto resample = [&](int gi) {
-      const Geom gg = group_geom(a, blockIdx.x + (long long)gi * gridDim.x, R);
+      const Geom gg = group_geom(a, blockIdx.x + (unsigned)gi * gridDim.x, R);
       const Ctx cx = ctx_of(gi);
       PROF_T0();
       mbar_wait_parked(&bars.csig_ready[gi & 3], (uint32_t)(gi >> 2) & 1u);
@@ -562,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
     };
 
     auto sort_composite = [&](int gi) {
-      const Geom gg = group_geom(a, blockIdx.x + (long long)gi * gridDim.x, R);
+      const Geom gg = group_geom(a, blockIdx.x + (unsigned)gi * gridDim.x, R);
       const Ctx cx = ctx_of(gi);
       PROF_T0();
       mbar_wait_parked(nf > 0 ? &bars.fsig_ready[gi & 3] : &bars.csig_ready[gi & 3], (uint32_t)(gi >> 2) & 1u);
@@ -570,7 +605,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
       // ---- sort + final march: omega per sample (scattered to original order), depth, weight sum
       for (int r = rw; r < gg.nr; r += kRayWarps) {
         float wsum, dnum;
-        warp_sort_and_weights<E, true>(cx.dep + r * S, cx.sig + r * S, wa + r * S, nullptr, S, lane, wsum, dnum, mn, mx,
+        warp_sort_and_weights<E, true, ER>(cx.dep + r * S, cx.sig + r * S, wa + r * S, nullptr, S, lane, wsum, dnum, mn, mx,
                                        wb + r * 2 * S);          // wb and wc are contiguous: 2*S floats per ray
         if (lane == 0) {
           const long long g = gg.ray0 + (long long)r * gg.rstride;
@@ -584,9 +619,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
       // ---- composite: ray warp (q, hc) sums channels [16hc, 16hc+16) over the samples held by its lanes
       tcgen05_fence_after();
       const int row = q * 32 + lane, r = row >> dpt_shift, i = row & (dpt - 1);
-      float acc[16];
+      uint64_t acc2[8];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
+      for (int c = 0; c < 8; ++c) acc2[c] = 0ull;
+      const uint64_t kOne2 = pack2(1.0f, 1.0f), kScale2 = pack2(1.002f, 1.002f), kShift2 = pack2(-0.001f, -0.001f);
 #pragma unroll 1
       for (int sl = 0; sl < nc + nf; ++sl) {
         const bool fine = sl >= nc;
@@ -598,15 +634,29 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
         uint32_t v[16];
         tmem_ld16(tmem + Cols<MODE>::slots + slot * kSlotCols + lane_base + 16 * hc, v);
         tmem_wait_ld();
+        // rows outside the group (om = 0) still hold finite values: the operand tiles start zeroed and only ever
+        // receive finite features, so no select is needed to keep NaNs out of the sum
+        const uint64_t om2 = pack2(om, om);
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
-          const float4 bz = *reinterpret_cast<const float4*>(tl.bias2 + 16 * hc + 4 * c4);
-          const float bb[4] = {bz.x, bz.y, bz.z, bz.w};
+          const ulonglong2 bz = *reinterpret_cast<const ulonglong2*>(tl.bias2 + 16 * hc + 4 * c4);
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            acc[4 * c4 + c] = valid ? fmaf(om, colour_act_neglog2(__uint_as_float(v[4 * c4 + c]) + bb[c]), acc[4 * c4 + c]) : acc[4 * c4 + c];
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int c = 4 * c4 + 2 * h2;
+            float z0, z1;
+            unpack2(add2(pack2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), h2 == 0 ? bz.x : bz.y), z0, z1);
+            // sigmoid(x) * 1.002 - 0.001 with z = -x * log2e (training/triplane.py:134)
+            const uint64_t den = add2(pack2(ex2_fast(z0), ex2_fast(z1)), kOne2);
+            float d0, d1;
+            unpack2(den, d0, d1);
+            const uint64_t col = fma2(pack2(rcp_fast(d0), rcp_fast(d1)), kScale2, kShift2);
+            acc2[c >> 1] = fma2(om2, col, acc2[c >> 1]);
+          }
         }
       }
+      float acc[16];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) unpack2(acc2[c], acc[2 * c], acc[2 * c + 1]);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) { __threadfence_block(); atomicAdd(&freed_warps, 1u); }   // this warp is done with the group's slots
@@ -636,11 +686,12 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
       PROF_ADD(17, pl);
     };
 
-    setup(0);
-    if (G > 1) setup(1);
+    prefetch(0); setup(0);
+    if (G > 1) { prefetch(1); setup(1); }
+    if (G > 2) prefetch(2);
     for (int g = 0; g < G; ++g) {
       if (nf > 0) resample(g);
-      if (g + 2 < G) setup(g + 2);
+      if (g + 2 < G) { setup(g + 2); if (g + 3 < G) prefetch(g + 3); }
       if (nf > 0) { if (g >= 1) sort_composite(g - 1); }
       else sort_composite(g);
     }
@@ -664,14 +715,15 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
 template <int MODE>
 static size_t smem_bytes(int R, int S, int Df) {
   return 1024 + sizeof(Tiles<MODE>) + sizeof(Tap2) * kGatherWarps * 24 +
-         sizeof(float) * ((size_t)kCtx * (2 * R * S + R * Df + R * 8) + (size_t)3 * R * S + R + 8);
+         sizeof(float) * ((size_t)kCtx * (2 * R * S + R * Df + R * 8) + (size_t)3 * R * S + R + (size_t)R * S + R * 8 + 8);
 }
 
 typedef void (*Kernel)(const RenderArgs);
 template <int MODE>
 static Kernel pick_kernel(int S, bool prof) {
-  if (prof && S > 64 && S <= 128) return render_ws_kernel<MODE, 4, true>;      // TPR_PHASE_TIMING=1 (profiles/phase_timing.py)
-  return S <= 64 ? render_ws_kernel<MODE, 2, false> : S <= 128 ? render_ws_kernel<MODE, 4, false> : render_ws_kernel<MODE, 8, false>;
+  if (prof && S > 64 && S <= 96) return render_ws_kernel<MODE, 4, 3, true>;      // TPR_PHASE_TIMING=1 (profiles/phase_timing.py)
+  return S <= 64 ? render_ws_kernel<MODE, 2, 2, false> : S <= 96 ? render_ws_kernel<MODE, 4, 3, false>
+       : S <= 128 ? render_ws_kernel<MODE, 4, 4, false> : render_ws_kernel<MODE, 8, 8, false>;
 }
 
 }  // namespace ws
@@ -696,6 +748,7 @@ int launch_render_ws(RenderArgs a, int bf16, int sms, int smem_optin, long long 
   if (a.col_w > 0 && (a.col_w % a.R != 0 || (long long)a.col_w * a.col_w != n_rays)) a.col_w = 0;
   a.tiles_per_img = (n_rays + a.R - 1) / a.R;
   a.n_tiles = a.tiles_per_img * n_img;
+  if (a.n_tiles >= (1ll << 31) || n_rays >= (1ll << 31)) return -1;      // group_geom works in 32 bits
   ws::Kernel k = bf16 ? ws::pick_kernel<1>(S, a.dbg != nullptr) : ws::pick_kernel<0>(S, a.dbg != nullptr);
   const size_t smem = bf16 ? ws::smem_bytes<1>(a.R, S, a.Df) : ws::smem_bytes<0>(a.R, S, a.Df);
   cudaFuncAttributes fa;
