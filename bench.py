@@ -81,10 +81,10 @@ class ClockSampler:
 # synthetic workload
 # ----------------------------------------------------------------------------------------------
 def make_inputs(torch, dev, seed, n_img=N_IMG, res=RES):
-    from oracle import triplane_oracle as O         # only for the camera orbit constants (host-side numpy)
+    cams = importlib.import_module('g-nerf_b200.camera_utils')
     g = torch.Generator(device='cpu').manual_seed(seed)
     planes = torch.randn((n_img, 3, 32, PLANE_RES, PLANE_RES), generator=g, dtype=torch.float32)
-    c2w, K = O.orbit_cameras(n_img)
+    c2w, K = cams.orbit_cameras(n_img)
     return planes, torch.from_numpy(c2w), torch.from_numpy(K)
 
 
@@ -288,7 +288,7 @@ def main():
                        'step': 'ImportanceRenderer.forward incl. plane repack, decoder pack, both torch.rand draws'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                          'frac': achieved / pk['hbm_gbs'], 'traffic': None, 'peak_kind': pk_kind,
-                         'kernel': ('render_kernel' if args.mode == 'fp32_ffma' else 'render_tc_kernel') + ' (tpr_render: +2 helper launches of ~2 us)', 'kernel_ms': kern_ms,
+                         'kernel': ('render_kernel' if args.mode == 'fp32_ffma' else 'render_ws_kernel') + ' (tpr_render: +2 helper launches of ~2 us)', 'kernel_ms': kern_ms,
                          'algorithmic_bytes_per_launch': samples_per_step * BYTES_PER_SAMPLE},
             'e2e': {'value': world * samples_per_step / (e2e_ms * 1e-3), 'unit': METRIC, 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
