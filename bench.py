@@ -238,20 +238,22 @@ def main():
     clocks = sampler_clk.stop() if rank == 0 else None
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
 
-    # ---- end to end: pinned host inputs -> device -> forward -> host, every step
+    # ---- end to end: the forward with HOST buffers (ImportanceRenderer.forward_host -> tpr_render_host): every step
+    # copies that step's planes and rays from pinned host memory and reads rgb / depth / weight sums back to the host
     planes_pin, o_pin, d_pin = planes_h.pin_memory(), origins.cpu().pin_memory(), dirs.cpu().pin_memory()
-    out_pin = [torch.empty((N_IMG, m, c), dtype=torch.float32).pin_memory() for c in (32, 1, 1)]
+    out_pin = tuple(torch.empty((N_IMG, m, c), dtype=torch.float32).pin_memory() for c in (32, 1, 1))
     h2d = planes_pin.numel() * 4 + o_pin.numel() * 4 + d_pin.numel() * 4
     d2h = sum(t.numel() * 4 for t in out_pin)
 
     def e2e_step():
+        if world == 1:
+            renderer.forward_host(planes_pin, decoder, o_pin, d_pin, opts, out=out_pin)
+            return
+        # N > 1: the depth clamp needs the all-reduced range before depth can leave the device
         p = planes_pin.to(dev, non_blocking=True)
         o = o_pin.to(dev, non_blocking=True)
         d = d_pin.to(dev, non_blocking=True)
-        if world > 1:
-            outs = pkg.parallel.render_sharded(renderer, p, decoder, o, d, opts, gather=False)
-        else:
-            outs = renderer(p, decoder, o, d, opts)
+        outs = pkg.parallel.render_sharded(renderer, p, decoder, o, d, opts, gather=False)
         for dst, src in zip(out_pin, outs):
             dst.copy_(src, non_blocking=True)
 
@@ -292,7 +294,9 @@ def main():
                          'algorithmic_bytes_per_launch': samples_per_step * BYTES_PER_SAMPLE},
             'e2e': {'value': world * samples_per_step / (e2e_ms * 1e-3), 'unit': METRIC, 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
-            'gpu_launches': 5 * args.steps,
+            'gpu_launches': 5 * args.steps,                    # pack_planes, pack_decoder, range_init, render_ws, finish
+            'e2e_api': 'ImportanceRenderer.forward_host (tpr_render_host: per-image H2D / repack+render / D2H pipeline)'
+            if world == 1 else 'pinned .to(device) + render_sharded + pinned copy back',
             'clocks': clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

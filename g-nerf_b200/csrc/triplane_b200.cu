@@ -9,6 +9,7 @@
 #include <math.h>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "triplane_b200.h"
 #include "tpr_device.cuh"
@@ -643,11 +644,15 @@ static void render_config(int Dc, int Df, int smem_optin, int& R, int& threads, 
   threads = (threads + 31) / 32 * 32;
 }
 
-int tpr_render(const float* planes_packed, int64_t n_img, int32_t height, int32_t width, const float* decoder_packed,
-               const float* origins, const float* dirs, int64_t n_rays, const float* jitter, const float* u,
-               const float* ray_start_per_ray, const float* ray_end_per_ray, const TprOptions* opt, float* rgb,
-               float* depth, float* weight_sum, float* fine_depths, int32_t* fine_inds, float* depth_range_io,
-               int32_t clamp_depth, void* scratch, size_t scratch_bytes, void* stream) {
+// The body of tpr_render.  `phases`: kRangeInit resets the running depth range in `scratch` before rendering,
+// kFinish decodes it (and clamps when clamp_depth != 0) afterwards.  tpr_render_host renders image by image
+// against ONE running range and finishes once.
+enum { kRangeInit = 1, kFinish = 2 };
+static int render_impl(const float* planes_packed, int64_t n_img, int32_t height, int32_t width, const float* decoder_packed,
+                       const float* origins, const float* dirs, int64_t n_rays, const float* jitter, const float* u,
+                       const float* ray_start_per_ray, const float* ray_end_per_ray, const TprOptions* opt, float* rgb,
+                       float* depth, float* weight_sum, float* fine_depths, int32_t* fine_inds, float* depth_range_io,
+                       int32_t clamp_depth, void* scratch, size_t scratch_bytes, void* stream, int phases) {
   if (!planes_packed || !decoder_packed || !origins || !dirs || !jitter || !opt || !rgb || !depth || !weight_sum || !scratch)
     return fail(TPR_E_NULL, "tpr_render: NULL pointer");
   if ((ray_start_per_ray == nullptr) != (ray_end_per_ray == nullptr))
@@ -690,8 +695,10 @@ int tpr_render(const float* planes_packed, int64_t n_img, int32_t height, int32_
   a.variant = env_int("TPR_WS_VARIANT", 0);
   a.dbg = env_int("TPR_PHASE_TIMING", 0) ? reinterpret_cast<long long*>(reinterpret_cast<char*>(scratch) + 64) : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
-  range_init_kernel<<<1, 1, 0, st>>>(a.range_enc);
-  TPR_CHECK_LAUNCH("range_init_kernel");
+  if (phases & kRangeInit) {
+    range_init_kernel<<<1, 1, 0, st>>>(a.range_enc);
+    TPR_CHECK_LAUNCH("range_init_kernel");
+  }
 
   const bool use_tc = opt->flags != TPR_MLP_FFMA && tc_rays_per_group(Dc, Df) > 0 && !env_int("TPR_FORCE_FFMA", 0);
   // TPR_RENDER_IMPL: 0 = pick (default), 1 = turn-taking tensor-core kernel, 2 = warp-specialised kernel (A/B runs)
@@ -735,9 +742,155 @@ int tpr_render(const float* planes_packed, int64_t n_img, int32_t height, int32_
     kern<<<(unsigned)grid, threads, smem, st>>>(a);
     TPR_CHECK_LAUNCH("render_kernel");
   }
-  finish_kernel<<<grid_for(a.n_rays_total, 256, di.sms, 4), 256, 0, st>>>(a.range_enc, depth_range_io, depth, a.n_rays_total,
-                                                                          clamp_depth);
+  if (phases & kFinish) {
+    finish_kernel<<<grid_for(a.n_rays_total, 256, di.sms, 4), 256, 0, st>>>(a.range_enc, depth_range_io, depth, a.n_rays_total,
+                                                                            clamp_depth);
+    TPR_CHECK_LAUNCH("finish_kernel");
+  }
+  return 0;
+}
+
+int tpr_render(const float* planes_packed, int64_t n_img, int32_t height, int32_t width, const float* decoder_packed,
+               const float* origins, const float* dirs, int64_t n_rays, const float* jitter, const float* u,
+               const float* ray_start_per_ray, const float* ray_end_per_ray, const TprOptions* opt, float* rgb,
+               float* depth, float* weight_sum, float* fine_depths, int32_t* fine_inds, float* depth_range_io,
+               int32_t clamp_depth, void* scratch, size_t scratch_bytes, void* stream) {
+  return render_impl(planes_packed, n_img, height, width, decoder_packed, origins, dirs, n_rays, jitter, u, ray_start_per_ray,
+                     ray_end_per_ray, opt, rgb, depth, weight_sum, fine_depths, fine_inds, depth_range_io, clamp_depth, scratch,
+                     scratch_bytes, stream, kRangeInit | kFinish);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The same forward with HOST buffers: planes / rays come from (pinned) host memory, outputs land in host memory.
+// One image's planes are 25 MB and take longer to cross PCIe than to render, so the images are pipelined over
+// three streams -- copy-in (H2D of image i+1), the caller's stream (repack + render of image i), copy-out (D2H of
+// image i-1) -- with the raw planes double buffered.  The global depth clamp (VR/ray_marcher.py:50) needs every
+// image, so depth is clamped and copied back last.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct HostPipe {
+  cudaStream_t in = nullptr, out = nullptr;
+  std::vector<cudaEvent_t> ev;
+  bool ok = false;
+};
+std::mutex g_pipe_mu;
+HostPipe g_pipe[64];
+
+// streams / events of the current device (created on first use; the only per-device state the library keeps)
+HostPipe* host_pipe(int n_events) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(g_pipe_mu);
+  HostPipe& p = g_pipe[dev];
+  if (!p.ok) {
+    if (cudaStreamCreateWithFlags(&p.in, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithFlags(&p.out, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    p.ok = true;
+  }
+  while ((int)p.ev.size() < n_events) {
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    p.ev.push_back(e);
+  }
+  return &p;
+}
+
+struct HostWs { size_t raw, packed, rays, rgb, depth, wsum, scratch, total; };
+HostWs host_ws_layout(int64_t n_img, int32_t H, int32_t W, int64_t n_rays) {
+  auto up = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
+  HostWs w;
+  const size_t img = (size_t)TPR_PLANES * TPR_CHANNELS * H * W * sizeof(float);
+  size_t o = 0;
+  w.raw = o; o += 2 * up(img);
+  w.packed = o; o += 2 * up(img);
+  w.rays = o; o += up((size_t)n_img * n_rays * 6 * sizeof(float));
+  w.rgb = o; o += up((size_t)n_img * n_rays * TPR_CHANNELS * sizeof(float));
+  w.depth = o; o += up((size_t)n_img * n_rays * sizeof(float));
+  w.wsum = o; o += up((size_t)n_img * n_rays * sizeof(float));
+  w.scratch = o; o += 1024;
+  w.total = o;
+  return w;
+}
+}  // namespace
+
+size_t tpr_render_host_workspace_bytes(int64_t n_img, int32_t height, int32_t width, int64_t n_rays) {
+  if (n_img <= 0 || height <= 0 || width <= 0 || n_rays <= 0) return 0;
+  return host_ws_layout(n_img, height, width, n_rays).total;
+}
+
+#define TPR_CUDA(call, what)                                       \
+  do {                                                             \
+    cudaError_t e__ = (call);                                      \
+    if (e__ != cudaSuccess) return cuda_fail(e__, what);           \
+  } while (0)
+
+int tpr_render_host(const float* planes_host, int64_t n_img, int32_t height, int32_t width, const float* decoder_packed,
+                    const float* origins_host, const float* dirs_host, int64_t n_rays, const float* jitter, const float* u,
+                    const TprOptions* opt, float* rgb_host, float* depth_host, float* weight_sum_host, float* depth_range_io,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  if (!planes_host || !decoder_packed || !origins_host || !dirs_host || !jitter || !opt || !rgb_host || !depth_host ||
+      !weight_sum_host || !workspace)
+    return fail(TPR_E_NULL, "tpr_render_host: NULL pointer");
+  if (n_img <= 0 || n_rays <= 0 || height <= 0 || width <= 0 || (int64_t)height * width > (1 << 24))
+    return fail(TPR_E_SHAPE, "tpr_render_host: bad shape");
+  if (opt->depth_resolution_importance > 0 && !u) return fail(TPR_E_NULL, "tpr_render_host: NULL u");
+  const HostWs w = host_ws_layout(n_img, height, width, n_rays);
+  if (workspace_bytes < w.total) return fail(TPR_E_SCRATCH, "tpr_render_host: workspace too small");
+  HostPipe* hp = host_pipe((int)(2 * n_img + 4));
+  if (!hp) return fail(TPR_E_DEVICE, "tpr_render_host: cannot create copy streams / events");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = reinterpret_cast<char*>(workspace);
+  const size_t img_floats = (size_t)TPR_PLANES * TPR_CHANNELS * height * width, img_bytes = img_floats * sizeof(float);
+  const size_t img_stride = (img_bytes + 1023) & ~(size_t)1023;
+  float* d_orig = reinterpret_cast<float*>(ws + w.rays);
+  float* d_dirs = d_orig + (size_t)n_img * n_rays * 3;
+  float* d_rgb = reinterpret_cast<float*>(ws + w.rgb);
+  float* d_depth = reinterpret_cast<float*>(ws + w.depth);
+  float* d_wsum = reinterpret_cast<float*>(ws + w.wsum);
+  const int Dc = opt->depth_resolution, Df = opt->depth_resolution_importance;
+  // events: [0] entry fence, [1..2] raw buffer free, [3] all copied out, [4+2i] image i copied in, [5+2i] image i rendered
+  cudaEvent_t* ev = hp->ev.data();
+
+  // the workspace may still be in use by earlier work on the caller's stream (a previous call)
+  TPR_CUDA(cudaEventRecord(ev[0], st), "cudaEventRecord");
+  TPR_CUDA(cudaStreamWaitEvent(hp->in, ev[0], 0), "cudaStreamWaitEvent");
+  TPR_CUDA(cudaStreamWaitEvent(hp->out, ev[0], 0), "cudaStreamWaitEvent");
+  const size_t ray_bytes = (size_t)n_img * n_rays * 3 * sizeof(float);
+  TPR_CUDA(cudaMemcpyAsync(d_orig, origins_host, ray_bytes, cudaMemcpyHostToDevice, hp->in), "cudaMemcpyAsync(origins)");
+  TPR_CUDA(cudaMemcpyAsync(d_dirs, dirs_host, ray_bytes, cudaMemcpyHostToDevice, hp->in), "cudaMemcpyAsync(dirs)");
+  for (int64_t i = 0; i < n_img; ++i) {
+    const int b = (int)(i & 1);
+    float* raw = reinterpret_cast<float*>(ws + w.raw + b * img_stride);
+    float* packed = reinterpret_cast<float*>(ws + w.packed + b * img_stride);
+    if (i >= 2) TPR_CUDA(cudaStreamWaitEvent(hp->in, ev[1 + b], 0), "cudaStreamWaitEvent");      // repack of image i-2 done
+    TPR_CUDA(cudaMemcpyAsync(raw, planes_host + (size_t)i * img_floats, img_bytes, cudaMemcpyHostToDevice, hp->in),
+             "cudaMemcpyAsync(planes)");
+    TPR_CUDA(cudaEventRecord(ev[4 + 2 * i], hp->in), "cudaEventRecord");
+    TPR_CUDA(cudaStreamWaitEvent(st, ev[4 + 2 * i], 0), "cudaStreamWaitEvent");
+    int rc = tpr_pack_planes(raw, 1, height, width, packed, st);
+    if (rc != 0) return rc;
+    TPR_CUDA(cudaEventRecord(ev[1 + b], st), "cudaEventRecord");
+    const size_t ro = (size_t)i * n_rays;
+    rc = render_impl(packed, 1, height, width, decoder_packed, d_orig + ro * 3, d_dirs + ro * 3, n_rays, jitter + ro * Dc,
+                     u ? u + ro * Df : nullptr, nullptr, nullptr, opt, d_rgb + ro * TPR_CHANNELS, d_depth + ro, d_wsum + ro,
+                     nullptr, nullptr, nullptr, 0, ws + w.scratch, 1024, st, i == 0 ? kRangeInit : 0);
+    if (rc != 0) return rc;
+    TPR_CUDA(cudaEventRecord(ev[5 + 2 * i], st), "cudaEventRecord");
+    TPR_CUDA(cudaStreamWaitEvent(hp->out, ev[5 + 2 * i], 0), "cudaStreamWaitEvent");
+    TPR_CUDA(cudaMemcpyAsync(rgb_host + ro * TPR_CHANNELS, d_rgb + ro * TPR_CHANNELS, (size_t)n_rays * TPR_CHANNELS * sizeof(float),
+                             cudaMemcpyDeviceToHost, hp->out), "cudaMemcpyAsync(rgb)");
+    TPR_CUDA(cudaMemcpyAsync(weight_sum_host + ro, d_wsum + ro, (size_t)n_rays * sizeof(float), cudaMemcpyDeviceToHost, hp->out),
+             "cudaMemcpyAsync(weight_sum)");
+  }
+  DeviceInfo di = device_info();
+  const long long total = (long long)n_img * n_rays;
+  finish_kernel<<<grid_for(total, 256, di.sms, 4), 256, 0, st>>>(reinterpret_cast<unsigned*>(ws + w.scratch), depth_range_io,
+                                                                 d_depth, total, 1);
   TPR_CHECK_LAUNCH("finish_kernel");
+  TPR_CUDA(cudaMemcpyAsync(depth_host, d_depth, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(depth)");
+  // the caller's stream completes only when every output has landed
+  TPR_CUDA(cudaEventRecord(ev[3], hp->out), "cudaEventRecord");
+  TPR_CUDA(cudaStreamWaitEvent(st, ev[3], 0), "cudaStreamWaitEvent");
   return 0;
 }
 

@@ -215,6 +215,64 @@ class ImportanceRenderer(torch.nn.Module):
         self.last_fine = (fine_d, fine_i)
         return rgb, depth, wsum
 
+    # ------------------------------------------------------------------ forward with host buffers
+    def forward_host(self, planes, decoder, ray_origins, ray_directions, rendering_options, *, noise=None, out=None):
+        """``forward`` for a caller whose tensors live in (pinned) HOST memory: ``planes`` [N,3,32,H,W],
+        ``ray_origins`` / ``ray_directions`` [N,M,3] are CPU tensors and the three outputs are returned as pinned CPU
+        tensors (or written into ``out``).  The library pipelines H2D copy, repack + render and D2H copy image by
+        image (tpr_render_host), so the call costs about max(PCIe time, render time) instead of their sum.  The
+        result is complete once the current CUDA stream has been synchronised.  Scalar ray limits only."""
+        opts = rendering_options
+        for t, name in ((planes, 'planes'), (ray_origins, 'ray_origins'), (ray_directions, 'ray_directions')):
+            if not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError(f'forward_host: {name} must be a contiguous float32 CPU tensor (pinned for async copies)')
+        if planes.dim() != 5 or planes.shape[1] != 3 or planes.shape[2] != 32:
+            raise RuntimeError(f'planes must be [N,3,32,H,W], got {tuple(planes.shape)}')
+        if opts.get('clamp_mode', None) != 'softplus':
+            raise AssertionError('MipRayMarcher only supports `clamp_mode`=`softplus`!')      # VR/ray_marcher.py:35
+        if opts.get('density_noise', 0) > 0:
+            raise NotImplementedError('density_noise > 0 (VR/renderer.py:146) is not supported by the fused renderer')
+        if isinstance(opts['ray_start'], str) or isinstance(opts['ray_end'], str):
+            raise NotImplementedError("forward_host supports scalar ray limits only (use forward() for 'auto')")
+        n, _, _, h, w = planes.shape
+        m = ray_origins.shape[1]
+        if tuple(ray_origins.shape) != (n, m, 3) or ray_directions.shape != ray_origins.shape:
+            raise RuntimeError(f'batch mismatch: planes N={n}, origins {tuple(ray_origins.shape)}, '
+                               f'directions {tuple(ray_directions.shape)}')
+        dec = pack_decoder(decoder)                  # the decoder's parameters are device tensors
+        dev = dec.device
+        dc = int(opts['depth_resolution'])
+        df = int(opts['depth_resolution_importance'])
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            if noise is None:
+                jitter = torch.rand((n, m, dc, 1), device=dev, dtype=torch.float32)
+                u = torch.rand(n * m, df, device=dev) if df > 0 else None
+            else:
+                jitter = _require_cuda_f32(noise[0], 'noise[0]').reshape(n, m, dc, 1)
+                u = _require_cuda_f32(noise[1], 'noise[1]').reshape(n * m, df) if df > 0 else None
+            o = _lib.TprOptions(ray_start=float(opts['ray_start']), ray_end=float(opts['ray_end']),
+                                box_warp=float(opts['box_warp']), depth_resolution=dc, depth_resolution_importance=df,
+                                disparity_space_sampling=int(bool(opts.get('disparity_space_sampling', False))),
+                                white_back=int(bool(opts.get('white_back', False))), flags=_mlp_flag(opts), tile_width=0)
+            if out is None:
+                out = tuple(torch.empty((n, m, c), dtype=torch.float32).pin_memory() for c in (32, 1, 1))
+            for t, c in zip(out, (32, 1, 1)):
+                if tuple(t.shape) != (n, m, c) or t.dtype != torch.float32 or t.is_cuda or not t.is_contiguous():
+                    raise RuntimeError(f'out tensors must be contiguous float32 CPU tensors [{n},{m},{c}]')
+            nws = L.tpr_render_host_workspace_bytes(n, h, w, m)
+            ws = getattr(self, '_host_ws', None)
+            if ws is None or ws.numel() < nws or ws.device != dev:
+                # kept for the renderer's lifetime: the library's copy streams use it behind torch's allocator's back
+                ws = self._host_ws = torch.empty(nws, device=dev, dtype=torch.uint8)
+            rng = torch.empty(2, device=dev, dtype=torch.float32)
+            _lib.check(L.tpr_render_host(_ptr(planes), n, h, w, _ptr(dec), _ptr(ray_origins), _ptr(ray_directions), m,
+                                         _ptr(jitter), _ptr(u), ctypes.byref(o), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
+                                         _ptr(rng), _ptr(ws), ws.numel(), _stream()), 'tpr_render_host')
+            self._host_keepalive = (dec, jitter, u, planes, ray_origins, ray_directions)    # until the next call
+        self.last_depth_range = rng
+        return out
+
     # ------------------------------------------------------------------ run_model (VR/renderer.py:142-148)
     def run_model(self, planes, decoder, sample_coordinates, sample_directions, options, *, want_rgb=True):
         """``sample_directions`` is accepted and ignored, exactly like OSGDecoder ignores it

@@ -134,6 +134,24 @@ int tpr_render(const float* planes_packed, int64_t n_img, int32_t height, int32_
                void* scratch, size_t scratch_bytes, void* stream);
 int tpr_clamp_depth(float* depth, int64_t n, const float* depth_range /*[2] device*/, void* stream);
 
+/* ---- a13 with HOST buffers: the call a CPU-side caller makes (and the one bench.py times end to end) ---------- */
+/* Same result as tpr_render for scalar ray limits, but planes [N,3,32,H,W] (the backbone's layout, NOT repacked),
+ * origins and dirs are HOST pointers (pinned memory for the copies to be asynchronous) and rgb / depth /
+ * weight_sum are written to HOST memory.  decoder_packed, jitter and u stay DEVICE pointers (the two uniform draws
+ * are made on the device, exactly like the reference's torch.rand calls).  One image's planes take longer to cross
+ * PCIe than to render, so the library pipelines image by image over two internal copy streams (created once per
+ * device, the only state the library keeps) and `stream`: H2D of image i+1, repack + render of image i and D2H of
+ * image i-1 overlap.  `workspace` is a DEVICE buffer of tpr_render_host_workspace_bytes() bytes.
+ * Asynchronous like every other entry: the outputs are complete when `stream` has drained.
+ * depth_range_io: DEVICE [2], receives the global depth range (may be NULL). */
+size_t tpr_render_host_workspace_bytes(int64_t n_img, int32_t height, int32_t width, int64_t n_rays);
+int tpr_render_host(const float* planes_host, int64_t n_img, int32_t height, int32_t width,
+                    const float* decoder_packed,
+                    const float* origins_host /*[N,M,3]*/, const float* dirs_host /*[N,M,3]*/, int64_t n_rays,
+                    const float* jitter, const float* u, const TprOptions* opt,
+                    float* rgb_host, float* depth_host, float* weight_sum_host, float* depth_range_io,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a9: MipRayMarcher2.forward (VR/ray_marcher.py:25-57), stand-alone ------------------ */
 /* colors [R,S,C], densities [R,S], depths [R,S] in the given (not re-sorted) order ->
  * rgb [R,C], depth [R], weights [R,S-1].  depth_range is FOUR floats: [0..1] receive
