@@ -30,6 +30,22 @@ METRIC = 'ray-samples/sec'
 WORKLOAD = 'config2: batch 8 x 128^2 rays x (48+48) samples, 3x32x256^2 fp32 planes/image'
 
 
+def ncu_traffic(mode):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+    `ncu --set full` summary of this same command (profiles/); None if there is no capture for this mode."""
+    name = {'fp32': 'r01_render_ws_fp32_ncu_full_summary.txt', 'bf16': 'r01_render_ws_bf16_ncu_full_summary.txt'}.get(mode)
+    path = os.path.join(ROOT, 'profiles', name) if name else None
+    if not path or not os.path.exists(path):
+        return None
+    tot = 0.0
+    for line in open(path):
+        for key in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            if line.startswith(key):
+                unit = line[line.index('[') + 1:line.index(']')]
+                tot += float(line.split('=')[1]) * {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1.0}[unit]
+    return tot or None
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -289,7 +305,9 @@ def main():
                        'l2': 'inputs larger than L2: 201 MB planes + 201 MB repack + 50 MB noise per step (126 MB L2)',
                        'step': 'ImportanceRenderer.forward incl. plane repack, decoder pack, both torch.rand draws'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                         'frac': achieved / pk['hbm_gbs'], 'traffic': None, 'peak_kind': pk_kind,
+                         'frac': achieved / pk['hbm_gbs'], 'traffic': ncu_traffic(args.mode), 'peak_kind': pk_kind,
+                         'traffic_note': 'DRAM bytes per launch (ncu --set full, profiles/): one image\'s 25 MB of planes stays '
+                                         'L2-resident, so the 1536 B/sample are L2/L1 traffic and frac can exceed 1',
                          'kernel': ('render_kernel' if args.mode == 'fp32_ffma' else 'render_ws_kernel') + ' (tpr_render: +2 helper launches of ~2 us)', 'kernel_ms': kern_ms,
                          'algorithmic_bytes_per_launch': samples_per_step * BYTES_PER_SAMPLE},
             'e2e': {'value': world * samples_per_step / (e2e_ms * 1e-3), 'unit': METRIC, 'ms_per_step': e2e_ms,
