@@ -9,15 +9,17 @@ from ctypes import c_char_p, c_double, c_float, c_int32, c_int64, c_size_t, c_vo
 
 from .build import LIB_PATH
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MLP_FP32, MLP_BF16, MLP_FFMA = 0, 1, 2
+LAYOUT_CHANNELS_LAST, LAYOUT_CHANNELS_FIRST = 0, 1
 
 
 class TprOptions(ctypes.Structure):
     _fields_ = [('ray_start', c_double), ('ray_end', c_double), ('box_warp', c_double),
                 ('depth_resolution', c_int32), ('depth_resolution_importance', c_int32),
                 ('disparity_space_sampling', c_int32), ('white_back', c_int32),
-                ('flags', c_int32), ('tile_width', c_int32), ('reserved', c_int32 * 5)]
+                ('flags', c_int32), ('tile_width', c_int32), ('plane_sets', c_int32),
+                ('output_layout', c_int32), ('depth_clamp_group', c_int32), ('reserved', c_int32 * 2)]
 
 
 _P = c_void_p
@@ -41,6 +43,7 @@ _SIGNATURES = {
     'tpr_ray_march': (ctypes.c_int, [_P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, _P, c_int32, _P]),
     'tpr_sample_importance': (ctypes.c_int, [_P, _P, _P, c_int64, c_int32, c_int32, _P, _P, _P]),
     'tpr_sample_pdf': (ctypes.c_int, [_P, c_int32, _P, _P, c_int64, c_int32, c_int32, _P, _P, _P]),
+    'tpr_sample_stratified': (ctypes.c_int, [_P, c_int64, _P, _P, ctypes.POINTER(TprOptions), _P, _P]),
     'tpr_ray_limits_box': (ctypes.c_int, [_P, _P, c_int64, c_float, _P, _P, _P]),
     'tpr_gather_microbench': (c_int64, [_P, c_int64, c_int32, c_int32, _P, _P]),
     'tpr_mma_microbench': (ctypes.c_int, [c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),

@@ -19,7 +19,35 @@ struct RenderArgs {
   int variant;                           // debug: A/B switches (TPR_WS_VARIANT)
   int col_w;                             // > 0: rays form an image col_w pixels wide and a group is R rays of one image COLUMN
   long long* dbg;                        // optional [16] per-phase cycle counters of CTA 0 (TPR_PHASE_TIMING=1)
+  int plane_sets;                        // >= 1: image (camera) n samples plane set n % plane_sets
+  int nchw;                              // != 0: rgb is written channels-first, [N,32,M] (training/triplane.py:81)
+  int clamp_group;                       // k > 0: images [j*k, (j+1)*k) share a depth-clamp range (slot j); 0: one range
 };
+
+// Depth ranges in the scratch block (unsigned words, ordered-uint encoded): [0..1] whole call, then from
+// kRangeSlotOff one (min, max) pair per clamp slot.  Bytes 64..191 hold the optional phase counters.
+constexpr int kRangeSlotOff = 64;
+__device__ __forceinline__ int range_slot(const RenderArgs& a, int n) { return a.clamp_group > 0 ? n / a.clamp_group : 0; }
+// Fold the running range of slot `slot` (smn, smx; per-lane partials) into the call-wide running range (mn, mx) and,
+// with per-slot clamping on, into the slot's words; then restart it.  Warp-collective.
+__device__ __forceinline__ void range_fold(const RenderArgs& a, int slot, float& smn, float& smx, float& mn, float& mx, int lane) {
+  mn = fminf(mn, smn); mx = fmaxf(mx, smx);
+  if (a.clamp_group > 0) {
+    const float lo = warp_min(smn), hi = warp_max(smx);
+    if (lane == 0 && lo <= hi) {
+      atomicMin(a.range_enc + kRangeSlotOff + 2 * slot, float_to_ordered(lo));
+      atomicMax(a.range_enc + kRangeSlotOff + 2 * slot + 1, float_to_ordered(hi));
+    }
+  }
+  smn = __int_as_float(0x7f800000); smx = -__int_as_float(0x7f800000);
+}
+
+// this ray's first rgb element and the stride between its channels, for either output layout
+__device__ __forceinline__ float* rgb_ptr(const RenderArgs& a, long long g, int n, long long& cstride) {
+  if (a.nchw) { cstride = a.rays_per_img; return a.rgb + (long long)n * (kC - 1) * a.rays_per_img + g; }   // n*32*M + (g - n*M)
+  cstride = 1;
+  return a.rgb + g * kC;
+}
 
 constexpr int kRenderMaxThreads = 512;
 

@@ -319,6 +319,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderAr
     const bool per_ray = a.rs != nullptr;
     const size_t img_stride = (size_t)3 * a.H * a.W * kC;
     float mn = __int_as_float(0x7f800000), mx = -__int_as_float(0x7f800000);
+    float smn = mn, smx = mx;                         // running depth range of the current clamp slot
+    int cur_slot = 0;
     long long tprev = clock64();
 #define TPR_MARK(i) do { if (a.dbg != nullptr && blockIdx.x == 0 && tid == 0) { long long now_ = clock64(); a.dbg[i] += now_ - tprev; tprev = now_; } } while (0)
 #define WORKER_SYNC() named_bar_sync(1, kTcWorkers)
@@ -335,7 +337,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderAr
       const long long rstride = colm ? a.col_w : 1;
       const int nr = colm ? R : (int)min((long long)R, a.rays_per_img - gi * R);
 #define RAY_G(r) (ray0 + (long long)(r) * rstride)
-      const float* img = a.planes + (size_t)n * img_stride;
+      const float* img = a.planes + (size_t)(n % a.plane_sets) * img_stride;
+      if (range_slot(a, (int)n) != cur_slot) { range_fold(a, cur_slot, smn, smx, mn, mx, lane); cur_slot = range_slot(a, (int)n); }
       // ---- rays + coarse depths
       if (tid < nr * 6) {
         const int r = tid / 6, c = tid - r * 6;
@@ -407,7 +410,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderAr
       // ---- sort + final march: omega per sample (scattered to original order), depth, weight sum
       for (int r = warp; r < nr; r += kTcWarps) {
         float wsum, dnum;
-        warp_sort_and_weights<E, true>(rs.dep + r * S, rs.sig + r * S, rs.wa + r * S, nullptr, S, lane, wsum, dnum, mn, mx);
+        warp_sort_and_weights<E, true>(rs.dep + r * S, rs.sig + r * S, rs.wa + r * S, nullptr, S, lane, wsum, dnum, smn, smx);
         if (lane == 0) {
           rs.rayw[r] = wsum;
           a.depth[RAY_G(r)] = dnum / wsum;            // NaN -> inf and the clamp happen in finish_kernel
@@ -450,15 +453,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderAr
             if (a.white_back) v = v + 1.0f - ws;         // VR/ray_marcher.py:52-53
             o8[c] = v * 2.0f - 1.0f;                     // :55
           }
-          float4* dst = reinterpret_cast<float4*>(a.rgb + RAY_G(r) * kC + 8 * j);
-          dst[0] = make_float4(o8[0], o8[1], o8[2], o8[3]);
-          dst[1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
+          long long cstride;
+          float* dst1 = rgb_ptr(a, RAY_G(r), (int)n, cstride) + 8 * j * cstride;
+          if (a.nchw) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) dst1[c * cstride] = o8[c];
+          } else {
+            float4* dst = reinterpret_cast<float4*>(dst1);
+            dst[0] = make_float4(o8[0], o8[1], o8[2], o8[3]);
+            dst[1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
+          }
         }
         tcgen05_fence_before();
       }
       WORKER_SYNC();                                     // slots, ray arrays free for the next group
       TPR_MARK(10);
     }
+    range_fold(a, cur_slot, smn, smx, mn, mx, lane);
+    mn = warp_min(mn); mx = warp_max(mx);
     if (lane == 0 && mn <= mx) {
       atomicMin(&range_sm[0], float_to_ordered(mn));
       atomicMax(&range_sm[1], float_to_ordered(mx));

@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
         PROF_T0();
         mbar_wait_parked(pass == 0 ? &bars.coarse_ready[gi & 3] : &bars.fine_ready[gi & 3], cpar);
         PROF_ADD(pass, tid == 0);
-        const float* img = a.planes + (size_t)gg.n * img_stride;
+        const float* img = a.planes + (size_t)((unsigned)gg.n % (unsigned)a.plane_sets) * img_stride;
         const int T = pass == 0 ? nc : nf, Dx = pass == 0 ? Dc : Df, off = pass == 0 ? 0 : Dc;
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
@@ -538,6 +538,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
     constexpr int kRayThreads = kRayWarps * 32;
     float* wa = scratch; float* wb = wa + R * S; float* wc = wb + R * S; float* rayw = wc + R * S;
     float mn = __int_as_float(0x7f800000), mx = -__int_as_float(0x7f800000);
+    float smn = mn, smx = mx;                         // running depth range of the current clamp slot
+    int cur_slot = 0;
 #define RAY_SYNC() named_bar_sync(2, kRayThreads)
 
     const bool pl = rtid == 0;
@@ -602,10 +604,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
       PROF_T0();
       mbar_wait_parked(nf > 0 ? &bars.fsig_ready[gi & 3] : &bars.csig_ready[gi & 3], (uint32_t)(gi >> 2) & 1u);
       PROF_ADD(15, pl);
+      if (range_slot(a, gg.n) != cur_slot) { range_fold(a, cur_slot, smn, smx, mn, mx, lane); cur_slot = range_slot(a, gg.n); }
       // ---- sort + final march: omega per sample (scattered to original order), depth, weight sum
       for (int r = rw; r < gg.nr; r += kRayWarps) {
         float wsum, dnum;
-        warp_sort_and_weights<E, true, ER>(cx.dep + r * S, cx.sig + r * S, wa + r * S, nullptr, S, lane, wsum, dnum, mn, mx,
+        warp_sort_and_weights<E, true, ER>(cx.dep + r * S, cx.sig + r * S, wa + r * S, nullptr, S, lane, wsum, dnum, smn, smx,
                                        wb + r * 2 * S);          // wb and wc are contiguous: 2*S floats per ray
         if (lane == 0) {
           const long long g = gg.ray0 + (long long)r * gg.rstride;
@@ -669,7 +672,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
       }
       if (i == 0 && r < gg.nr) {
         const float wsr = rayw[r];
-        float4* dst = reinterpret_cast<float4*>(a.rgb + (gg.ray0 + (long long)r * gg.rstride) * kC + 16 * hc);
+        long long cstride;
+        float* dst1 = rgb_ptr(a, gg.ray0 + (long long)r * gg.rstride, gg.n, cstride) + 16 * hc * cstride;
+        float4* dst = reinterpret_cast<float4*>(dst1);
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           float o4[4];
@@ -679,7 +684,12 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
             if (a.white_back) v = v + 1.0f - wsr;      // VR/ray_marcher.py:52-53
             o4[c] = v * 2.0f - 1.0f;                   // :55
           }
-          dst[c4] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+          if (a.nchw) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dst1[(4 * c4 + c) * cstride] = o4[c];
+          } else {
+            dst[c4] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+          }
         }
       }
       RAY_SYNC();                                      // wa / rayw are reused by the next resample / sort
@@ -696,6 +706,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
       else sort_composite(g);
     }
     if (nf > 0) sort_composite(G - 1);
+    range_fold(a, cur_slot, smn, smx, mn, mx, lane);
     mn = warp_min(mn); mx = warp_max(mx);
     if (lane == 0 && mn <= mx) {
       atomicMin(&range_sm[0], float_to_ordered(mn));

@@ -111,6 +111,18 @@ __global__ void ray_sample_kernel(const float* __restrict__ c2w, const float* __
 }
 
 // =======================================================================================
+// a7 stand-alone: sample_stratified (VR/renderer.py:169-192), one thread per depth
+// =======================================================================================
+__global__ void sample_stratified_kernel(const RenderArgs a, long long total, float* __restrict__ depths) {
+  const bool per_ray = a.rs != nullptr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long g = i / a.Dc;
+    const int k = (int)(i - g * a.Dc);
+    depths[i] = coarse_depth(a, k, a.jitter[i], per_ray ? a.rs[g] : a.ray_start, per_ray ? a.re[g] : a.ray_end, per_ray);
+  }
+}
+
+// =======================================================================================
 // a14: get_ray_limits_box (VR/math_utils.py:46-98), one thread per ray
 // =======================================================================================
 __global__ void ray_limits_box_kernel(const float* __restrict__ o, const float* __restrict__ d, long long n, float side,
@@ -249,7 +261,7 @@ __device__ __forceinline__ void tile_pass(const RenderArgs& a, const TileSmem& s
 }
 
 template <int E>
-__device__ __forceinline__ void ray_composite(const RenderArgs& a, const TileSmem& sm, int r, long long g, int S,
+__device__ __forceinline__ void ray_composite(const RenderArgs& a, const TileSmem& sm, int r, long long g, int n, int S,
                                               float& mn, float& mx) {
   const int lane = threadIdx.x & 31;
   float* om = sm.wa + r * S;
@@ -272,7 +284,8 @@ __device__ __forceinline__ void ray_composite(const RenderArgs& a, const TileSme
   }
   float c = acc0 + acc1;
   if (a.white_back) c = c + 1.0f - wsum;              // VR/ray_marcher.py:52-53
-  a.rgb[g * kC + lane] = c * 2.0f - 1.0f;             // :55
+  long long cstride;
+  rgb_ptr(a, g, n, cstride)[lane * cstride] = c * 2.0f - 1.0f;      // :55
   if (lane == 0) {
     a.depth[g] = dnum / wsum;                         // NaN -> inf and the clamp happen in finish_kernel
     a.wsum[g] = wsum;
@@ -299,6 +312,8 @@ __global__ void __launch_bounds__(kRenderMaxThreads, 1) render_kernel(const Rend
   const bool per_ray = a.rs != nullptr;
   const size_t img_stride = (size_t)3 * a.H * a.W * kC;
   float mn = __int_as_float(0x7f800000), mx = -__int_as_float(0x7f800000);
+  float smn = mn, smx = mx;                           // running depth range of the current clamp slot
+  int cur_slot = 0;
 
   for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     // a tile is R consecutive rays of ONE image, so the plane block is CTA-uniform
@@ -306,7 +321,8 @@ __global__ void __launch_bounds__(kRenderMaxThreads, 1) render_kernel(const Rend
     const long long m0 = (tile - n * a.tiles_per_img) * R;
     const long long g0 = n * a.rays_per_img + m0;
     const int nr = (int)min((long long)R, a.rays_per_img - m0);
-    const float* img = a.planes + (size_t)n * img_stride;
+    const float* img = a.planes + (size_t)(n % a.plane_sets) * img_stride;
+    if (range_slot(a, (int)n) != cur_slot) { range_fold(a, cur_slot, smn, smx, mn, mx, lane); cur_slot = range_slot(a, (int)n); }
     __syncthreads();                                   // previous tile fully consumed
     // ---- rays
     if (threadIdx.x < nr * 6) {
@@ -341,8 +357,10 @@ __global__ void __launch_bounds__(kRenderMaxThreads, 1) render_kernel(const Rend
       __syncthreads();
     }
     // ---- D: merge + final march
-    for (int r = warp; r < nr; r += nwarps) ray_composite<E>(a, sm, r, g0 + r, S, mn, mx);
+    for (int r = warp; r < nr; r += nwarps) ray_composite<E>(a, sm, r, g0 + r, (int)n, S, smn, smx);
   }
+  range_fold(a, cur_slot, smn, smx, mn, mx, lane);
+  mn = warp_min(mn); mx = warp_max(mx);
   if (lane == 0 && mn <= mx) {
     atomicMin(&range_sm[0], float_to_ordered(mn));
     atomicMax(&range_sm[1], float_to_ordered(mx));
@@ -354,18 +372,31 @@ __global__ void __launch_bounds__(kRenderMaxThreads, 1) render_kernel(const Rend
   }
 }
 
-__global__ void range_init_kernel(unsigned* enc) {
-  enc[0] = 0xffffffffu; enc[1] = 0u;
-  for (int i = 0; i < 16; ++i) reinterpret_cast<long long*>(reinterpret_cast<char*>(enc) + 64)[i] = 0;   // phase counters
+// n_slots < 0: `enc` is just the two range words (tpr_ray_march); otherwise the render scratch block
+__global__ void range_init_kernel(unsigned* enc, int n_slots) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    enc[0] = 0xffffffffu; enc[1] = 0u;
+    if (n_slots >= 0)
+      for (int i = 0; i < 16; ++i) reinterpret_cast<long long*>(reinterpret_cast<char*>(enc) + 64)[i] = 0;   // phase counters
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += gridDim.x * blockDim.x) {
+    enc[kRangeSlotOff + 2 * i] = 0xffffffffu; enc[kRangeSlotOff + 2 * i + 1] = 0u;
+  }
 }
 
 // decode the (min,max) and optionally apply nan_to_num(inf) + clamp (VR/ray_marcher.py:49-50)
+// rays_per_slot > 0: ray i clamps against the range of slot i / rays_per_slot instead of the call-wide one
 __global__ void finish_kernel(const unsigned* __restrict__ enc, float* __restrict__ range_out,
-                              float* __restrict__ depth, long long n, int do_clamp) {
-  const float lo = ordered_to_float(enc[0]), hi = ordered_to_float(enc[1]);
-  if (blockIdx.x == 0 && threadIdx.x == 0 && range_out) { range_out[0] = lo; range_out[1] = hi; }
+                              float* __restrict__ depth, long long n, int do_clamp, long long rays_per_slot) {
+  const float glo = ordered_to_float(enc[0]), ghi = ordered_to_float(enc[1]);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && range_out) { range_out[0] = glo; range_out[1] = ghi; }
   if (!do_clamp) return;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float lo = glo, hi = ghi;
+    if (rays_per_slot > 0) {
+      const long long s = i / rays_per_slot;
+      lo = ordered_to_float(enc[kRangeSlotOff + 2 * s]); hi = ordered_to_float(enc[kRangeSlotOff + 2 * s + 1]);
+    }
     float d = depth[i];
     if (d != d) d = __int_as_float(0x7f800000);
     depth[i] = fminf(fmaxf(d, lo), hi);
@@ -574,6 +605,34 @@ int tpr_ray_limits_box(const float* origins, const float* dirs, int64_t n_rays, 
   return 0;
 }
 
+// the depth-sampling constants of RenderArgs, derived exactly as torch derives them from the python floats
+static void set_depth_constants(RenderArgs& a, const TprOptions* opt) {
+  const int Dc = opt->depth_resolution;
+  a.ray_start = (float)opt->ray_start; a.ray_end = (float)opt->ray_end;                 // torch.linspace casts to float32
+  a.lin_step = (a.ray_end - a.ray_start) / (float)(Dc - 1);                             // torch.linspace step, float32
+  a.jitter_scale = (float)((opt->ray_end - opt->ray_start) / (Dc - 1));                 // python float (VR/renderer.py:189)
+  a.inv_start = (float)(1.0 / opt->ray_start); a.inv_end = (float)(1.0 / opt->ray_end); // python floats (:181)
+  a.Dc = Dc; a.disparity = opt->disparity_space_sampling;
+}
+
+int tpr_sample_stratified(const float* jitter, int64_t n_rays, const float* ray_start_per_ray, const float* ray_end_per_ray,
+                          const TprOptions* opt, float* depths, void* stream) {
+  if (!jitter || !opt || !depths) return fail(TPR_E_NULL, "tpr_sample_stratified: NULL pointer");
+  if ((ray_start_per_ray == nullptr) != (ray_end_per_ray == nullptr))
+    return fail(TPR_E_NULL, "tpr_sample_stratified: per-ray limits need both start and end");
+  if (n_rays <= 0 || opt->depth_resolution < 2) return fail(TPR_E_SHAPE, "tpr_sample_stratified: need n_rays > 0, depth_resolution >= 2");
+  DeviceInfo di = device_info();
+  if (!di.ok) return fail(TPR_E_DEVICE, "tpr_sample_stratified: no CUDA device");
+  RenderArgs a;
+  memset(&a, 0, sizeof(a));
+  set_depth_constants(a, opt);
+  a.jitter = jitter; a.rs = ray_start_per_ray; a.re = ray_end_per_ray;
+  const long long total = (long long)n_rays * opt->depth_resolution;
+  sample_stratified_kernel<<<grid_for(total, 256, di.sms, 16), 256, 0, (cudaStream_t)stream>>>(a, total, depths);
+  TPR_CHECK_LAUNCH("sample_stratified_kernel");
+  return 0;
+}
+
 static int launch_run_model(bool from_features, const float* planes, int64_t n_img, int32_t H, int32_t W,
                             const float* dec, const float* in, int64_t n_pts, double box_warp, float* rgb, float* sigma,
                             int32_t flags, void* stream) {
@@ -619,7 +678,12 @@ int tpr_decode(const float* features, int64_t n_img, int64_t n_pts, const float*
   return launch_run_model(true, nullptr, n_img, 0, 0, decoder_packed, features, n_pts, 1.0, rgb, sigma, flags, stream);
 }
 
-size_t tpr_render_scratch_bytes(int64_t, int64_t, const TprOptions*) { return 512; }
+// [0..8) call-wide depth range, [64..192) phase counters, from byte 256 one (min, max) pair per depth-clamp slot
+size_t tpr_render_scratch_bytes(int64_t n_img, int64_t, const TprOptions* opt) {
+  const int64_t k = opt ? opt->depth_clamp_group : 0;
+  const int64_t slots = (k > 0 && n_img > 0) ? (n_img + k - 1) / k : 0;
+  return (size_t)(512 + 8 * slots);
+}
 
 // pick rays-per-CTA and threads for render_kernel
 static void render_config(int Dc, int Df, int smem_optin, int& R, int& threads, size_t& smem) {
@@ -667,6 +731,12 @@ static int render_impl(const float* planes_packed, int64_t n_img, int32_t height
   if (opt->flags != TPR_MLP_FP32 && opt->flags != TPR_MLP_BF16 && opt->flags != TPR_MLP_FFMA)
     return fail(TPR_E_OPTION, "tpr_render: unknown decoder flag");
   if (scratch_bytes < tpr_render_scratch_bytes(n_img, n_rays, opt)) return fail(TPR_E_SCRATCH, "tpr_render: scratch too small");
+  if (n_img >= (1ll << 31)) return fail(TPR_E_SHAPE, "tpr_render: too many images");
+  if (opt->plane_sets < 0 || (opt->plane_sets > 0 && n_img % opt->plane_sets != 0))
+    return fail(TPR_E_SHAPE, "tpr_render: n_img must be a multiple of plane_sets");
+  if (opt->depth_clamp_group < 0) return fail(TPR_E_OPTION, "tpr_render: depth_clamp_group < 0");
+  if (opt->output_layout != TPR_LAYOUT_CHANNELS_LAST && opt->output_layout != TPR_LAYOUT_CHANNELS_FIRST)
+    return fail(TPR_E_OPTION, "tpr_render: unknown output_layout");
   DeviceInfo di = device_info();
   if (!di.ok) return fail(TPR_E_DEVICE, "tpr_render: no CUDA device");
 
@@ -676,12 +746,13 @@ static int render_impl(const float* planes_packed, int64_t n_img, int32_t height
   a.origins = origins; a.dirs = dirs; a.jitter = jitter; a.u = u;
   a.rs = ray_start_per_ray; a.re = ray_end_per_ray;
   a.n_rays_total = (long long)n_img * n_rays; a.rays_per_img = n_rays;
-  a.ray_start = (float)opt->ray_start; a.ray_end = (float)opt->ray_end;                 // torch.linspace casts to float32
+  set_depth_constants(a, opt);
   a.box_scale = (float)(2.0 / opt->box_warp);                                           // python float (VR/renderer.py:61)
-  a.lin_step = (a.ray_end - a.ray_start) / (float)(Dc - 1);                             // torch.linspace step, float32
-  a.jitter_scale = (float)((opt->ray_end - opt->ray_start) / (Dc - 1));                 // python float (VR/renderer.py:189)
-  a.inv_start = (float)(1.0 / opt->ray_start); a.inv_end = (float)(1.0 / opt->ray_end); // python floats (:181)
-  a.Dc = Dc; a.Df = Df; a.disparity = opt->disparity_space_sampling; a.white_back = opt->white_back;
+  a.Df = Df; a.white_back = opt->white_back;
+  a.plane_sets = opt->plane_sets > 0 ? opt->plane_sets : (int)n_img;
+  a.nchw = opt->output_layout == TPR_LAYOUT_CHANNELS_FIRST;
+  a.clamp_group = opt->depth_clamp_group;
+  const int n_slots = a.clamp_group > 0 ? (int)((n_img + a.clamp_group - 1) / a.clamp_group) : 0;
   a.rgb = rgb; a.depth = depth; a.wsum = weight_sum; a.fine_depths = fine_depths; a.fine_inds = fine_inds;
   a.range_enc = reinterpret_cast<unsigned*>(scratch);
   {
@@ -696,7 +767,7 @@ static int render_impl(const float* planes_packed, int64_t n_img, int32_t height
   a.dbg = env_int("TPR_PHASE_TIMING", 0) ? reinterpret_cast<long long*>(reinterpret_cast<char*>(scratch) + 64) : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   if (phases & kRangeInit) {
-    range_init_kernel<<<1, 1, 0, st>>>(a.range_enc);
+    range_init_kernel<<<n_slots > 256 ? (n_slots + 255) / 256 : 1, n_slots > 0 ? 256 : 1, 0, st>>>(a.range_enc, n_slots);
     TPR_CHECK_LAUNCH("range_init_kernel");
   }
 
@@ -744,7 +815,7 @@ static int render_impl(const float* planes_packed, int64_t n_img, int32_t height
   }
   if (phases & kFinish) {
     finish_kernel<<<grid_for(a.n_rays_total, 256, di.sms, 4), 256, 0, st>>>(a.range_enc, depth_range_io, depth, a.n_rays_total,
-                                                                            clamp_depth);
+                                                                            clamp_depth, (long long)a.clamp_group * n_rays);
     TPR_CHECK_LAUNCH("finish_kernel");
   }
   return 0;
@@ -834,6 +905,9 @@ int tpr_render_host(const float* planes_host, int64_t n_img, int32_t height, int
   if (n_img <= 0 || n_rays <= 0 || height <= 0 || width <= 0 || (int64_t)height * width > (1 << 24))
     return fail(TPR_E_SHAPE, "tpr_render_host: bad shape");
   if (opt->depth_resolution_importance > 0 && !u) return fail(TPR_E_NULL, "tpr_render_host: NULL u");
+  if (opt->plane_sets != 0 && opt->plane_sets != n_img)
+    return fail(TPR_E_OPTION, "tpr_render_host: plane_sets must be 0 (every image brings its own planes across PCIe)");
+  if (opt->depth_clamp_group != 0) return fail(TPR_E_OPTION, "tpr_render_host: depth_clamp_group must be 0");
   const HostWs w = host_ws_layout(n_img, height, width, n_rays);
   if (workspace_bytes < w.total) return fail(TPR_E_SCRATCH, "tpr_render_host: workspace too small");
   HostPipe* hp = host_pipe((int)(2 * n_img + 4));
@@ -885,7 +959,7 @@ int tpr_render_host(const float* planes_host, int64_t n_img, int32_t height, int
   DeviceInfo di = device_info();
   const long long total = (long long)n_img * n_rays;
   finish_kernel<<<grid_for(total, 256, di.sms, 4), 256, 0, st>>>(reinterpret_cast<unsigned*>(ws + w.scratch), depth_range_io,
-                                                                 d_depth, total, 1);
+                                                                 d_depth, total, 1, 0);
   TPR_CHECK_LAUNCH("finish_kernel");
   TPR_CUDA(cudaMemcpyAsync(depth_host, d_depth, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(depth)");
   // the caller's stream completes only when every output has landed
@@ -915,12 +989,12 @@ int tpr_ray_march(const float* colors, const float* densities, const float* dept
   cudaStream_t st = (cudaStream_t)stream;
   // depth_range[2..3] hold the encoded (min,max) until finish_kernel decodes them into [0..1]
   unsigned* enc = reinterpret_cast<unsigned*>(depth_range) + 2;
-  range_init_kernel<<<1, 1, 0, st>>>(enc);
+  range_init_kernel<<<1, 1, 0, st>>>(enc, -1);
   TPR_CHECK_LAUNCH("range_init_kernel");
   ray_march_kernel<<<grid_for(n_rays, 8, di.sms, 8), 256, 0, st>>>(colors, densities, depths, n_rays, n_samples, n_channels,
                                                                    white_back, rgb, depth, weights, enc);
   TPR_CHECK_LAUNCH("ray_march_kernel");
-  finish_kernel<<<grid_for(n_rays, 256, di.sms, 4), 256, 0, st>>>(enc, depth_range, depth, n_rays, clamp_depth);
+  finish_kernel<<<grid_for(n_rays, 256, di.sms, 4), 256, 0, st>>>(enc, depth_range, depth, n_rays, clamp_depth, 0);
   TPR_CHECK_LAUNCH("finish_kernel");
   return 0;
 }

@@ -48,7 +48,8 @@ def install(reference_package: str = 'training.volumetric_rendering'):
         setattr(cls, name, _dispatch(ours, _saved[(cls, name)], probe))
     # attributes our forward() sets/reads on the (reference-constructed) instance
     for attr, val in (('last_depth_range', None), ('last_fine', None), ('debug_outputs', False),
-                      ('defer_depth_clamp', False), ('_timing_events', None)):
+                      ('defer_depth_clamp', False), ('_timing_events', None), ('cache_packed_planes', False),
+                      ('_plane_cache', None), ('_packed', _r.ImportanceRenderer._packed)):
         setattr(ref_r.ImportanceRenderer, attr, val)
 
 

@@ -108,6 +108,15 @@ def pack_decoder(decoder) -> torch.Tensor:
     return out
 
 
+def _layout_flag(options):
+    mode = options.get('output_layout', 'channels_last')
+    if mode == 'channels_last':
+        return _lib.LAYOUT_CHANNELS_LAST
+    if mode == 'channels_first':
+        return _lib.LAYOUT_CHANNELS_FIRST
+    raise RuntimeError(f"rendering_options['output_layout'] must be 'channels_last' or 'channels_first', got {mode!r}")
+
+
 def _mlp_flag(options):
     mode = options.get('decoder_precision', 'fp32')
     if mode == 'fp32':
@@ -131,6 +140,23 @@ class ImportanceRenderer(torch.nn.Module):
         self.last_fine = None
         self.debug_outputs = False
         self.defer_depth_clamp = False
+        # plane cache: remember the last repacked planes and reuse them while the caller
+        # keeps passing the same, unmodified tensor (gen_videos.py renders 120 frames of one identity)
+        self.cache_packed_planes = False
+        self._plane_cache = None
+
+    def _packed(self, planes):
+        """pack_planes with a one-entry cache.  A hit needs the same storage address, shape and version counter; the
+        cache holds a reference to the tensor it packed, so that address cannot have been recycled for other data."""
+        if isinstance(planes, PackedPlanes) or not self.cache_packed_planes or not isinstance(planes, torch.Tensor):
+            return pack_planes(planes)
+        key = (planes.data_ptr(), tuple(planes.shape), planes._version, planes.device)
+        hit = self._plane_cache
+        if hit is not None and hit[0] == key:
+            return hit[2]
+        pp = pack_planes(planes)
+        self._plane_cache = (key, planes, pp)
+        return pp
 
     # ------------------------------------------------------------------ forward (VR/renderer.py:88-140)
     def forward(self, planes, decoder, ray_origins, ray_directions, rendering_options, *, noise=None, out=None):
@@ -147,11 +173,15 @@ class ImportanceRenderer(torch.nn.Module):
             raise AssertionError('MipRayMarcher only supports `clamp_mode`=`softplus`!')      # VR/ray_marcher.py:35
         if opts.get('density_noise', 0) > 0:
             raise NotImplementedError('density_noise > 0 (VR/renderer.py:146) is not supported by the fused renderer')
-        pp = pack_planes(planes)
+        pp = self._packed(planes)
         n, m, _ = ray_origins.shape
-        if pp.n_img != n or ray_directions.shape != ray_origins.shape:
+        # N cameras over N plane sets (the reference's batch), or F*P cameras over P plane sets, camera n sampling
+        # set n % P: F frames of an orbit, each a batch of P identities, as one call
+        if n % pp.n_img != 0 or ray_directions.shape != ray_origins.shape:
             raise RuntimeError(f'batch mismatch: planes N={pp.n_img}, origins {tuple(ray_origins.shape)}, '
                                f'directions {tuple(ray_directions.shape)}')
+        layout = _layout_flag(opts)
+        clamp_group = int(opts.get('depth_clamp_group', 0))
         dev = ray_origins.device
         dec = pack_decoder(decoder)
         dc = int(opts['depth_resolution'])
@@ -183,16 +213,24 @@ class ImportanceRenderer(torch.nn.Module):
                                 depth_resolution=dc, depth_resolution_importance=df,
                                 disparity_space_sampling=int(bool(opts.get('disparity_space_sampling', False))),
                                 white_back=int(bool(opts.get('white_back', False))), flags=_mlp_flag(opts),
-                                tile_width=0)
-            if out is None:
+                                tile_width=0, plane_sets=pp.n_img, output_layout=layout, depth_clamp_group=clamp_group)
+            if out is None and layout == _lib.LAYOUT_CHANNELS_FIRST:
+                # Memory is [N,32,M] -- the feature image of training/triplane.py:81 -- and the tensor returned is its
+                # [N,M,32] view, so the caller's `permute(0, 2, 1).reshape(N, 32, H, W).contiguous()` is a no-op
+                rgb = torch.empty((n, 32, m), device=dev, dtype=torch.float32).permute(0, 2, 1)
+                depth = torch.empty((n, m, 1), device=dev, dtype=torch.float32)
+                wsum = torch.empty((n, m, 1), device=dev, dtype=torch.float32)
+            elif out is None:
                 rgb = torch.empty((n, m, 32), device=dev, dtype=torch.float32)
                 depth = torch.empty((n, m, 1), device=dev, dtype=torch.float32)
                 wsum = torch.empty((n, m, 1), device=dev, dtype=torch.float32)
             else:
                 rgb, depth, wsum = out
                 for t, c in ((rgb, 32), (depth, 1), (wsum, 1)):
-                    if (tuple(t.shape) != (n, m, c) or t.dtype != torch.float32 or t.device != dev or not t.is_contiguous()):
-                        raise RuntimeError(f'out tensors must be contiguous float32 [{n},{m},{c}] on {dev}')
+                    dense = t.permute(0, 2, 1).is_contiguous() if (c == 32 and layout == _lib.LAYOUT_CHANNELS_FIRST) else t.is_contiguous()
+                    if tuple(t.shape) != (n, m, c) or t.dtype != torch.float32 or t.device != dev or not dense:
+                        raise RuntimeError(f'out tensors must be dense float32 [{n},{m},{c}] on {dev} '
+                                           f"(rgb: the [N,M,32] view of an [N,32,M] buffer when output_layout='channels_first')")
             rng = torch.empty(2, device=dev, dtype=torch.float32)
             nscratch = L.tpr_render_scratch_bytes(n, m, ctypes.byref(o))
             scratch = torch.empty(nscratch, device=dev, dtype=torch.uint8)
@@ -281,7 +319,7 @@ class ImportanceRenderer(torch.nn.Module):
         _forbid_autograd(planes if isinstance(planes, torch.Tensor) else None, xyz)
         if options.get('density_noise', 0) > 0:
             raise NotImplementedError('density_noise > 0 (VR/renderer.py:146) is not supported by the fused renderer')
-        pp = pack_planes(planes)
+        pp = self._packed(planes)
         n, p, _ = xyz.shape
         if pp.n_img != n:
             raise RuntimeError(f'batch mismatch: planes N={pp.n_img}, coordinates N={n}')
@@ -296,8 +334,35 @@ class ImportanceRenderer(torch.nn.Module):
         return {'rgb': rgb, 'sigma': sigma}
 
     # ------------------------------------------------------------------ the remaining public helpers
-    def sample_stratified(self, ray_origins, ray_start, ray_end, depth_resolution, disparity_space_sampling=False):
-        raise NotImplementedError('sample_stratified is fused into forward() (csrc/triplane_b200.cu: coarse_depth)')
+    def sample_stratified(self, ray_origins, ray_start, ray_end, depth_resolution, disparity_space_sampling=False, *,
+                          jitter=None):
+        """Coarse depths [N,M,D,1] (VR/renderer.py:169-192); ``ray_start`` / ``ray_end`` are python floats or per-ray
+        tensors [N,M,1].  forward() never calls this (the depths are produced inside the fused kernel by the same
+        device function); it exists because it is part of the reference class.  ``jitter`` [N,M,D,1] overrides the
+        ``torch.rand`` draw."""
+        ray_origins = _require_cuda_f32(ray_origins, 'ray_origins', (3,))
+        n, m, _ = ray_origins.shape
+        dev, d = ray_origins.device, int(depth_resolution)
+        per_ray = isinstance(ray_start, torch.Tensor)
+        if per_ray != isinstance(ray_end, torch.Tensor):
+            raise RuntimeError('ray_start and ray_end must both be floats or both be tensors')
+        if disparity_space_sampling and per_ray:
+            raise RuntimeError('disparity_space_sampling takes scalar ray limits (VR/renderer.py:174-181)')
+        with torch.cuda.device(dev):
+            if jitter is None:
+                jitter = torch.rand((n, m, d, 1), device=dev, dtype=torch.float32)
+            jitter = _require_cuda_f32(jitter, 'jitter').reshape(n, m, d, 1)
+            rs = _require_cuda_f32(ray_start, 'ray_start').reshape(-1) if per_ray else None
+            re = _require_cuda_f32(ray_end, 'ray_end').reshape(-1) if per_ray else None
+            if per_ray and (rs.numel() != n * m or re.numel() != n * m):
+                raise RuntimeError(f'per-ray limits must have {n * m} elements')
+            o = _lib.TprOptions(ray_start=0.0 if per_ray else float(ray_start), ray_end=0.0 if per_ray else float(ray_end),
+                                box_warp=1.0, depth_resolution=d, depth_resolution_importance=0,
+                                disparity_space_sampling=int(bool(disparity_space_sampling)))
+            out = torch.empty((n, m, d, 1), device=dev, dtype=torch.float32)
+            _lib.check(_lib.lib().tpr_sample_stratified(_ptr(jitter), n * m, _ptr(rs), _ptr(re), ctypes.byref(o), _ptr(out),
+                                                        _stream()), 'tpr_sample_stratified')
+        return out
 
     def sample_importance(self, z_vals, weights, N_importance, *, u=None, return_inds=False):
         """z_vals [N,M,S,1], weights [N,M,S-1,1] -> [N,M,N_importance,1] (VR/renderer.py:194-212)."""

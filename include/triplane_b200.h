@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TPR_ABI_VERSION 1
+#define TPR_ABI_VERSION 2
 
 /* fixed by the reference model: OSGDecoder(32 -> 64 -> 1+32), three planes
  * (training/triplane.py:42,113-122; VR/renderer.py:29-37) */
@@ -69,8 +69,23 @@ typedef struct TprOptions {
   int32_t flags;                 /* TPR_MLP_* */
   int32_t tile_width;            /* perf hint only, never changes results: rays form a square image this many pixels
                                     wide with x fastest (0 = infer from a perfect-square ray count, < 0 = no image) */
-  int32_t reserved[5];
+  int32_t plane_sets;            /* 0 (= n_img): image n samples plane set n, the reference's one-to-one batch.  P > 0:
+                                    planes_packed holds P plane sets and image (camera) n samples set n % P -- several
+                                    frames of the gen_videos.py:153-171 orbit, each a batch of P identities, rendered as ONE
+                                    call against planes packed once.  n_img must be a multiple of P */
+  int32_t output_layout;         /* TPR_LAYOUT_*: how rgb is written */
+  int32_t depth_clamp_group;     /* 0: the depth clamp (VR/ray_marcher.py:50) uses the range of ALL sample depths of the call,
+                                    like one reference forward.  k > 0: every k consecutive images clamp against their own
+                                    range (k = the batch of one reference forward when several forwards are batched) */
+  int32_t reserved[2];
 } TprOptions;
+
+/* output_layout */
+enum {
+  TPR_LAYOUT_CHANNELS_LAST = 0,  /* rgb [N,M,32], what ImportanceRenderer.forward returns (VR/renderer.py:140) */
+  TPR_LAYOUT_CHANNELS_FIRST = 1  /* rgb [N,32,M] = the [N,32,H,W] feature image TriPlaneGenerator.synthesis builds from it with
+                                    permute + contiguous (training/triplane.py:81): the transpose is folded into the store */
+};
 
 int tpr_abi_version(void);
 const char* tpr_last_error(void);
@@ -143,7 +158,8 @@ int tpr_clamp_depth(float* depth, int64_t n, const float* depth_range /*[2] devi
  * device, the only state the library keeps) and `stream`: H2D of image i+1, repack + render of image i and D2H of
  * image i-1 overlap.  `workspace` is a DEVICE buffer of tpr_render_host_workspace_bytes() bytes.
  * Asynchronous like every other entry: the outputs are complete when `stream` has drained.
- * depth_range_io: DEVICE [2], receives the global depth range (may be NULL). */
+ * depth_range_io: DEVICE [2], receives the global depth range (may be NULL).  opt->cameras_per_plane_set must be 0 or 1
+ * (every image brings its own planes across PCIe). */
 size_t tpr_render_host_workspace_bytes(int64_t n_img, int32_t height, int32_t width, int64_t n_rays);
 int tpr_render_host(const float* planes_host, int64_t n_img, int32_t height, int32_t width,
                     const float* decoder_packed,
@@ -171,6 +187,13 @@ int tpr_sample_importance(const float* z_vals, const float* weights, const float
 int tpr_sample_pdf(const float* bins, int32_t bins_stride, const float* weights, const float* u,
                    int64_t n_rays, int32_t n_weights, int32_t n_importance,
                    float* samples, int32_t* inds, void* stream);
+
+/* ---- a7: sample_stratified (VR/renderer.py:169-192), stand-alone ------------------------------ */
+/* jitter [R,D] stands for the torch.rand_like draw (:177,185,190).  Scalar limits from opt (ray_start, ray_end,
+ * depth_resolution, disparity_space_sampling); ray_start_per_ray / ray_end_per_ray [R] (both or neither) select the
+ * per-ray branch (:183-186).  depths [R,D]. */
+int tpr_sample_stratified(const float* jitter, int64_t n_rays, const float* ray_start_per_ray,
+                          const float* ray_end_per_ray, const TprOptions* opt, float* depths, void* stream);
 
 /* ---- a14: math_utils.get_ray_limits_box (VR/math_utils.py:46-98) ------------------------ */
 int tpr_ray_limits_box(const float* origins, const float* dirs, int64_t n_rays,

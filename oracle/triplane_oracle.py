@@ -203,7 +203,10 @@ def run_model(planes, dec: DecoderParams, xyz, box_warp: float):
 # --------------------------------------------------------------------------
 def torch_linspace(start: float, end: float, steps: int) -> np.ndarray:
     """float32 torch.linspace: start+i*step for the lower half, end-(steps-1-i)*step
-    for the upper half (ATen RangeFactories), step computed in float32."""
+    for the upper half (ATen RangeFactories), step computed in float32.  This is the per-element
+    formula of the CUDA kernel (and of the CPU kernel's scalar tail); the CPU kernel's vectorised
+    body computes base+lane*step per SIMD vector instead, which differs from it by <= 2 ulp
+    (tests/golden/stratified.npz, generated on CPU, pins that bound)."""
     start, end = F32(start), F32(end)
     step = (end - start) / F32(steps - 1)
     i = np.arange(steps)
@@ -226,6 +229,18 @@ def stratified_depths(jitter: np.ndarray, ray_start: float, ray_end: float,
         return (F32(1) / (F32(1.0 / ray_start) * (F32(1) - t) + F32(1.0 / ray_end) * t)).astype(F32)
     base = torch_linspace(ray_start, ray_end, d).reshape(1, 1, d, 1)
     return (base + jitter * F32((ray_end - ray_start) / (d - 1))).astype(F32)
+
+
+def stratified_depths_per_ray(jitter: np.ndarray, ray_start: np.ndarray, ray_end: np.ndarray) -> np.ndarray:
+    """Tensor-limits branch (VR/renderer.py:183-186 with math_utils.linspace, VR/math_utils.py:101-118):
+    jitter [N,M,D,1], ray_start / ray_end [N,M,1] -> [N,M,D,1]."""
+    jitter = np.asarray(jitter, F32)
+    rs, re = np.asarray(ray_start, F32), np.asarray(ray_end, F32)
+    d = jitter.shape[2]
+    steps = (np.arange(d, dtype=F32) / F32(d - 1)).reshape(1, 1, d, 1)
+    base = rs[:, :, None] + steps * (re - rs)[:, :, None]
+    delta = (re - rs) / F32(d - 1)
+    return (base + jitter * delta[:, :, None]).astype(F32)
 
 
 # --------------------------------------------------------------------------

@@ -27,11 +27,11 @@ def test_library_exports_every_declared_symbol(pkg):
     for s in header_symbols():
         assert hasattr(lib, s), f'{s} declared in the header but not exported'
     assert set(header_symbols()) == set(pkg._lib.EXPORTED_SYMBOLS), 'binding and header disagree'
-    assert lib.tpr_abi_version() == 1
+    assert lib.tpr_abi_version() == 2
 
 
 def test_options_struct_layout_matches_header(pkg):
-    # 3 doubles + 6 int32 + 5 reserved int32 = 68 -> padded to 72 (8-byte alignment)
+    # 3 doubles + 9 int32 + 2 reserved int32 = 68 -> padded to 72 (8-byte alignment)
     assert ctypes.sizeof(pkg._lib.TprOptions) == 72
 
 
@@ -51,6 +51,18 @@ def test_argument_errors_are_reported_without_a_device(pkg):
     assert rc == -2 and b'depth resolutions' in lib.tpr_last_error()
     with pytest.raises(RuntimeError, match='code -2'):
         pkg._lib.check(rc, 'tpr_render')
+    o = pkg._lib.TprOptions(ray_start=2.25, ray_end=3.3, box_warp=1.0, depth_resolution=8, depth_resolution_importance=8,
+                            plane_sets=3)
+    rc = lib.tpr_render(p, 4, 8, 8, p, p, p, 4, p, p, None, None, ctypes.byref(o), p, p, p, None, None, None, 1, p, 1024, None)
+    assert rc == -2 and b'plane_sets' in lib.tpr_last_error()            # 4 images over 3 plane sets
+    o = pkg._lib.TprOptions(ray_start=2.25, ray_end=3.3, box_warp=1.0, depth_resolution=8, depth_resolution_importance=8,
+                            output_layout=7)
+    rc = lib.tpr_render(p, 4, 8, 8, p, p, p, 4, p, p, None, None, ctypes.byref(o), p, p, p, None, None, None, 1, p, 1024, None)
+    assert rc == -3 and b'output_layout' in lib.tpr_last_error()
+    o = pkg._lib.TprOptions(depth_resolution=8, depth_clamp_group=2)
+    assert lib.tpr_render_scratch_bytes(8, 16, ctypes.byref(o)) == 512 + 8 * 4   # one (min, max) pair per clamp slot
+    assert lib.tpr_sample_stratified(None, 4, None, None, ctypes.byref(o), p, None) == -1
+    assert lib.tpr_sample_stratified(p, 4, p, None, ctypes.byref(o), p, None) == -1  # per-ray limits need both
 
 
 def test_host_shim_rejects_cpu_tensors_and_bad_decoders(pkg):

@@ -88,3 +88,22 @@ def test_softplus_and_edges():
     d = np.linspace(1, 2, 5, dtype=np.float32).reshape(1, 1, 5, 1)
     rgb, depth, w = O.march(np.ones((1, 1, 5, 3), np.float32), np.full((1, 1, 5, 1), -1e4, np.float32), d)
     assert (w == 0).all() and depth[0, 0, 0] == 2.0 and (rgb == -1).all()
+
+
+def test_stratified_depths_against_reference_fixture():
+    """sample_stratified, all three branches (VR/renderer.py:169-192).  The fixture comes from the reference on CPU, whose
+    torch.linspace is vectorised (base + lane*step per SIMD vector): <= 2 ulp from the per-element CUDA formula the oracle
+    restates; the per-ray branch (math_utils.linspace, plain tensor arithmetic) is bit-exact."""
+    import os
+    from tests.cases import GOLDEN_DIR
+    from tests.stratified_cases import CASES as SC, inputs
+    gold = np.load(os.path.join(GOLDEN_DIR, 'stratified.npz'))
+    for name, (n, m, d, rs, re, disp) in SC.items():
+        jitter, lim = inputs(name)
+        want = gold[name]
+        got = O.stratified_depths(jitter, rs, re, disp) if lim is None else O.stratified_depths_per_ray(jitter, *lim)
+        assert got.shape == want.shape
+        if lim is not None:
+            np.testing.assert_array_equal(got, want)
+        else:
+            assert np.abs(got - want).max() <= 2 * np.spacing(np.float32(want.max()))
