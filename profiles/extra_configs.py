@@ -57,4 +57,34 @@ if not args.skip5:
     xyz_r = xyz[:, perm].contiguous()
     ms = timed(lambda: R.run_model(pp, dec, xyz_r, None, dict(bench.OPTS, decoder_precision=args.mode), want_rgb=False))
     out['config5_shuffled'] = {'points': g ** 3, 'ms': ms, 'points_per_s': g ** 3 / ms * 1e3}
+# config 3 (renderer part): the gen_videos.py orbit of one identity -- 120 frames x 64^2 rays x (96+96) samples
+ap3 = dict(bench.OPTS, depth_resolution=96, depth_resolution_importance=96, decoder_precision=args.mode)
+planes_h, _, _ = bench.make_inputs(torch, dev, 11, n_img=1)
+planes = planes_h.to(dev)
+cams = importlib.import_module('g-nerf_b200.camera_utils')
+c2w, K = cams.orbit_cameras(120)
+c2w, K = torch.from_numpy(c2w).to(dev), torch.from_numpy(K).to(dev)
+samples = 120 * 64 * 64 * 192
+
+
+def frame_loop():                                   # what gen_videos.py does: one forward (and one repack) per frame
+    for f in range(120):
+        o, d = S(c2w[f:f + 1], K[f:f + 1], 64)
+        R(planes, dec, o, d, ap3)
+
+
+def frame_loop_cached():
+    R.cache_packed_planes = True
+    for f in range(120):
+        o, d = S(c2w[f:f + 1], K[f:f + 1], 64)
+        R(planes, dec, o, d, ap3)
+    R.cache_packed_planes = False
+
+
+ms = timed(frame_loop, warm=1, n=3)
+out['config3_frame_loop'] = {'ms_per_orbit': ms, 'ray_samples_per_s': samples / ms * 1e3}
+ms = timed(frame_loop_cached, warm=1, n=3)
+out['config3_frame_loop_plane_cache'] = {'ms_per_orbit': ms, 'ray_samples_per_s': samples / ms * 1e3}
+ms = timed(lambda: pkg.render_frames(R, planes, dec, c2w, K, 64, ap3), warm=1, n=5)
+out['config3_render_frames'] = {'ms_per_orbit': ms, 'ray_samples_per_s': samples / ms * 1e3}
 print(json.dumps(out))
