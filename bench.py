@@ -187,6 +187,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--mode', default='fp32', choices=['fp32', 'bf16', 'fp32_ffma'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--gather', default='peer', choices=['peer', 'nccl'],
+                    help='N > 1: peer = the render kernel stores into every GPU\'s gather buffers over NVLink; '
+                         'nccl = render, then an in-place all-gather (A/B)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -215,16 +218,18 @@ def main():
     samples_per_step = N_IMG * m * (DC + DF)
 
     kernel_events = []
+    peer = pkg.parallel.PeerGather(N_IMG, m) if world > 1 and args.gather == 'peer' else None
 
     def step(record=False):
         """The hot path as a user calls it, inputs resident in HBM.  N > 1: every rank renders its batch into
-        its slice of the gather buffers, the depth range is all-reduced, outputs are all-gathered in place."""
+        its slice of EVERY rank's gather buffers (peer stores in the render kernel's epilogue), the depth range is
+        all-reduced (which also completes the exchange) and the gathered depths are clamped."""
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             renderer._timing_events = (e0, e1)
             kernel_events.append((e0, e1))
         if world > 1:
-            out = pkg.parallel.render_sharded(renderer, planes, decoder, origins, dirs, opts)
+            out = pkg.parallel.render_sharded(renderer, planes, decoder, origins, dirs, opts, peer=peer)
         else:
             out = renderer(planes, decoder, origins, dirs, opts)
         renderer._timing_events = None
@@ -300,8 +305,10 @@ def main():
             'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'bf16-mlp' if args.mode == 'bf16' else 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'per_gpu_batch': N_IMG, 'rays_per_image': m, 'samples_per_ray': DC + DF,
-                       'decoder_precision': args.mode, 'parallelism': f'image-batch sharding x{world}, all-gather of outputs'
-                       if world > 1 else 'single GPU',
+                       'decoder_precision': args.mode,
+                       'parallelism': (f'image-batch sharding x{world}, ' +
+                                       ('outputs gathered by the render kernel (NVLink peer stores) + 2-float all-reduce'
+                                        if peer is not None else 'NCCL all-gather of outputs')) if world > 1 else 'single GPU',
                        'l2': 'inputs larger than L2: 201 MB planes + 201 MB repack + 50 MB noise per step (126 MB L2)',
                        'step': 'ImportanceRenderer.forward incl. plane repack, decoder pack, both torch.rand draws'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
@@ -320,6 +327,8 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'], _ = cpu_baseline(48)
         print(json.dumps(line))
+    if peer is not None:
+        peer.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -9,7 +9,7 @@ from ctypes import c_char_p, c_double, c_float, c_int32, c_int64, c_size_t, c_vo
 
 from .build import LIB_PATH
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MLP_FP32, MLP_BF16, MLP_FFMA = 0, 1, 2
 LAYOUT_CHANNELS_LAST, LAYOUT_CHANNELS_FIRST = 0, 1
 
@@ -20,6 +20,14 @@ class TprOptions(ctypes.Structure):
                 ('disparity_space_sampling', c_int32), ('white_back', c_int32),
                 ('flags', c_int32), ('tile_width', c_int32), ('plane_sets', c_int32),
                 ('output_layout', c_int32), ('depth_clamp_group', c_int32), ('reserved', c_int32 * 2)]
+
+
+MAX_PEERS, PEER_HANDLE_BYTES = 15, 64
+
+
+class TprPeerSinks(ctypes.Structure):
+    _fields_ = [('n_peers', c_int32), ('reserved', c_int32), ('rgb', c_void_p * MAX_PEERS),
+                ('depth', c_void_p * MAX_PEERS), ('weight_sum', c_void_p * MAX_PEERS)]
 
 
 _P = c_void_p
@@ -36,6 +44,13 @@ _SIGNATURES = {
     'tpr_render_scratch_bytes': (c_size_t, [c_int64, c_int64, ctypes.POINTER(TprOptions)]),
     'tpr_render': (ctypes.c_int, [_P, c_int64, c_int32, c_int32, _P, _P, _P, c_int64, _P, _P, _P, _P,
                                   ctypes.POINTER(TprOptions), _P, _P, _P, _P, _P, _P, c_int32, _P, c_size_t, _P]),
+    'tpr_render_peers': (ctypes.c_int, [_P, c_int64, c_int32, c_int32, _P, _P, _P, c_int64, _P, _P, _P, _P,
+                                        ctypes.POINTER(TprOptions), _P, _P, _P, _P, _P, c_size_t,
+                                        ctypes.POINTER(TprPeerSinks), _P]),
+    'tpr_peer_alloc': (ctypes.c_int, [c_size_t, ctypes.POINTER(c_void_p), ctypes.c_char_p]),
+    'tpr_peer_open': (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(c_void_p)]),
+    'tpr_peer_close': (ctypes.c_int, [_P]),
+    'tpr_peer_free': (ctypes.c_int, [_P]),
     'tpr_clamp_depth': (ctypes.c_int, [_P, c_int64, _P, _P]),
     'tpr_render_host_workspace_bytes': (c_size_t, [c_int64, c_int32, c_int32, c_int64]),
     'tpr_render_host': (ctypes.c_int, [_P, c_int64, c_int32, c_int32, _P, _P, _P, c_int64, _P, _P,

@@ -13,12 +13,13 @@ SOURCES = ['triplane_b200.cu', 'tpr_tc_debug.cu', 'tpr_render_tc.cu', 'tpr_rende
 HEADERS = [os.path.join(CSRC, 'tpr_device.cuh'), os.path.join(CSRC, 'tpr_render.cuh'), os.path.join(CSRC, 'tpr_tc.cuh'), os.path.join(ROOT, 'include', 'triplane_b200.h')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-shared', '-Xcompiler', '-fPIC', '--threads', '0']
+              '-Xcompiler', '-fPIC']
+OBJ_DIR = os.path.join(LIB_DIR, 'obj')
 
 
-def _digest():
+def _digest(paths):
     h = hashlib.sha256()
-    for f in [os.path.join(CSRC, s) for s in SOURCES] + HEADERS:
+    for f in paths:
         with open(f, 'rb') as fh:
             h.update(fh.read())
     h.update(' '.join(NVCC_FLAGS).encode())
@@ -26,24 +27,35 @@ def _digest():
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile if the sources changed since the last build; return the library path."""
-    os.makedirs(LIB_DIR, exist_ok=True)
-    stamp = os.path.join(LIB_DIR, 'libtriplane_b200.sha256')
-    dig = _digest()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
-        return LIB_PATH
+    """Compile what changed since the last build (one object per source, compiled in parallel, then linked);
+    return the library path."""
+    os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + ['-I', os.path.join(ROOT, 'include'), '-I', CSRC]
-    if verbose:
-        cmd += ['-Xptxas', '-v']
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ['-o', LIB_PATH]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
-    with open(stamp, 'w') as fh:
-        fh.write(dig)
+    jobs, objs = [], []
+    for src in SOURCES:
+        path = os.path.join(CSRC, src)
+        obj = os.path.join(OBJ_DIR, src[:-3] + '.o')
+        stamp = obj + '.sha256'
+        dig = _digest([path] + HEADERS)
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+            continue
+        cmd = [nvcc] + NVCC_FLAGS + ['-I', os.path.join(ROOT, 'include'), '-I', CSRC] + (['-Xptxas', '-v'] if verbose else []) + \
+              ['-c', path, '-o', obj]
+        jobs.append((src, stamp, dig, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, stamp, dig, proc in jobs:
+        out, _ = proc.communicate()
+        if proc.returncode != 0:
+            raise RuntimeError(f'nvcc failed on {src}:\n{out}')
+        if verbose:
+            print(out)
+        with open(stamp, 'w') as fh:
+            fh.write(dig)
+    if jobs or not os.path.exists(LIB_PATH):
+        res = subprocess.run([nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a'] + objs + ['-o', LIB_PATH],
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError('link failed:\n' + res.stdout + res.stderr)
     return LIB_PATH
 
 

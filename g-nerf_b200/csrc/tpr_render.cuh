@@ -5,6 +5,12 @@
 
 namespace tpr {
 
+// Multi-GPU: where this call's outputs are ALSO stored -- the same slice of every peer GPU's gather buffers, through
+// peer-mapped (NVLink) device pointers.  The render kernel's epilogue writes the 136 bytes per ray to every sink, so
+// the "all-gather" of SURVEY.md section 8(e) is part of the render and overlaps it ray group by ray group.
+constexpr int kMaxPeers = 15;
+struct PeerSinks { int n; float* rgb[kMaxPeers]; float* depth[kMaxPeers]; float* wsum[kMaxPeers]; };
+
 struct RenderArgs {
   const float* planes; int H, W;
   const float* dec;
@@ -22,6 +28,7 @@ struct RenderArgs {
   int plane_sets;                        // >= 1: image (camera) n samples plane set n % plane_sets
   int nchw;                              // != 0: rgb is written channels-first, [N,32,M] (training/triplane.py:81)
   int clamp_group;                       // k > 0: images [j*k, (j+1)*k) share a depth-clamp range (slot j); 0: one range
+  PeerSinks peers;                       // n > 0: every output store is repeated into these peer buffers
 };
 
 // Depth ranges in the scratch block (unsigned words, ordered-uint encoded): [0..1] whole call, then from

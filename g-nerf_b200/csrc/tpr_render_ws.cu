@@ -613,8 +613,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
         if (lane == 0) {
           const long long g = gg.ray0 + (long long)r * gg.rstride;
           rayw[r] = wsum;
-          a.depth[g] = dnum / wsum;                   // NaN -> inf and the clamp happen in finish_kernel
+          const float dq = dnum / wsum;               // NaN -> inf and the clamp happen in finish_kernel
+          a.depth[g] = dq;
           a.wsum[g] = wsum;
+          for (int p = 0; p < a.peers.n; ++p) { a.peers.depth[p][g] = dq; a.peers.wsum[p][g] = wsum; }   // NVLink stores
         }
       }
       RAY_SYNC();
@@ -674,21 +676,25 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
         const float wsr = rayw[r];
         long long cstride;
         float* dst1 = rgb_ptr(a, gg.ray0 + (long long)r * gg.rstride, gg.n, cstride) + 16 * hc * cstride;
-        float4* dst = reinterpret_cast<float4*>(dst1);
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          float o4[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float v = acc[4 * c4 + c];
-            if (a.white_back) v = v + 1.0f - wsr;      // VR/ray_marcher.py:52-53
-            o4[c] = v * 2.0f - 1.0f;                   // :55
-          }
+        for (int c = 0; c < 16; ++c) {
+          float v = acc[c];
+          if (a.white_back) v = v + 1.0f - wsr;        // VR/ray_marcher.py:52-53
+          acc[c] = v * 2.0f - 1.0f;                    // :55
+        }
+        // this GPU's buffer first, then the same element of every peer's gather buffer (peer-mapped pointers: the
+        // stores travel over NVLink while the other warps of the SM keep rendering)
+        const long long eoff = dst1 - a.rgb;
+#pragma unroll 1
+        for (int p = -1; p < a.peers.n; ++p) {
+          float* d1 = p < 0 ? dst1 : a.peers.rgb[p] + eoff;
           if (a.nchw) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) dst1[(4 * c4 + c) * cstride] = o4[c];
+            for (int c = 0; c < 16; ++c) d1[c * cstride] = acc[c];
           } else {
-            dst[c4] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+            float4* dst = reinterpret_cast<float4*>(d1);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) dst[c4] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
           }
         }
       }

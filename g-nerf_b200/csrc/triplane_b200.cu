@@ -412,6 +412,20 @@ __global__ void clamp_depth_kernel(float* __restrict__ depth, long long n, const
   }
 }
 
+// copy one GPU's rendered outputs into the peers' gather buffers (plain stores through peer-mapped pointers)
+__global__ void peer_scatter_kernel(const PeerSinks peers, const float* __restrict__ rgb, const float* __restrict__ depth,
+                                    const float* __restrict__ wsum, long long n_rays) {
+  const long long n4 = n_rays * (kC / 4);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(rgb)[i];
+    for (int p = 0; p < peers.n; ++p) reinterpret_cast<float4*>(peers.rgb[p])[i] = v;
+    if (i < n_rays) {
+      const float d = depth[i], w = wsum[i];
+      for (int p = 0; p < peers.n; ++p) { peers.depth[p][i] = d; peers.wsum[p][i] = w; }
+    }
+  }
+}
+
 // =======================================================================================
 // a9 stand-alone: MipRayMarcher2.forward, one warp per ray, samples in the given order
 // =======================================================================================
@@ -716,7 +730,8 @@ static int render_impl(const float* planes_packed, int64_t n_img, int32_t height
                        const float* origins, const float* dirs, int64_t n_rays, const float* jitter, const float* u,
                        const float* ray_start_per_ray, const float* ray_end_per_ray, const TprOptions* opt, float* rgb,
                        float* depth, float* weight_sum, float* fine_depths, int32_t* fine_inds, float* depth_range_io,
-                       int32_t clamp_depth, void* scratch, size_t scratch_bytes, void* stream, int phases) {
+                       int32_t clamp_depth, void* scratch, size_t scratch_bytes, void* stream, int phases,
+                       const TprPeerSinks* peers = nullptr) {
   if (!planes_packed || !decoder_packed || !origins || !dirs || !jitter || !opt || !rgb || !depth || !weight_sum || !scratch)
     return fail(TPR_E_NULL, "tpr_render: NULL pointer");
   if ((ray_start_per_ray == nullptr) != (ray_end_per_ray == nullptr))
@@ -755,6 +770,15 @@ static int render_impl(const float* planes_packed, int64_t n_img, int32_t height
   const int n_slots = a.clamp_group > 0 ? (int)((n_img + a.clamp_group - 1) / a.clamp_group) : 0;
   a.rgb = rgb; a.depth = depth; a.wsum = weight_sum; a.fine_depths = fine_depths; a.fine_inds = fine_inds;
   a.range_enc = reinterpret_cast<unsigned*>(scratch);
+  if (peers) {
+    if (peers->n_peers < 0 || peers->n_peers > TPR_MAX_PEERS) return fail(TPR_E_SHAPE, "tpr_render_peers: n_peers out of range");
+    if (clamp_depth) return fail(TPR_E_OPTION, "tpr_render_peers: the depth clamp needs the all-reduced range; pass clamp_depth = 0");
+    a.peers.n = peers->n_peers;
+    for (int p = 0; p < peers->n_peers; ++p) {
+      if (!peers->rgb[p] || !peers->depth[p] || !peers->weight_sum[p]) return fail(TPR_E_NULL, "tpr_render_peers: NULL peer pointer");
+      a.peers.rgb[p] = peers->rgb[p]; a.peers.depth[p] = peers->depth[p]; a.peers.wsum[p] = peers->weight_sum[p];
+    }
+  }
   {
     // column grouping needs the rays to be a square image with x fastest (what RaySampler produces); the caller
     // can say so through tile_width, otherwise it is inferred from a perfect-square ray count
@@ -781,6 +805,7 @@ static int render_impl(const float* planes_packed, int64_t n_img, int32_t height
     if (rc > 0) return cuda_fail((cudaError_t)rc, "render_ws_kernel");
     done = rc == 0;                       // < 0: does not fit shared memory, fall through
   }
+  const bool kernel_stores_to_peers = done;     // only the warp-specialised kernel has the peer stores in its epilogue
   if (done) {
   } else if (use_tc) {
     // decoder on the tensor cores: 3xTF32 for the fp32 parity mode, bf16 operands for the PSNR mode
@@ -813,6 +838,11 @@ static int render_impl(const float* planes_packed, int64_t n_img, int32_t height
     kern<<<(unsigned)grid, threads, smem, st>>>(a);
     TPR_CHECK_LAUNCH("render_kernel");
   }
+  if (a.peers.n > 0 && !kernel_stores_to_peers) {
+    // sample counts that do not fit the warp-specialised kernel: forward this GPU's outputs after the render
+    peer_scatter_kernel<<<grid_for(a.n_rays_total * kC, 256, di.sms, 8), 256, 0, st>>>(a.peers, rgb, depth, weight_sum, a.n_rays_total);
+    TPR_CHECK_LAUNCH("peer_scatter_kernel");
+  }
   if (phases & kFinish) {
     finish_kernel<<<grid_for(a.n_rays_total, 256, di.sms, 4), 256, 0, st>>>(a.range_enc, depth_range_io, depth, a.n_rays_total,
                                                                             clamp_depth, (long long)a.clamp_group * n_rays);
@@ -829,6 +859,55 @@ int tpr_render(const float* planes_packed, int64_t n_img, int32_t height, int32_
   return render_impl(planes_packed, n_img, height, width, decoder_packed, origins, dirs, n_rays, jitter, u, ray_start_per_ray,
                      ray_end_per_ray, opt, rgb, depth, weight_sum, fine_depths, fine_inds, depth_range_io, clamp_depth, scratch,
                      scratch_bytes, stream, kRangeInit | kFinish);
+}
+
+int tpr_render_peers(const float* planes_packed, int64_t n_img, int32_t height, int32_t width, const float* decoder_packed,
+                     const float* origins, const float* dirs, int64_t n_rays, const float* jitter, const float* u,
+                     const float* ray_start_per_ray, const float* ray_end_per_ray, const TprOptions* opt, float* rgb,
+                     float* depth, float* weight_sum, float* depth_range_io, void* scratch, size_t scratch_bytes,
+                     const TprPeerSinks* peers, void* stream) {
+  if (!peers) return fail(TPR_E_NULL, "tpr_render_peers: NULL peers");
+  return render_impl(planes_packed, n_img, height, width, decoder_packed, origins, dirs, n_rays, jitter, u, ray_start_per_ray,
+                     ray_end_per_ray, opt, rgb, depth, weight_sum, nullptr, nullptr, depth_range_io, 0, scratch,
+                     scratch_bytes, stream, kRangeInit | kFinish, peers);
+}
+
+// peer-mappable gather buffers (see the header): the one place the library owns device memory, with explicit
+// create / destroy.  cudaIpc* needs a cudaMalloc allocation whose base address is the exported pointer, which a
+// sub-allocating caller (PyTorch's caching allocator) cannot promise.
+int tpr_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle_out) {
+  if (!dev_ptr || !handle_out) return fail(TPR_E_NULL, "tpr_peer_alloc: NULL pointer");
+  if (bytes == 0) return fail(TPR_E_SHAPE, "tpr_peer_alloc: zero bytes");
+  static_assert(sizeof(cudaIpcMemHandle_t) == TPR_PEER_HANDLE_BYTES, "handle size");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(peer buffer)");
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "cudaIpcGetMemHandle"); }
+  memcpy(handle_out, &h, sizeof(h));
+  *dev_ptr = p;
+  return 0;
+}
+int tpr_peer_open(const unsigned char* handle, void** dev_ptr) {
+  if (!handle || !dev_ptr) return fail(TPR_E_NULL, "tpr_peer_open: NULL pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle (no NVLink / PCIe peer access between these GPUs?)");
+  *dev_ptr = p;
+  return 0;
+}
+int tpr_peer_close(void* dev_ptr) {
+  if (!dev_ptr) return fail(TPR_E_NULL, "tpr_peer_close: NULL pointer");
+  cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "cudaIpcCloseMemHandle");
+}
+int tpr_peer_free(void* dev_ptr) {
+  if (!dev_ptr) return fail(TPR_E_NULL, "tpr_peer_free: NULL pointer");
+  cudaError_t e = cudaFree(dev_ptr);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "cudaFree(peer buffer)");
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -2,11 +2,15 @@
 
 Partition: by image first -- a GPU renders the images whose planes it holds, so
 planes never move -- then by contiguous ray range inside an image when there are fewer images than GPUs.
-The only data-path collectives are
-  * an all-reduce (MIN, MAX) of two scalars: the global depth range MipRayMarcher2 clamps against
-    (training/volumetric_rendering/ray_marcher.py:50 reduces over the whole batch), and
-  * an in-place all-gather of rgb [.,32] + depth [.,1] + weight_sum [.,1] (136 B per ray): every rank
-    renders straight into its own slice of the gather buffers, so there is no staging copy.
+The exchange is 136 bytes per ray (rgb [.,32] + depth [.,1] + weight_sum [.,1]) to every GPU, plus the one
+cross-ray dependency: the global depth range MipRayMarcher2 clamps against
+(training/volumetric_rendering/ray_marcher.py:50 reduces over the whole batch).  Two ways:
+  * PeerGather (the GPU product path): the render kernel's epilogue stores each ray's outputs into this
+    rank's slice of EVERY rank's gather buffers through peer-mapped NVLink pointers (tpr_render_peers), so the
+    gather rides along with the render; one 2-float all-reduce carries the depth range and is also the barrier
+    that completes the exchange.  No all-gather, no staging copy.
+  * NCCL / gloo collectives (CPU tests, GPUs without peer access): every rank renders straight into its own
+    slice of the gather buffers, then one all-reduce of the range and an in-place all-gather.
 The host logic is backend-agnostic (NCCL on GPUs, gloo in the CPU tests); the per-shard render is the fused
 CUDA renderer unless a test injects another callable.
 """
@@ -60,6 +64,127 @@ def shard_ray_counts(plan: Sequence[Sequence[Shard]]) -> List[int]:
     return [sum(s.n_rays for s in shards) for shards in plan]
 
 
+class _DeviceBlock:
+    """A raw device allocation as a __cuda_array_interface__ object, so torch can wrap it without copying."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {'shape': (n_floats,), 'typestr': '<f4', 'data': (ptr, False), 'version': 2,
+                                         'strides': None}
+
+
+class PeerGather:
+    """Gather buffers of one rank, mapped into every other rank of the node (NVLink / NVSwitch peer access).
+
+    Holds ``sets`` (default 2, used alternately) groups of three buffers -- rgb [world,n,m,32], depth [world,n,m,1],
+    weight_sum [world,n,m,1] -- in ONE peer-mappable allocation (tpr_peer_alloc), exchanges the 64-byte IPC handles
+    with ``all_gather_object`` and maps every peer's allocation (tpr_peer_open).  ``sinks(k)`` is the TprPeerSinks
+    the render kernel needs to store this rank's slice into every peer; ``views(k)`` are this rank's own buffers.
+
+    Why two sets: rank A's render of step s+1 writes into rank B's buffers while B may still be reading step s.
+    With alternating sets a buffer is rewritten at step s+2, and A can only start that render after B has entered
+    the all-reduce of step s+1, i.e. after B's stream has passed everything B enqueued for step s.  The tensors
+    ``render_sharded`` returns therefore stay valid until the call after the next one.
+    """
+
+    def __init__(self, n_local: int, n_rays: int, *, group=None, device=None, sets: int = 2):
+        import ctypes
+        from . import _lib
+        if not dist.is_initialized():
+            raise RuntimeError('PeerGather needs an initialised torch.distributed process group')
+        self.group, self.world, self.rank = group, dist.get_world_size(group), dist.get_rank(group)
+        if self.world - 1 > _lib.MAX_PEERS:
+            raise RuntimeError(f'PeerGather supports at most {_lib.MAX_PEERS + 1} ranks')
+        self.n, self.m, self.sets = int(n_local), int(n_rays), int(sets)
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self._step = 0
+        self._lib, self._ctypes = _lib, ctypes
+        rays = self.world * self.n * self.m
+        self._set_floats = rays * 34
+        self._off = {'rgb': 0, 'depth': rays * 32, 'wsum': rays * 33}            # float offsets inside a set
+        n_floats = self._set_floats * self.sets
+        L = _lib.lib()
+        ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(_lib.PEER_HANDLE_BYTES)
+        with torch.cuda.device(self.device):
+            _lib.check(L.tpr_peer_alloc(n_floats * 4, ctypes.byref(ptr), handle), 'tpr_peer_alloc')
+            self._own = ptr.value
+            self.flat = torch.as_tensor(_DeviceBlock(self._own, n_floats), device=self.device)
+            self.flat.zero_()
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle.raw, group=group)
+            self._peer_base = {}
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    continue
+                p = ctypes.c_void_p()
+                _lib.check(L.tpr_peer_open(h, ctypes.byref(p)), f'tpr_peer_open(rank {r})')
+                self._peer_base[r] = p.value
+        dist.barrier(group=group)            # nobody renders into a peer before every rank has zeroed and mapped
+
+    def next_set(self) -> int:
+        k = self._step % self.sets
+        self._step += 1
+        return k
+
+    def views(self, k: int):
+        """(rgb [world,n,m,32], depth [world,n,m,1], weight_sum [world,n,m,1]) of set k in this rank's memory."""
+        base = k * self._set_floats
+        rays = self.world * self.n * self.m
+        mk = lambda off, c: self.flat[base + off: base + off + rays * c].view(self.world, self.n, self.m, c)   # noqa: E731
+        return mk(self._off['rgb'], 32), mk(self._off['depth'], 1), mk(self._off['wsum'], 1)
+
+    def sinks(self, k: int):
+        """TprPeerSinks: where THIS rank's slice of set k lives in every peer's allocation."""
+        s = self._lib.TprPeerSinks()
+        s.n_peers = self.world - 1
+        slice_rays = self.rank * self.n * self.m
+        for i, (r, pb) in enumerate(sorted(self._peer_base.items())):
+            b = pb + 4 * k * self._set_floats
+            s.rgb[i] = b + 4 * (self._off['rgb'] + slice_rays * 32)
+            s.depth[i] = b + 4 * (self._off['depth'] + slice_rays)
+            s.weight_sum[i] = b + 4 * (self._off['wsum'] + slice_rays)
+        return s
+
+    def close(self):
+        """Unmap the peers and free the allocation (collective: every rank must call it)."""
+        if self._own is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        L = self._lib.lib()
+        with torch.cuda.device(self.device):
+            for p in self._peer_base.values():
+                self._lib.check(L.tpr_peer_close(self._ctypes.c_void_p(p)), 'tpr_peer_close')
+            dist.barrier(group=self.group)   # every mapping is gone before anybody frees
+            self.flat = None
+            self._lib.check(L.tpr_peer_free(self._ctypes.c_void_p(self._own)), 'tpr_peer_free')
+        self._own, self._peer_base = None, {}
+
+
+def _all_reduce_range(lo, hi, world, group):
+    """(min over ranks of lo, max over ranks of hi) with ONE all-reduce: MAX of (-lo, hi)."""
+    t = torch.cat([-lo, hi])
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return -t[0:1], t[1:2]
+
+
+def _render_peer_gather(renderer, planes, decoder, ray_origins, ray_directions, rendering_options, noise, peer: 'PeerGather'):
+    """render + gather in one kernel: see PeerGather."""
+    n, m, _ = ray_origins.shape
+    if (n, m) != (peer.n, peer.m):
+        raise RuntimeError(f'PeerGather was built for {peer.n} images x {peer.m} rays per rank, got {n} x {m}')
+    k = peer.next_set()
+    bufs = peer.views(k)
+    out = tuple(b[peer.rank] for b in bufs)
+    renderer(planes, decoder, ray_origins, ray_directions, rendering_options, noise=noise, out=out, peer_sinks=peer.sinks(k))
+    rng = renderer.last_depth_range
+    # the depth range of the whole batch; on every rank this all-reduce completes only after every peer's render
+    # kernel (and with it the peer's stores into this rank's buffers) has finished: it is the exchange's barrier
+    lo, hi = _all_reduce_range(rng[0:1], rng[1:2], peer.world, peer.group)
+    _clamp_cuda(bufs[1], lo, hi)             # nan_to_num + clamp of ALL gathered depths (4 bytes per ray)
+    return tuple(b.view(peer.world * n, m, -1) for b in bufs)
+
+
 def _default_local_render(renderer, planes, decoder, origins, dirs, options, noise, out):
     """Render one rank's rays with the fused CUDA renderer, leaving the global depth clamp to the caller."""
     renderer.defer_depth_clamp = True
@@ -71,13 +196,17 @@ def _default_local_render(renderer, planes, decoder, origins, dirs, options, noi
 
 
 def render_sharded(renderer, planes, decoder, ray_origins, ray_directions, rendering_options, *,
-                   group=None, noise=None, local_render: Optional[Callable] = None, gather: bool = True):
-    """Render THIS rank's images and return the whole job's outputs.
+                   group=None, noise=None, local_render: Optional[Callable] = None, gather: bool = True,
+                   peer: Optional[PeerGather] = None):
+    """Render THIS rank's images and return the whole job's outputs.  With ``peer`` (a PeerGather built once for
+    this shape) the gather happens inside the render kernel over NVLink; without it, through collectives.
 
     planes [n_local,3,32,H,W], ray_origins / ray_directions [n_local,M,3]: this rank's share (image-sharded:
     every rank holds the same number of images).  Returns (rgb [world*n_local,M,32], depth [...,1],
     weight_sum [...,1]) in rank order when ``gather`` is true, else this rank's slice after the global clamp.
     """
+    if peer is not None:
+        return _render_peer_gather(renderer, planes, decoder, ray_origins, ray_directions, rendering_options, noise, peer)
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     n, m, _ = ray_origins.shape
@@ -91,10 +220,7 @@ def render_sharded(renderer, planes, decoder, ray_origins, ray_directions, rende
         if dst.data_ptr() != src.data_ptr():          # a local_render that ignored `out`
             dst.copy_(src)
     # the one cross-ray dependency: clamp(depth, min(all depths), max(all depths))
-    lo, hi = rng[0:1].clone(), rng[1:2].clone()
-    if world > 1:
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    lo, hi = _all_reduce_range(rng[0:1], rng[1:2], world, group)
     d = out[1]
     if d.is_cuda:
         _clamp_cuda(d, lo, hi)

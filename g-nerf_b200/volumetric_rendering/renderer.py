@@ -159,12 +159,15 @@ class ImportanceRenderer(torch.nn.Module):
         return pp
 
     # ------------------------------------------------------------------ forward (VR/renderer.py:88-140)
-    def forward(self, planes, decoder, ray_origins, ray_directions, rendering_options, *, noise=None, out=None):
+    def forward(self, planes, decoder, ray_origins, ray_directions, rendering_options, *, noise=None, out=None,
+                peer_sinks=None):
         """``noise=(jitter [N,M,Dc,1], u [N*M,Df])`` overrides the two uniform draws (used by parity
         tests, which must feed the oracle and the kernels the same numbers); by default they are drawn
         with the reference's own torch calls in the reference's order (VR/renderer.py:190,237).
         ``out=(rgb, depth, weight_sum)`` renders into caller-owned contiguous tensors (the multi-GPU path
-        passes slices of its all-gather buffers)."""
+        passes slices of its gather buffers).  ``peer_sinks`` (a ``_lib.TprPeerSinks``, built by
+        ``parallel.PeerGather``): the kernel also stores every ray's outputs into the peer GPUs' gather buffers over
+        NVLink and leaves the depth clamp to the caller (it needs the all-reduced range)."""
         opts = rendering_options
         ray_origins = _require_cuda_f32(ray_origins, 'ray_origins', (3,))
         ray_directions = _require_cuda_f32(ray_directions, 'ray_directions', (3,))
@@ -241,11 +244,17 @@ class ImportanceRenderer(torch.nn.Module):
             ev = self._timing_events          # bench.py: CUDA events bracketing the render launch on this stream
             if ev is not None:
                 ev[0].record()
-            _lib.check(L.tpr_render(_ptr(pp.data), n, pp.height, pp.width, _ptr(dec), _ptr(ray_origins),
-                                    _ptr(ray_directions), m, _ptr(jitter), _ptr(u), _ptr(rs_t), _ptr(re_t),
-                                    ctypes.byref(o), _ptr(rgb), _ptr(depth), _ptr(wsum), _ptr(fine_d), _ptr(fine_i),
-                                    _ptr(rng), 0 if self.defer_depth_clamp else 1, _ptr(scratch), nscratch, _stream()),
-                       'tpr_render')
+            if peer_sinks is not None:
+                _lib.check(L.tpr_render_peers(_ptr(pp.data), n, pp.height, pp.width, _ptr(dec), _ptr(ray_origins),
+                                              _ptr(ray_directions), m, _ptr(jitter), _ptr(u), _ptr(rs_t), _ptr(re_t),
+                                              ctypes.byref(o), _ptr(rgb), _ptr(depth), _ptr(wsum), _ptr(rng), _ptr(scratch),
+                                              nscratch, ctypes.byref(peer_sinks), _stream()), 'tpr_render_peers')
+            else:
+                _lib.check(L.tpr_render(_ptr(pp.data), n, pp.height, pp.width, _ptr(dec), _ptr(ray_origins),
+                                        _ptr(ray_directions), m, _ptr(jitter), _ptr(u), _ptr(rs_t), _ptr(re_t),
+                                        ctypes.byref(o), _ptr(rgb), _ptr(depth), _ptr(wsum), _ptr(fine_d), _ptr(fine_i),
+                                        _ptr(rng), 0 if self.defer_depth_clamp else 1, _ptr(scratch), nscratch, _stream()),
+                           'tpr_render')
             if ev is not None:
                 ev[1].record()
         self.last_depth_range = rng

@@ -11,7 +11,8 @@
  *   - every pointer is a DEVICE pointer on the current CUDA device unless the name ends in _host;
  *     all tensors are dense, contiguous, float32 (int32/int64 where stated);
  *   - the caller owns all memory (inputs, outputs, scratch); the library never allocates, frees
- *     or keeps a device pointer after the call returns;
+ *     or keeps a device pointer after the call returns (one exception with explicit create /
+ *     destroy calls: the peer-mapped gather buffers of the multi-GPU section, tpr_peer_*);
  *   - every entry point is asynchronous on `stream` (a cudaStream_t passed as void*), never
  *     synchronises the device, and is re-entrant across host threads and streams;
  *   - return value: 0 = success, < 0 = argument error (TPR_E_*), > 0 = a cudaError_t from the
@@ -28,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TPR_ABI_VERSION 2
+#define TPR_ABI_VERSION 3
 
 /* fixed by the reference model: OSGDecoder(32 -> 64 -> 1+32), three planes
  * (training/triplane.py:42,113-122; VR/renderer.py:29-37) */
@@ -148,6 +149,44 @@ int tpr_render(const float* planes_packed, int64_t n_img, int32_t height, int32_
                float* depth_range_io, int32_t clamp_depth,
                void* scratch, size_t scratch_bytes, void* stream);
 int tpr_clamp_depth(float* depth, int64_t n, const float* depth_range /*[2] device*/, void* stream);
+
+/* ---- a13 on several GPUs: render + gather in one kernel ------------------------------ */
+/* One process per GPU renders its share of the images; every GPU needs all rendered features / depths / weight
+ * sums (136 bytes per ray).  Instead of an all-gather AFTER the render, the render kernel's epilogue stores each
+ * ray's outputs into this GPU's slice of its own gather buffers AND into the same slice of every peer's gather
+ * buffers through peer-mapped NVLink pointers, so the exchange rides along with the render, ray group by ray group.
+ * The caller completes the exchange with any cross-GPU barrier that orders "my render kernel finished" before
+ * "peers read" -- the all-reduce of the depth range (VR/ray_marcher.py:50 clamps against the range of the WHOLE
+ * batch) is that barrier -- and then clamps the gathered depths with tpr_clamp_depth.
+ *
+ * Peer buffers: tpr_peer_alloc makes a device allocation that other processes on the same node can map
+ * (cudaMalloc + cudaIpcGetMemHandle; `handle_out` is the 64-byte cudaIpcMemHandle_t to send to the peers by any
+ * means, e.g. torch.distributed.all_gather_object); tpr_peer_open maps a peer's allocation into this process
+ * (cudaIpcOpenMemHandle, enabling peer access); tpr_peer_close / tpr_peer_free undo them. */
+#define TPR_MAX_PEERS 15
+#define TPR_PEER_HANDLE_BYTES 64
+typedef struct TprPeerSinks {
+  int32_t n_peers;                    /* 0 .. TPR_MAX_PEERS */
+  int32_t reserved;
+  float* rgb[TPR_MAX_PEERS];          /* peer-mapped pointers shaped and laid out exactly like rgb / depth / weight_sum */
+  float* depth[TPR_MAX_PEERS];
+  float* weight_sum[TPR_MAX_PEERS];
+} TprPeerSinks;
+int tpr_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle_out /*[64]*/);
+int tpr_peer_open(const unsigned char* handle /*[64]*/, void** dev_ptr);
+int tpr_peer_close(void* dev_ptr);
+int tpr_peer_free(void* dev_ptr);
+/* tpr_render with peer sinks.  clamp_depth must be 0 (the clamp needs the all-reduced range). */
+int tpr_render_peers(const float* planes_packed, int64_t n_img, int32_t height, int32_t width,
+                     const float* decoder_packed,
+                     const float* origins, const float* dirs, int64_t n_rays,
+                     const float* jitter, const float* u,
+                     const float* ray_start_per_ray, const float* ray_end_per_ray,
+                     const TprOptions* opt,
+                     float* rgb, float* depth, float* weight_sum,
+                     float* depth_range_io,
+                     void* scratch, size_t scratch_bytes,
+                     const TprPeerSinks* peers, void* stream);
 
 /* ---- a13 with HOST buffers: the call a CPU-side caller makes (and the one bench.py times end to end) ---------- */
 /* Same result as tpr_render for scalar ray limits, but planes [N,3,32,H,W] (the backbone's layout, NOT repacked),

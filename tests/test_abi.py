@@ -27,12 +27,20 @@ def test_library_exports_every_declared_symbol(pkg):
     for s in header_symbols():
         assert hasattr(lib, s), f'{s} declared in the header but not exported'
     assert set(header_symbols()) == set(pkg._lib.EXPORTED_SYMBOLS), 'binding and header disagree'
-    assert lib.tpr_abi_version() == 2
+    assert lib.tpr_abi_version() == 3
 
 
 def test_options_struct_layout_matches_header(pkg):
     # 3 doubles + 9 int32 + 2 reserved int32 = 68 -> padded to 72 (8-byte alignment)
     assert ctypes.sizeof(pkg._lib.TprOptions) == 72
+
+
+def test_peer_sinks_struct_layout_matches_header(pkg):
+    # 2 int32 + 3 arrays of 15 pointers
+    assert ctypes.sizeof(pkg._lib.TprPeerSinks) == 8 + 3 * 15 * 8
+    lib = pkg._lib.lib()
+    assert lib.tpr_peer_alloc(0, None, None) == -1 and lib.tpr_peer_open(None, None) == -1
+    assert lib.tpr_peer_close(None) == -1 and lib.tpr_peer_free(None) == -1
 
 
 def test_argument_errors_are_reported_without_a_device(pkg):

@@ -23,12 +23,12 @@ def T(a):
     return torch.from_numpy(np.ascontiguousarray(a)).to(dev())
 
 
-def make_decoder(pkg, dec: O.DecoderParams):
+def make_decoder(pkg, dec: O.DecoderParams, device=None):
     m = pkg.OSGDecoder(32, {'decoder_lr_mul': dec.lr_mul, 'decoder_output_dim': 32})
     with torch.no_grad():
         m.net[0].weight.copy_(torch.from_numpy(dec.w1)); m.net[0].bias.copy_(torch.from_numpy(dec.b1))
         m.net[2].weight.copy_(torch.from_numpy(dec.w2)); m.net[2].bias.copy_(torch.from_numpy(dec.b2))
-    return m.to(dev()).requires_grad_(False)
+    return m.to(device or dev()).requires_grad_(False)
 
 
 def test_native_library_is_the_thing_under_test(pkg):
