@@ -23,6 +23,9 @@ int launch_render_tc(RenderArgs a, int bf16, int sms, int smem_optin, long long 
 // warp-specialised tensor-core render path (tpr_render_ws.cu)
 int ws_rays_per_group(int Dc, int Df, int bf16);
 int launch_render_ws(RenderArgs a, int bf16, int sms, int smem_optin, long long n_img, long long n_rays, cudaStream_t st);
+// tpr_run_model_ws.cu
+int launch_run_model_ws(const float* planes, long long n_img, int H, int W, const float* dec, const float* xyz, long long n_pts,
+                        float box_scale, float* rgb, float* sigma, int bf16, int sms, int smem_optin, cudaStream_t st);
 
 // =======================================================================================
 // layout preparation
@@ -657,9 +660,19 @@ static int launch_run_model(bool from_features, const float* planes, int64_t n_i
   if (!from_features && !(box_warp > 0.0)) return fail(TPR_E_OPTION, "run_model: box_warp must be > 0");
   if (flags != TPR_MLP_FP32 && flags != TPR_MLP_BF16 && flags != TPR_MLP_FFMA)
     return fail(TPR_E_OPTION, "run_model: unknown decoder flag");
-  // point queries always run the fp32 FFMA decoder (at least as accurate as any requested mode)
   DeviceInfo di = device_info();
   if (!di.ok) return fail(TPR_E_DEVICE, "run_model: no CUDA device");
+  const float box_scale = (float)(2.0 / box_warp);      // python float (VR/renderer.py:61)
+  // Point queries with enough points to fill the GPU run the warp-specialised tensor-core kernel (3xTF32 in the fp32
+  // mode, bf16 operands in the bf16 mode); small queries, pre-gathered features (tpr_decode) and TPR_MLP_FFMA run the
+  // fp32 FFMA kernel below, whose 32-point chunks spread over the SMs at any size.
+  if (!from_features && flags != TPR_MLP_FFMA && (long long)n_img * n_pts >= env_int("TPR_RM_WS_MIN_POINTS", 1 << 16) &&
+      !env_int("TPR_FORCE_FFMA", 0)) {
+    int rc = launch_run_model_ws(planes, n_img, H, W, dec, in, n_pts, box_scale, rgb, sigma, flags == TPR_MLP_BF16, di.sms,
+                                 di.smem_optin, (cudaStream_t)stream);
+    if (rc > 0) return cuda_fail((cudaError_t)rc, "run_model_ws_kernel");
+    if (rc == 0) return 0;
+  }
   const size_t smem = sizeof(float) * (kDecFloats + kRmWarps * 32 * kC);
   static std::once_flag once[2];
   cudaError_t attr_err = cudaSuccess;
@@ -671,7 +684,6 @@ static int launch_run_model(bool from_features, const float* planes, int64_t n_i
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(run_model_kernel)");
   const long long total = (long long)n_img * n_pts;
   const int grid = grid_for(total, kRmThreads, di.sms, env_int("TPR_RM_WAVES", 3));
-  const float box_scale = (float)(2.0 / box_warp);      // python float (VR/renderer.py:61)
   if (from_features)
     run_model_kernel<true><<<grid, kRmThreads, smem, (cudaStream_t)stream>>>(nullptr, 0, 0, dec, in, n_img, n_pts, 0.f, rgb, sigma);
   else
