@@ -521,6 +521,7 @@ typedef void (*Kernel)(const RenderArgs);
 template <int MODE>
 static Kernel pick_kernel(int S, bool prof) {
   if (prof && S > 64 && S <= 96) return render_ws_kernel<MODE, 4, 3, true>;      // TPR_PHASE_TIMING=1 (profiles/phase_timing.py)
+  if (prof && S > 128) return render_ws_kernel<MODE, 8, 8, true>;
   return S <= 64 ? render_ws_kernel<MODE, 2, 2, false> : S <= 96 ? render_ws_kernel<MODE, 4, 3, false>
        : S <= 128 ? render_ws_kernel<MODE, 4, 4, false> : render_ws_kernel<MODE, 8, 8, false>;
 }

@@ -125,3 +125,26 @@ def decoder_tuple(dec, device):
     """oracle.triplane_oracle.DecoderParams -> the tuple decode() takes."""
     t = lambda a: torch.from_numpy(a).to(device)
     return (t(dec.w1), t(dec.b1), t(dec.w2), t(dec.b2), float(dec.lr_mul))
+
+
+def render_grads(planes, dec, origins, dirs, options, jitter, u, g_rgb, g_depth, g_wsum):
+    """Gradients of L = sum(rgb*g_rgb) + sum(depth*g_depth) + sum(wsum*g_wsum) w.r.t. planes and the four decoder
+    tensors, by autograd through render().  The importance resampling is cut out of the graph exactly where the
+    reference cuts it (torch.no_grad + detach, VR/renderer.py:198,210): importance_depths' output is detached.
+    Returns ((rgb, depth, wsum), (g_planes, g_w1, g_b1, g_w2, g_b2))."""
+    planes = planes.detach().clone().requires_grad_(True)
+    w1, b1, w2, b2 = (p.detach().clone().requires_grad_(True) for p in dec[:4])
+    global importance_depths
+    real = importance_depths
+
+    def detached(depths, weights, uu):
+        with torch.no_grad():
+            return real(depths, weights, uu)
+    importance_depths = detached
+    try:
+        rgb, depth, wsum = render(planes, (w1, b1, w2, b2, dec[4]), origins, dirs, options, jitter, u)
+    finally:
+        importance_depths = real
+    loss = (rgb * g_rgb).sum() + (depth * g_depth).sum() + (wsum * g_wsum).sum()
+    grads = torch.autograd.grad(loss, (planes, w1, b1, w2, b2))
+    return (rgb.detach(), depth.detach(), wsum.detach()), grads

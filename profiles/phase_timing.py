@@ -16,12 +16,14 @@ WS = ['GATHER wait coarse_ready', 'GATHER wait fine_ready', 'GATHER wait a1_free
       'DECODE issue M2', 'DECODE wait m2_done', 'DECODE sigma readback', 'RAYS setup', 'RAYS wait csig', 'RAYS resample',
       'RAYS wait fsig', 'RAYS sort+march', 'RAYS composite']
 TC = ['setup', 'G0+sync', 'issueM1', 'G(t+1)', 'wait bar1/2', 'E1+sync', 'issueM2', 'pass-end wait+sigma', 'resample', 'sort', 'composite']
+D = int(os.environ.get('TPR_PT_DEPTH', '48'))          # samples per pass (96 = gen_videos / config 4)
+RPG = 8 if D <= 48 else 4                                # rays per group the kernel picks
 for mode in sys.argv[1:] or ['fp32']:
-    opts = dict(bench.OPTS, decoder_precision=mode)
+    opts = dict(bench.OPTS, decoder_precision=mode, depth_resolution=D, depth_resolution_importance=D)
     for _ in range(3): R(planes, dec, o, d, opts)
     torch.cuda.synchronize()
     t = R.last_scratch[64:64 + 24 * 8].view(torch.int64).cpu().numpy()
-    ngroups = 16384 * 8 / 8 / 148
+    ngroups = 16384 * 8 / RPG / 148
     names = TC if os.environ.get('TPR_RENDER_IMPL') == '1' else WS
     print(mode, 'CTA0 cycles per group (', int(ngroups), 'groups )')
     for n, v in zip(names, t): print(f'  {n:32s} {int(v / ngroups):7d}')

@@ -25,3 +25,26 @@ def load_case(name):
     opts = dict(O.FFHQ_OPTIONS, depth_resolution=dc, depth_resolution_importance=df, **extra)
     gold = dict(np.load(os.path.join(GOLDEN_DIR, f'{name}.npz')))
     return scene, opts, gold
+
+
+# Gradient fixtures; must stay in sync with tests/golden/make_golden_backward.py (CASES, loss_weights).
+BWD_CASES = {
+    'bwd_ffhq':   (21, 2, 8, 20, 48, 48, 0.5, {}),
+    'bwd_white':  (22, 1, 7, 24, 20, 13, 0.5, {'white_back': True}),
+    'bwd_coarse': (23, 1, 6, 16, 32, 0, 0.5, {'box_warp': 0.6}),
+}
+
+
+def loss_weights(seed, n, m):
+    """Upstream gradients (A for rgb, B for depth, C for weight_sum) of L = sum(rgb*A) + sum(depth*B) + sum(wsum*C)."""
+    rng = np.random.RandomState(seed + 2000)
+    return (rng.standard_normal((n, m, 32)).astype(np.float32), rng.standard_normal((n, m, 1)).astype(np.float32),
+            rng.standard_normal((n, m, 1)).astype(np.float32))
+
+
+def load_bwd_case(name):
+    seed, n, res, pres, dc, df, bs, extra = BWD_CASES[name]
+    scene = O.synthetic_scene(seed, n, res, pres, dc, df, bs)
+    opts = dict(O.FFHQ_OPTIONS, depth_resolution=dc, depth_resolution_importance=df, **extra)
+    gold = dict(np.load(os.path.join(GOLDEN_DIR, f'{name}.npz')))
+    return scene, opts, gold, loss_weights(seed, n, res * res)

@@ -38,3 +38,21 @@ def test_torch_oracle_march_matches_reference_fixture():
     np.testing.assert_array_equal(rgb.numpy(), gold['march_rgb'])
     np.testing.assert_array_equal(depth.numpy(), gold['march_depth'])
     np.testing.assert_array_equal(w.numpy(), gold['march_w'])
+
+
+from tests.cases import BWD_CASES, load_bwd_case
+
+
+@pytest.mark.parametrize('name', list(BWD_CASES))
+def test_torch_oracle_gradients_match_reference_fixture(name):
+    """autograd through the restatement == autograd through the unmodified reference (tests/golden/bwd_*.npz,
+    made by tests/golden/make_golden_backward.py): pins the gradient oracle the CUDA backward is checked against."""
+    scene, opts, gold, (A, B, C) = load_bwd_case(name)
+    t = torch.from_numpy
+    dec = TO.decoder_tuple(scene['dec'], 'cpu')
+    (rgb, depth, wsum), grads = TO.render_grads(t(scene['planes']), dec, t(scene['origins']), t(scene['dirs']), opts,
+                                                t(scene['jitter']), t(scene['u']), t(A), t(B), t(C))
+    np.testing.assert_array_equal(rgb.numpy(), gold['rgb'])
+    for g, k in zip(grads, ('g_planes', 'g_w1', 'g_b1', 'g_w2', 'g_b2')):
+        scale = float(np.abs(gold[k]).max())
+        assert float(np.abs(g.numpy() - gold[k]).max()) <= 1e-6 * max(scale, 1.0), k
