@@ -96,14 +96,26 @@ __device__ __forceinline__ float coarse_depth(const RenderArgs& a, int k, float 
 // (the ray warps are latency bound) -- and scatters (depth, sigma, index) to that rank.  Two equal depths would
 // get the same rank; a rank-sum check detects that and falls back to the network with its index tie-break.
 // ER: rows of 32 elements the rank count looks at (ceil(S/32) <= ER <= E; E itself must be a power of two for the network).
+// `pre_ranked`: tmp / om already hold the ray sorted (pair_rank_scatter below did the first half of this function).
 template <int E, bool kScatter, int ER = E>
 __device__ __forceinline__ void warp_sort_and_weights(const float* z, const float* sg, float* om, int* oi, int S, int lane,
                                                       float& wsum_out, float& dnum_out, float& mn, float& mx,
-                                                      float* tmp = nullptr) {
+                                                      float* tmp = nullptr, bool pre_ranked = false) {
   float key[E]; int idx[E];
   float sgm[E];
   bool ranked = false;
-  if (tmp != nullptr) {
+  if (pre_ranked) {
+    const float* zs = tmp; const float* ss = tmp + S; const int* is = reinterpret_cast<const int*>(om);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int p = lane * E + e;
+      key[e] = p < S ? zs[p] : __int_as_float(0x7f800000);
+      sgm[e] = p < S ? ss[p] : 0.0f;
+      idx[e] = p < S ? is[p] : p;
+    }
+    __syncwarp();                                // `om` is rewritten below
+    ranked = true;
+  } else if (tmp != nullptr) {
     // element p = e*32 + lane (strided: conflict-free reads and writes)
     float ze[ER]; int cnt[ER];
 #pragma unroll
@@ -207,6 +219,98 @@ __device__ __forceinline__ void warp_sort_and_weights(const float* z, const floa
   lmn = warp_min((lane * E) < S ? lmn : __int_as_float(0x7f800000));
   lmx = warp_max(lmx);
   mn = fminf(mn, lmn); mx = fmaxf(mx, lmx);
+}
+
+// Rank count of a ray's S depths by a PAIR of warps (h = 0, 1), for the kernels whose groups have half as many rays as
+// there are ray warps (R = 4: 96+96 samples, the gen_videos.py:127-128 case, where the single-warp count above --
+// S * ceil(S/32) compares per lane with half the ray warps idle -- was the critical path of the whole kernel).
+// Two savings: (1) the coarse depths z[0..Dc) are already ascending (VR/renderer.py:169-192: linspace + jitter below one
+// bin; checked here, not assumed), so a coarse sample's rank is its index plus the number of SMALLER FINE samples and only
+// the fine samples are compared against everything; (2) each warp of the pair counts over half of every range and
+// warp 1 hands its partial counts to warp 0 through `om`.  Warp 0 then scatters (depth, sigma, index) to the ranks:
+// tmp[0..S) depths, tmp[S..2S) sigmas, om[0..S) original indices -- what warp_sort_and_weights(pre_ranked) reads.
+// Returns (to warp 0; warp 1's return value is meaningless) whether the ranks form a permutation; ties, NaNs or
+// a non-ascending coarse row make it false and the caller falls back to the single-warp path.
+// Needs Dc % 32 == 0 and Df % 8 == 0.  `bar`: a named barrier id private to the pair.
+template <int ER, int E0>
+__device__ __forceinline__ void pair_count_coarse(const float* zc, int n, const float (&ze)[ER], int (&cnt)[ER]) {
+#pragma unroll 2
+  for (int j = 0; j < n; j += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(zc + j);
+#pragma unroll
+    for (int e = E0; e < ER; ++e)
+      cnt[e] += (int)(v.x < ze[e]) + (int)(v.y < ze[e]) + (int)(v.z < ze[e]) + (int)(v.w < ze[e]);
+  }
+}
+template <int ER>
+__device__ __forceinline__ bool pair_rank_scatter(const float* z, const float* sg, float* om, float* tmp, int S, int Dc,
+                                                  int lane, int h, int bar) {
+  const int Df = S - Dc, e0 = Dc >> 5;
+  float ze[ER]; int cnt[ER];
+  bool asc = true;
+#pragma unroll
+  for (int e = 0; e < ER; ++e) {
+    const int p = e * 32 + lane;
+    ze[e] = p < S ? z[p] : __int_as_float(0x7f800000);
+    cnt[e] = 0;
+    if (p + 1 < Dc) asc &= z[p] <= z[p + 1];
+  }
+  {   // every row against this warp's half of the fine samples
+    const float* zf = z + Dc + h * (Df >> 1);
+    const int n = Df >> 1;
+#pragma unroll 2
+    for (int j = 0; j < n; j += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(zf + j);
+#pragma unroll
+      for (int e = 0; e < ER; ++e)
+        cnt[e] += (int)(v.x < ze[e]) + (int)(v.y < ze[e]) + (int)(v.z < ze[e]) + (int)(v.w < ze[e]);
+    }
+  }
+  {   // the fine rows (e >= e0) against this warp's half of the coarse samples
+    const float* zc = z + h * (Dc >> 1);
+    const int n = Dc >> 1;
+    if (e0 == 3 && ER > 3) pair_count_coarse<ER, (ER > 3 ? 3 : 0)>(zc, n, ze, cnt);
+    else if (e0 == 2 && ER > 2) pair_count_coarse<ER, (ER > 2 ? 2 : 0)>(zc, n, ze, cnt);
+    else if (e0 == 4 && ER > 4) pair_count_coarse<ER, (ER > 4 ? 4 : 0)>(zc, n, ze, cnt);
+    else {
+#pragma unroll 1
+      for (int j = 0; j < n; ++j) {
+        const float v = zc[j];
+#pragma unroll
+        for (int e = 0; e < ER; ++e) cnt[e] += (int)(e >= e0 && v < ze[e]);
+      }
+    }
+  }
+  int* part = reinterpret_cast<int*>(om);
+  if (h == 1) {
+#pragma unroll
+    for (int e = 0; e < ER; ++e) if (e * 32 + lane < S) part[e * 32 + lane] = cnt[e];
+  }
+  asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory");
+  if (h == 1) return false;
+  int rsum = 0;
+#pragma unroll
+  for (int e = 0; e < ER; ++e) {
+    const int p = e * 32 + lane;
+    if (p < S) { cnt[e] += part[p] + (p < Dc ? p : 0); rsum += cnt[e]; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(kFull, rsum, o);
+  const bool ok = __all_sync(kFull, asc) && rsum == S * (S - 1) / 2;
+  if (ok) {
+    float* zs = tmp; float* ss = tmp + S; int* is = reinterpret_cast<int*>(om);
+    float sv[ER];
+#pragma unroll
+    for (int e = 0; e < ER; ++e) sv[e] = e * 32 + lane < S ? sg[e * 32 + lane] : 0.0f;
+    __syncwarp();                                // every lane has read its partial counts out of `om`
+#pragma unroll
+    for (int e = 0; e < ER; ++e) {
+      const int p = e * 32 + lane;
+      if (p < S) { zs[cnt[e]] = ze[e]; ss[cnt[e]] = sv[e]; is[cnt[e]] = p; }
+    }
+    __syncwarp();
+  }
+  return ok;
 }
 
 // one warp: coarse weights -> smoothed pdf -> CDF -> Df inverse-CDF draws (VR/renderer.py:194-253).

@@ -388,10 +388,17 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
       PROF_ADD(15, pl);
       if (range_slot(a, gg.n) != cur_slot) { range_fold(a, cur_slot, smn, smx, mn, mx, lane); cur_slot = range_slot(a, gg.n); }
       // ---- sort + final march: omega per sample (scattered to original order), depth, weight sum
-      for (int r = rw; r < gg.nr; r += kRayWarps) {
+      // R = 4: two warps per ray share the rank count (pair_rank_scatter); warp rw < 4 then runs the march alone
+      const bool pairs = R == 4 && nf > 0 && (Dc & 31) == 0 && (Df & 7) == 0;
+      for (int r = pairs ? (rw & 3) : rw; r < gg.nr; r += kRayWarps) {
         float wsum, dnum;
+        bool pre = false;
+        if (pairs) {
+          pre = pair_rank_scatter<ER>(cx.dep + r * S, cx.sig + r * S, wa + r * S, wb + r * 2 * S, S, Dc, lane, rw >> 2, 7 + r);
+          if (rw >= 4) break;
+        }
         warp_sort_and_weights<E, true, ER>(cx.dep + r * S, cx.sig + r * S, wa + r * S, nullptr, S, lane, wsum, dnum, smn, smx,
-                                       wb + r * 2 * S);          // wb and wc are contiguous: 2*S floats per ray
+                                       wb + r * 2 * S, pre);     // wb and wc are contiguous: 2*S floats per ray
         if (lane == 0) {
           const long long g = gg.ray0 + (long long)r * gg.rstride;
           rayw[r] = wsum;
@@ -521,9 +528,10 @@ typedef void (*Kernel)(const RenderArgs);
 template <int MODE>
 static Kernel pick_kernel(int S, bool prof) {
   if (prof && S > 64 && S <= 96) return render_ws_kernel<MODE, 4, 3, true>;      // TPR_PHASE_TIMING=1 (profiles/phase_timing.py)
-  if (prof && S > 128) return render_ws_kernel<MODE, 8, 8, true>;
+  if (prof && S > 128 && S <= 192) return render_ws_kernel<MODE, 8, 6, true>;                 // (192 samples: TPR_PT_DEPTH=96)
   return S <= 64 ? render_ws_kernel<MODE, 2, 2, false> : S <= 96 ? render_ws_kernel<MODE, 4, 3, false>
-       : S <= 128 ? render_ws_kernel<MODE, 4, 4, false> : render_ws_kernel<MODE, 8, 8, false>;
+       : S <= 128 ? render_ws_kernel<MODE, 4, 4, false> : S <= 192 ? render_ws_kernel<MODE, 8, 6, false>
+       : render_ws_kernel<MODE, 8, 8, false>;
 }
 
 }  // namespace ws

@@ -60,6 +60,11 @@ CASES = {
     'disparity':   (14, 1, 8, 32, 32, 32, 0.0, {'disparity_space_sampling': True}),
     'coarse_only': (15, 1, 8, 32, 32, 0, 0.5, {}),
     'wide_box':    (16, 1, 10, 40, 16, 16, 0.5, {'box_warp': 0.6}),   # many out-of-plane taps
+    # R = 4 ray groups of the warp-specialised kernel (more than 64 samples per pass): the gen_videos.py:127-128 depths,
+    # and two shapes that exercise the pair rank count with 2 / 3 purely-coarse rows
+    'inference_96': (17, 1, 12, 48, 96, 96, 0.5, {}),
+    'mid_64':       (18, 1, 10, 40, 64, 64, 0.5, {}),
+    'uneven_96_40': (19, 1, 8, 32, 96, 40, 0.5, {}),
 }
 
 
@@ -116,7 +121,7 @@ def run_case(name):
 
 
 def main():
-    for name in CASES:
+    for name in (sys.argv[1:] or CASES):      # optional: only the named cases
         sc, opts, out = run_case(name)
         # cross-check the numpy oracle against the reference before committing
         (rgb, depth, wsum), st = O.render(sc['planes'], sc['dec'], sc['origins'], sc['dirs'], opts,

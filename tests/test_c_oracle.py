@@ -21,7 +21,7 @@ def test_c_oracle_matches_reference_fixture_and_numpy_oracle(name):
         assert np.abs(got - b).max() < 1e-5
     if opts['depth_resolution_importance'] > 0:
         assert np.abs(st['depths_fine'] - gold['depths_fine']).max() < 1e-5
-        assert (st['inds'] != gold['inds']).mean() < 1e-4
+        assert int((st['inds'] != gold['inds']).sum()) <= max(1, 1e-4 * gold['inds'].size)
 
 
 def test_c_oracle_uses_threads():

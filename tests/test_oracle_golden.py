@@ -29,7 +29,8 @@ def test_render_matches_reference(name):
         assert np.abs(st['depths_fine'] - gold['depths_fine']).max() < TOL
         # searchsorted indices from the full pipeline (weights differ in the last ulp, so allow the
         # rare flip; the stage-wise test below is exact)
-        assert (st['inds'] != gold['inds']).mean() < 1e-4
+        flips = int((st['inds'] != gold['inds']).sum())
+        assert flips <= max(1, 1e-4 * gold['inds'].size), flips       # (one flip in a 6400-draw case is 1.6e-4)
 
 
 @pytest.mark.parametrize('name', [n for n in CASES if CASES[n][5] > 0])
