@@ -9,7 +9,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, 'csrc')
 LIB_DIR = os.path.join(PKG, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libtriplane_b200.so')
-SOURCES = ['triplane_b200.cu', 'tpr_tc_debug.cu', 'tpr_render_tc.cu', 'tpr_render_ws.cu', 'tpr_run_model_ws.cu', 'tpr_microbench.cu']
+SOURCES = ['triplane_b200.cu', 'tpr_tc_debug.cu', 'tpr_render_tc.cu', 'tpr_render_ws.cu', 'tpr_run_model_ws.cu', 'tpr_microbench.cu', 'tpr_backward.cu']
 HEADERS = [os.path.join(CSRC, 'tpr_device.cuh'), os.path.join(CSRC, 'tpr_render.cuh'), os.path.join(CSRC, 'tpr_tc.cuh'), os.path.join(CSRC, 'tpr_ws.cuh'), os.path.join(ROOT, 'include', 'triplane_b200.h')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',

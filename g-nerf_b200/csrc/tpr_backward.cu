@@ -1,0 +1,550 @@
+// Backward pass of ImportanceRenderer.forward for sm_100a: gradients of the rendered
+// (rgb, depth, weight_sum) with respect to the tri-planes and the four OSGDecoder tensors -- what the reference's
+// training step back-propagates through the renderer (training/training_loop.py:335,377).
+//
+// What is differentiated (citations relative to /root/reference/g_nerf/, VR/ = training/volumetric_rendering/):
+//   * the importance depths are constants: the reference produces them under torch.no_grad() and detaches the coarse
+//     weights (VR/renderer.py:198,210), and the coarse depths depend on the jitter only (VR/renderer.py:169-192);
+//     ray origins / directions come from the camera and carry no gradient.  So the graph is
+//       planes, decoder -> (colour, sigma) of the S = Dc + Df samples of a ray (VR/renderer.py:142-148)
+//                       -> sort by depth (VR/renderer.py:157-167) -> final march (VR/ray_marcher.py:25-57).
+//   * the first march (coarse weights) only feeds the resampling, i.e. nothing.
+//
+// Three kernels, none of which stores per-sample activations of the decoder:
+//   points_kernel           sample positions origin + depth * direction of all S samples of every ray
+//   (tpr_run_model)         colours and densities of those points: the forward's tcgen05 point-query kernel
+//   march_backward_kernel   one warp per ray: sort, march, and the march's backward -> per sample d(loss)/d(sigma) and
+//                           the composite weight omega of its colour (d(loss)/d(colour_c) = 2 * g_rgb_c * omega)
+//   decode_backward_kernel  per tile of 128 samples: re-gather the features, layer 1 forward, the decoder's backward
+//                           (three small GEMMs per sample tile + two outer-product GEMMs for the weight gradients, all
+//                           on mma.sync m16n8k8 TF32 with the 3xTF32 split, fp32 accumulation), then the bilinear
+//                           scatter of d(loss)/d(features) into the packed plane gradient with 128-bit reductions
+//                           (red.global.add.v4.f32: one texel = one 128-byte line = 8 lanes).
+// The decoder GEMMs here use warp-level mma.sync, not tcgen05: the tile shapes (K = samples for the weight gradients)
+// need transposed operands that the forward's UMMA staging does not produce; moving them to tcgen05 is the next step
+// for this kernel.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "triplane_b200.h"
+#include "tpr_device.cuh"
+
+namespace tpr {
+namespace bwd {
+
+// ---------------------------------------------------------------------------------------------------------
+// sample positions (VR/renderer.py:105,123), in the forward's order: ray-major, coarse samples then importance samples
+// ---------------------------------------------------------------------------------------------------------
+__global__ void points_kernel(const float* __restrict__ origins, const float* __restrict__ dirs,
+                              const float* __restrict__ dc, const float* __restrict__ df, int Dc, int Df,
+                              long long n_rays_total, float* __restrict__ pts) {
+  const int S = Dc + Df;
+  const long long total = n_rays_total * S;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long g = i / S;
+    const int k = (int)(i - g * S);
+    const float d = k < Dc ? __ldg(dc + g * Dc + k) : __ldg(df + g * Df + (k - Dc));
+    pts[3 * i + 0] = __fadd_rn(__ldg(origins + 3 * g + 0), __fmul_rn(d, __ldg(dirs + 3 * g + 0)));
+    pts[3 * i + 1] = __fadd_rn(__ldg(origins + 3 * g + 1), __fmul_rn(d, __ldg(dirs + 3 * g + 1)));
+    pts[3 * i + 2] = __fadd_rn(__ldg(origins + 3 * g + 2), __fmul_rn(d, __ldg(dirs + 3 * g + 2)));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// march backward: one warp per ray
+// ---------------------------------------------------------------------------------------------------------
+struct MarchArgs {
+  const float* dc; const float* df; int Dc, Df;
+  const float* sigma;            // [rays, S]
+  const float* colours;          // [rays, S, 32]
+  const float* g_rgb;            // [rays, 32]
+  const float* g_depth;          // [rays]
+  const float* g_wsum;           // [rays]
+  const float* range;            // [2]: the forward's (min, max) of all depths (VR/ray_marcher.py:50)
+  int white_back;
+  long long n_rays;
+  float* gsig;                   // [rays, S]   d(loss)/d(sigma), sample order
+  float* omega;                  // [rays, S]   composite weight of the sample's colour
+};
+
+__device__ __forceinline__ float warp_excl_suffix_sum(float v, int lane) {
+  float incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_down_sync(kFull, incl, o);
+    if (lane + o < 32) incl += t;
+  }
+  return incl - v;
+}
+
+template <int E>
+__global__ void __launch_bounds__(128) march_backward_kernel(const MarchArgs a) {
+  extern __shared__ float sm[];
+  const int S = a.Dc + a.Df, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float* z = sm + wid * 7 * S; float* sg = z + S; float* q = sg + S;
+  float* zs = q + S; float* ss = zs + S; float* qs = ss + S; int* idx = reinterpret_cast<int*>(qs + S);
+  const float lo = __ldg(a.range), hi = __ldg(a.range + 1);
+  for (long long g = blockIdx.x * 4ll + wid; g < a.n_rays; g += gridDim.x * 4ll) {
+    // upstream gradient of rgb (x2: VR/ray_marcher.py:55)
+    float A2[32];
+    float sumA2 = 0.0f;
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(a.g_rgb + g * 32) + c4);
+      A2[4 * c4] = 2.0f * v.x; A2[4 * c4 + 1] = 2.0f * v.y; A2[4 * c4 + 2] = 2.0f * v.z; A2[4 * c4 + 3] = 2.0f * v.w;
+      sumA2 += (A2[4 * c4] + A2[4 * c4 + 1]) + (A2[4 * c4 + 2] + A2[4 * c4 + 3]);
+    }
+    const float B = __ldg(a.g_depth + g), C = __ldg(a.g_wsum + g);
+    for (int p = lane; p < S; p += 32) {
+      z[p] = p < a.Dc ? __ldg(a.dc + g * a.Dc + p) : __ldg(a.df + g * a.Df + (p - a.Dc));
+      sg[p] = __ldg(a.sigma + g * S + p);
+      const float4* row = reinterpret_cast<const float4*>(a.colours + (g * S + p) * 32);
+      float acc = 0.0f;
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 v = __ldg(row + c4);
+        acc = fmaf(A2[4 * c4], v.x, acc); acc = fmaf(A2[4 * c4 + 1], v.y, acc);
+        acc = fmaf(A2[4 * c4 + 2], v.z, acc); acc = fmaf(A2[4 * c4 + 3], v.w, acc);
+      }
+      q[p] = acc;                                   // sum_c d(loss)/d(rgb_raw_c) * colour_c
+    }
+    __syncwarp();
+    // sort by depth (VR/renderer.py:157-167): rank = number of smaller depths, ties by sample index (a stable sort)
+    for (int p = lane; p < S; p += 32) {
+      const float zp = z[p];
+      int cnt = 0;
+      for (int j = 0; j < S; ++j) { const float v = z[j]; cnt += (int)((v < zp) || (v == zp && j < p)); }
+      zs[cnt] = zp; ss[cnt] = sg[p]; qs[cnt] = q[p]; idx[cnt] = p;
+    }
+    __syncwarp();
+    // blocked: position p = lane * E + e
+    float key[E + 1], sgm[E + 1], qq[E + 1];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int p = lane * E + e;
+      key[e] = p < S ? zs[p] : 0.0f; sgm[e] = p < S ? ss[p] : 0.0f; qq[e] = p < S ? qs[p] : 0.0f;
+    }
+    key[E] = __shfl_down_sync(kFull, key[0], 1); sgm[E] = __shfl_down_sync(kFull, sgm[0], 1); qq[E] = __shfl_down_sync(kFull, qq[0], 1);
+    // forward march (VR/ray_marcher.py:26-46)
+    float al[E], ex[E], om1[E], dm[E], sx[E], T[E], w[E];
+    float prod = 1.0f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int p = lane * E + e;
+      const bool valid = p + 1 < S;
+      const float delta = key[e + 1] - key[e];
+      const float x = (sgm[e] + sgm[e + 1]) * 0.5f - 1.0f;
+      const float t = __expf(x);
+      const float dens = x > 20.0f ? x : __logf(1.0f + t);
+      sx[e] = x > 20.0f ? 1.0f : __fdividef(t, 1.0f + t);      // softplus'(x)
+      ex[e] = valid ? __expf(-(dens * delta)) : 1.0f;
+      al[e] = valid ? 1.0f - ex[e] : 0.0f;
+      om1[e] = 1.0f - al[e] + 1e-10f;
+      dm[e] = (key[e] + key[e + 1]) * 0.5f;
+      if (valid) prod *= om1[e];
+    }
+    float Tr = warp_excl_prod(prod, lane);
+    float wsum = 0.0f, dnum = 0.0f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      T[e] = Tr; w[e] = al[e] * Tr;
+      if (lane * E + e + 1 < S) Tr *= om1[e];
+      wsum += w[e]; dnum = fmaf(w[e], dm[e], dnum);
+    }
+    wsum = warp_sum(wsum); dnum = warp_sum(dnum);
+    const float depth_raw = dnum / wsum;
+    // nan_to_num + clamp (VR/ray_marcher.py:49-50): the gradient passes only where the depth is inside the range
+    const bool pass = depth_raw >= lo && depth_raw <= hi;
+    const float bscale = pass ? B / wsum : 0.0f;
+    const float wb = a.white_back ? sumA2 : 0.0f;               // rgb += 1 - sum(w) (VR/ray_marcher.py:52-53)
+    float gw[E], u[E], lane_tot = 0.0f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const bool valid = lane * E + e + 1 < S;
+      gw[e] = valid ? 0.5f * (qq[e] + qq[e + 1]) - wb + C + bscale * (dm[e] - depth_raw) : 0.0f;
+      u[e] = gw[e] * w[e];
+      lane_tot += u[e];
+    }
+    float run = warp_excl_suffix_sum(lane_tot, lane);           // sum of u over all later lanes
+    float gx[E];
+#pragma unroll
+    for (int e = E - 1; e >= 0; --e) {
+      const bool valid = lane * E + e + 1 < S;
+      // w_i = alpha_i T_i, T_j = prod_{k<j} (1 - alpha_k + 1e-10):  d/d(alpha_i) = gw_i T_i - sum_{j>i} gw_j w_j / (1 - alpha_i + 1e-10)
+      const float galpha = gw[e] * T[e] - run / om1[e];
+      run += u[e];
+      const float delta = key[e + 1] - key[e];
+      gx[e] = valid ? galpha * delta * ex[e] * sx[e] : 0.0f;   // alpha = 1 - exp(-softplus(x) delta)
+    }
+    float gx_prev = __shfl_up_sync(kFull, gx[E - 1], 1), w_prev = __shfl_up_sync(kFull, w[E - 1], 1);
+    if (lane == 0) { gx_prev = 0.0f; w_prev = 0.0f; }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int p = lane * E + e;
+      if (p < S) {
+        const float gxp = e == 0 ? gx_prev : gx[e > 0 ? e - 1 : 0], wp = e == 0 ? w_prev : w[e > 0 ? e - 1 : 0];
+        a.gsig[g * S + idx[p]] = 0.5f * (gxp + gx[e]);           // sigma_mid = (sigma_i + sigma_{i+1}) / 2
+        a.omega[g * S + idx[p]] = 0.5f * (wp + w[e]);            // colour_mid likewise (VR/ray_marcher.py:27)
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// decoder backward + plane-gradient scatter
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kT = 128;                 // samples per tile
+constexpr int kBT = 256;                // threads per CTA (8 warps x 16 samples)
+constexpr int FS = 36, HS = 72, YS = 44, W1S = 72, W2S = kOutPad;    // shared-memory row strides (floats)
+static_assert(W2S == 36, "W2t B-fragment loads assume a row stride of 36 floats");
+
+struct __align__(16) Smem {
+  float w1t[kC * W1S];                  // [k][j]   (W1 * gain / 3)
+  float w2t[kHid * W2S + 40];           // [j][o]   (W2 * gain), then finite padding (b2) for the K = 36..39 tail reads
+  float b1[kHid];
+  float F[kT * FS];                     // summed plane features
+  float H[kT * HS];                     // softplus(layer 1)
+  float GA[kT * HS];                    // d/d(layer-1 pre-activation)
+  float GY[kT * YS];                    // d/d(decoder outputs): [0] sigma, [1..32] colour logits, [33..43] = 0
+  float GF[kT * FS];                    // d/d(features)
+  uint32_t tap_off[kT * 12];            // float offset of each tap's texel inside its image
+  float tap_w[kT * 12];
+  int simg[kT];
+};
+
+struct DecArgs {
+  const float* planes; int H, W;        // packed [N,3,H,W,32]
+  const float* dec;                     // packed decoder
+  const float* pts;                     // [T,3]
+  const float* colours;                 // [T,32]
+  const float* gsig; const float* omega;// [T]
+  const float* g_rgb;                   // [rays,32]
+  long long total, pts_per_img; int S;
+  float box_scale;
+  float* g_planes;                      // packed, zero-initialised
+  float* g_dec;                         // [kDecFloats], zero-initialised
+};
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;          // the tensor core reads the top 19 bits of an fp32 register
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// 3xTF32: x = hi + lo; a.b ~ a_lo.b_hi + a_hi.b_lo + a_hi.b_hi (small terms first)
+__device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const uint32_t (&bh)[2],
+                                     const uint32_t (&bl)[2]) {
+  mma_tf32(d, al, bh);
+  mma_tf32(d, ah, bl);
+  mma_tf32(d, ah, bh);
+}
+
+__global__ void __launch_bounds__(kBT, 1) decode_backward_kernel(const DecArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw + ((16u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 15u)) & 15u));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;           // mma fragment coordinates
+  const int grp = lane >> 3, sub = lane & 7;       // gather: 8 lanes per sample
+  // ---- stage the decoder
+  for (int i = tid; i < kC * kHid; i += kBT) { const int k = i >> 6, j = i & 63; s.w1t[k * W1S + j] = __ldg(a.dec + kW1tOff + i); }
+  for (int i = tid; i < kHid * W2S + 40; i += kBT)
+    s.w2t[i] = i < kHid * W2S ? __ldg(a.dec + kW2tOff + i) : (i - kHid * W2S < kOutPad ? __ldg(a.dec + kB2Off + i - kHid * W2S) : 0.0f);
+  if (tid < kHid) s.b1[tid] = __ldg(a.dec + kB1Off + tid);
+  __syncthreads();
+
+  // weight-gradient accumulators of this warp: output tiles q = warp + 8 i (16 tiles of gW1t [32 x 64], 20 of gW2t [64 x 40])
+  float pacc[5][4];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) { pacc[i][0] = pacc[i][1] = pacc[i][2] = pacc[i][3] = 0.0f; }
+  float bacc = 0.0f;                               // tid < 64: gb1[tid]; 64 <= tid < 104: gb2[tid - 64]
+  const size_t img_stride = (size_t)3 * a.H * a.W * kC;
+  const long long n_tiles = (a.total + kT - 1) / kT;
+  const int row0 = warp * 16;
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long gs0 = tile * kT;
+    const long long n0 = gs0 / a.pts_per_img, rem0 = gs0 - n0 * a.pts_per_img;
+    const long long ray0 = gs0 / a.S;
+    const int rr0 = (int)(gs0 - ray0 * a.S);
+    // ---- taps of this warp's 16 samples x 3 planes (VR/renderer.py:39-65)
+    for (int i = lane; i < 48; i += 32) {
+      const int sl = i / 3, p = i - sl * 3, sr = row0 + sl;
+      const long long gs = gs0 + sr;
+      Taps tp;
+      int n = 0;
+      if (gs < a.total) {
+        const float px = __fmul_rn(__ldg(a.pts + 3 * gs + 0), a.box_scale), py = __fmul_rn(__ldg(a.pts + 3 * gs + 1), a.box_scale),
+                    pz = __fmul_rn(__ldg(a.pts + 3 * gs + 2), a.box_scale);
+        plane_taps(p == 2 ? pz : px, p == 0 ? py : (p == 1 ? pz : px), a.H, a.W, tp);      // (x,y) (x,z) (z,x)
+        long long r = rem0 + sr; n = (int)n0;
+        while (r >= a.pts_per_img) { r -= a.pts_per_img; ++n; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { tp.off[k] = 0; tp.w[k] = 0.0f; }
+      }
+      const int po = p * a.H * a.W * kC;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { s.tap_off[sr * 12 + p * 4 + k] = (uint32_t)(tp.off[k] + po); s.tap_w[sr * 12 + p * 4 + k] = tp.w[k]; }
+      if (p == 0) s.simg[sr] = n;
+    }
+    __syncwarp();
+    // ---- gather: F = sum over planes and taps (the plane mean's 1/3 is folded into W1t)
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+      const int sr = row0 + it * 4 + grp;
+      const float4* img = reinterpret_cast<const float4*>(a.planes + (size_t)s.simg[sr] * img_stride) + sub;
+      float4 v[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) v[k] = __ldg(img + (s.tap_off[sr * 12 + k] >> 2));
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const float w = s.tap_w[sr * 12 + k];
+        acc.x = fmaf(w, v[k].x, acc.x); acc.y = fmaf(w, v[k].y, acc.y); acc.z = fmaf(w, v[k].z, acc.z); acc.w = fmaf(w, v[k].w, acc.w);
+      }
+      *reinterpret_cast<float4*>(s.F + sr * FS + 4 * sub) = acc;
+      // ---- upstream gradient of the decoder outputs of this sample
+      const long long gs = gs0 + sr;
+      float gy[4] = {0.f, 0.f, 0.f, 0.f};
+      float gs_sig = 0.0f;
+      if (gs < a.total) {
+        const long long ray = ray0 + (unsigned)(rr0 + sr) / (unsigned)a.S;
+        const float4 col = __ldg(reinterpret_cast<const float4*>(a.colours + gs * 32) + sub);
+        const float4 A = __ldg(reinterpret_cast<const float4*>(a.g_rgb + ray * 32) + sub);
+        const float om = __ldg(a.omega + gs) * (2.0f * 1.002f);       // rgb*2-1 (VR/ray_marcher.py:55), sigmoid*1.002 (training/triplane.py:134)
+        const float cc[4] = {col.x, col.y, col.z, col.w}, aa[4] = {A.x, A.y, A.z, A.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float sv = (cc[k] + 0.001f) * (1.0f / 1.002f);           // sigmoid(logit)
+          gy[k] = aa[k] * om * sv * (1.0f - sv);
+        }
+        gs_sig = __ldg(a.gsig + gs);
+      }
+      float* gyr = s.GY + sr * YS;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) gyr[1 + 4 * sub + k] = gy[k];
+      if (sub == 0) gyr[0] = gs_sig;
+      for (int c = 33 + sub; c < YS; c += 8) gyr[c] = 0.0f;
+    }
+    __syncwarp();
+
+    // ---- layer 1 forward for rows row0 + {g, g+8}: a = F . W1t + b1  (training/triplane.py:126-131)
+    float sgd[8][4];                               // softplus'(a) = sigmoid(a), later d/d(a)
+    {
+      uint32_t ah[4][4], al[4][4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const float* f0 = s.F + (row0 + g) * FS + 8 * ks + t;
+        split_tf32(f0[0], ah[ks][0], al[ks][0]); split_tf32(f0[8 * FS], ah[ks][1], al[ks][1]);
+        split_tf32(f0[4], ah[ks][2], al[ks][2]); split_tf32(f0[8 * FS + 4], ah[ks][3], al[ks][3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        float acc[4];
+        acc[0] = acc[2] = s.b1[8 * nt + 2 * t]; acc[1] = acc[3] = s.b1[8 * nt + 2 * t + 1];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t bh[2], bl[2];
+          split_tf32(s.w1t[(8 * ks + t) * W1S + 8 * nt + g], bh[0], bl[0]);
+          split_tf32(s.w1t[(8 * ks + t + 4) * W1S + 8 * nt + g], bh[1], bl[1]);
+          mma3(acc, ah[ks], al[ks], bh, bl);
+        }
+        float h[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float e = __expf(acc[i]), d = 1.0f + e;
+          h[i] = acc[i] > 20.0f ? acc[i] : __logf(d);                 // Softplus(beta=1, threshold=20)
+          sgd[nt][i] = acc[i] > 20.0f ? 1.0f : __fdividef(e, d);
+        }
+        *reinterpret_cast<float2*>(s.H + (row0 + g) * HS + 8 * nt + 2 * t) = make_float2(h[0], h[1]);
+        *reinterpret_cast<float2*>(s.H + (row0 + g + 8) * HS + 8 * nt + 2 * t) = make_float2(h[2], h[3]);
+      }
+    }
+    // ---- d/d(hidden) = GY . W2 (K = 40 outputs, 33 real), times softplus' -> d/d(a)
+    {
+      uint32_t ah[5][4], al[5][4];
+#pragma unroll
+      for (int ks = 0; ks < 5; ++ks) {
+        const float* y0 = s.GY + (row0 + g) * YS + 8 * ks + t;
+        split_tf32(y0[0], ah[ks][0], al[ks][0]); split_tf32(y0[8 * YS], ah[ks][1], al[ks][1]);
+        split_tf32(y0[4], ah[ks][2], al[ks][2]); split_tf32(y0[8 * YS + 4], ah[ks][3], al[ks][3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 5; ++ks) {
+          uint32_t bh[2], bl[2];
+          const float* wr = s.w2t + (8 * nt + g) * W2S + 8 * ks + t;
+          split_tf32(wr[0], bh[0], bl[0]); split_tf32(wr[4], bh[1], bl[1]);
+          mma3(acc, ah[ks], al[ks], bh, bl);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sgd[nt][i] *= acc[i];
+        *reinterpret_cast<float2*>(s.GA + (row0 + g) * HS + 8 * nt + 2 * t) = make_float2(sgd[nt][0], sgd[nt][1]);
+        *reinterpret_cast<float2*>(s.GA + (row0 + g + 8) * HS + 8 * nt + 2 * t) = make_float2(sgd[nt][2], sgd[nt][3]);
+      }
+    }
+    // ---- d/d(features) = GA . W1t^T.  GA is still in registers in accumulator layout (row g / g+8, columns 2t, 2t+1 of
+    //      each 8-column block); it is fed back as the A operand with the K index permuted (k' = t <-> column 2t,
+    //      k' = t+4 <-> column 2t+1) and the B operand is read with the same permutation, so no shuffle is needed.
+    {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint32_t ah[4], al[4], bh[2], bl[2];
+          split_tf32(sgd[q][0], ah[0], al[0]); split_tf32(sgd[q][2], ah[1], al[1]);
+          split_tf32(sgd[q][1], ah[2], al[2]); split_tf32(sgd[q][3], ah[3], al[3]);
+          const float2 wv = *reinterpret_cast<const float2*>(s.w1t + (8 * nt + g) * W1S + 8 * q + 2 * t);
+          split_tf32(wv.x, bh[0], bl[0]); split_tf32(wv.y, bh[1], bl[1]);
+          mma3(acc, ah, al, bh, bl);
+        }
+        *reinterpret_cast<float2*>(s.GF + (row0 + g) * FS + 8 * nt + 2 * t) = make_float2(acc[0], acc[1]);
+        *reinterpret_cast<float2*>(s.GF + (row0 + g + 8) * FS + 8 * nt + 2 * t) = make_float2(acc[2], acc[3]);
+      }
+    }
+    __syncthreads();                                // F, H, GA, GY, GF of all 128 samples are in shared memory
+
+    // ---- scatter d/d(features) to the twelve texels of each sample: the transpose of the bilinear gather
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+      const int sr = row0 + it * 4 + grp;
+      const float4 gf = *reinterpret_cast<const float4*>(s.GF + sr * FS + 4 * sub);
+      float4* img = reinterpret_cast<float4*>(a.g_planes + (size_t)s.simg[sr] * img_stride) + sub;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const float w = s.tap_w[sr * 12 + k];
+        if (w != 0.0f) atomicAdd(img + (s.tap_off[sr * 12 + k] >> 2), make_float4(w * gf.x, w * gf.y, w * gf.z, w * gf.w));
+      }
+    }
+    // ---- weight gradients: sums over the tile's 128 samples of F (x) GA and H (x) GY
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int q = warp + 8 * i;
+      if (q < 36) {
+        const bool first = q < 16;
+        const int q2 = first ? q : q - 16;
+        const int mt = first ? q2 >> 3 : q2 / 5, nt = first ? q2 & 7 : q2 - (q2 / 5) * 5;
+        const float* As = first ? s.F : s.H; const int as = first ? FS : HS;
+        const float* Bs = first ? s.GA : s.GY; const int bs = first ? HS : YS;
+        const float* ap = As + t * as + 16 * mt + g;
+        const float* bp = Bs + t * bs + 8 * nt + g;
+#pragma unroll 4
+        for (int ks = 0; ks < 16; ++ks) {
+          uint32_t ah[4], al[4], bh[2], bl[2];
+          split_tf32(ap[0], ah[0], al[0]); split_tf32(ap[8], ah[1], al[1]);
+          split_tf32(ap[4 * as], ah[2], al[2]); split_tf32(ap[4 * as + 8], ah[3], al[3]);
+          split_tf32(bp[0], bh[0], bl[0]); split_tf32(bp[4 * bs], bh[1], bl[1]);
+          mma3(pacc[i], ah, al, bh, bl);
+          ap += 8 * as; bp += 8 * bs;
+        }
+      }
+    }
+    if (tid < kHid) {
+      float acc = 0.0f;
+#pragma unroll 8
+      for (int r = 0; r < kT; ++r) acc += s.GA[r * HS + tid];
+      bacc += acc;
+    } else if (tid < kHid + 40) {
+      float acc = 0.0f;
+#pragma unroll 8
+      for (int r = 0; r < kT; ++r) acc += s.GY[r * YS + tid - kHid];
+      bacc += acc;
+    }
+    __syncthreads();                                // the tile buffers are rewritten by the next tile
+  }
+
+  // ---- flush this CTA's partial weight gradients
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int q = warp + 8 * i;
+    if (q < 36) {
+      const bool first = q < 16;
+      const int q2 = first ? q : q - 16;
+      const int mt = first ? q2 >> 3 : q2 / 5, nt = first ? q2 & 7 : q2 - (q2 / 5) * 5;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int m = 16 * mt + g + (r >> 1) * 8, n = 8 * nt + 2 * t + (r & 1);
+        if (first) atomicAdd(a.g_dec + kW1tOff + m * kHid + n, pacc[i][r]);              // gW1t[k = m][j = n]
+        else if (n < kOutPad) atomicAdd(a.g_dec + kW2tOff + m * kOutPad + n, pacc[i][r]); // gW2t[j = m][o = n]
+      }
+    }
+  }
+  if (tid < kHid) atomicAdd(a.g_dec + kB1Off + tid, bacc);
+  else if (tid < kHid + kOutPad) atomicAdd(a.g_dec + kB2Off + tid - kHid, bacc);
+}
+
+// packed decoder gradient -> gradients of the module's raw tensors (training/networks_stylegan2.py:118-127: the runtime gains)
+__global__ void unpack_decoder_grad_kernel(const float* __restrict__ gd, float g_w1, float g_b1, float g_w2, float g_b2,
+                                           float* __restrict__ w1, float* __restrict__ b1, float* __restrict__ w2,
+                                           float* __restrict__ b2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < kHid * kC) { const int j = i / kC, k = i - j * kC; w1[i] = gd[kW1tOff + k * kHid + j] * (g_w1 * (1.0f / 3.0f)); }
+  if (i < kHid) b1[i] = gd[kB1Off + i] * g_b1;
+  if (i < TPR_OUT * kHid) { const int o = i / kHid, j = i - o * kHid; w2[i] = gd[kW2tOff + j * kOutPad + o] * g_w2; }
+  if (i < TPR_OUT) b2[i] = gd[kB2Off + i] * g_b2;
+}
+
+}  // namespace bwd
+
+// ---------------------------------------------------------------------------------------------------------
+// launchers (called from the C ABI in triplane_b200.cu); each returns a cudaError_t
+// ---------------------------------------------------------------------------------------------------------
+int launch_bwd_points(const float* origins, const float* dirs, const float* dc, const float* df, int Dc, int Df,
+                      long long n_rays_total, float* pts, int sms, cudaStream_t st) {
+  const long long total = n_rays_total * (Dc + Df);
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)sms * 32) blocks = (long long)sms * 32;
+  bwd::points_kernel<<<(unsigned)blocks, 256, 0, st>>>(origins, dirs, dc, df, Dc, Df, n_rays_total, pts);
+  return (int)cudaGetLastError();
+}
+
+int launch_bwd_march(const float* dc, const float* df, int Dc, int Df, const float* sigma, const float* colours,
+                     const float* g_rgb, const float* g_depth, const float* g_wsum, const float* range, int white_back,
+                     long long n_rays_total, float* gsig, float* omega, int sms, cudaStream_t st) {
+  bwd::MarchArgs a;
+  a.dc = dc; a.df = df; a.Dc = Dc; a.Df = Df; a.sigma = sigma; a.colours = colours; a.g_rgb = g_rgb; a.g_depth = g_depth;
+  a.g_wsum = g_wsum; a.range = range; a.white_back = white_back; a.n_rays = n_rays_total; a.gsig = gsig; a.omega = omega;
+  const int S = Dc + Df;
+  const size_t smem = (size_t)4 * 7 * S * sizeof(float);
+  long long blocks = (n_rays_total + 3) / 4;
+  if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+  const int E = (S + 31) / 32;
+  if (E <= 1) bwd::march_backward_kernel<1><<<(unsigned)blocks, 128, smem, st>>>(a);
+  else if (E <= 2) bwd::march_backward_kernel<2><<<(unsigned)blocks, 128, smem, st>>>(a);
+  else if (E <= 3) bwd::march_backward_kernel<3><<<(unsigned)blocks, 128, smem, st>>>(a);
+  else if (E <= 4) bwd::march_backward_kernel<4><<<(unsigned)blocks, 128, smem, st>>>(a);
+  else if (E <= 6) bwd::march_backward_kernel<6><<<(unsigned)blocks, 128, smem, st>>>(a);
+  else bwd::march_backward_kernel<8><<<(unsigned)blocks, 128, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+int launch_bwd_decode(const float* planes, int H, int W, const float* dec, const float* pts, const float* colours,
+                      const float* gsig, const float* omega, const float* g_rgb, long long total, long long pts_per_img, int S,
+                      float box_scale, float* g_planes, float* g_dec, int sms, cudaStream_t st) {
+  bwd::DecArgs a;
+  a.planes = planes; a.H = H; a.W = W; a.dec = dec; a.pts = pts; a.colours = colours; a.gsig = gsig; a.omega = omega;
+  a.g_rgb = g_rgb; a.total = total; a.pts_per_img = pts_per_img; a.S = S; a.box_scale = box_scale; a.g_planes = g_planes;
+  a.g_dec = g_dec;
+  const size_t smem = sizeof(bwd::Smem) + 16;
+  cudaError_t e = cudaFuncSetAttribute(bwd::decode_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const long long n_tiles = (total + bwd::kT - 1) / bwd::kT;
+  const long long grid = n_tiles < sms ? n_tiles : sms;
+  bwd::decode_backward_kernel<<<(unsigned)grid, bwd::kBT, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+int launch_unpack_decoder_grad(const float* gd, float g_w1, float g_b1, float g_w2, float g_b2, float* w1, float* b1, float* w2,
+                               float* b2, cudaStream_t st) {
+  bwd::unpack_decoder_grad_kernel<<<(TPR_OUT * kHid + 255) / 256, 256, 0, st>>>(gd, g_w1, g_b1, g_w2, g_b2, w1, b1, w2, b2);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace tpr

@@ -27,6 +27,18 @@ int launch_render_ws(RenderArgs a, int bf16, int sms, int smem_optin, long long 
 int launch_run_model_ws(const float* planes, long long n_img, int H, int W, const float* dec, const float* xyz, long long n_pts,
                         float box_scale, float* rgb, float* sigma, int bf16, int sms, int smem_optin, cudaStream_t st);
 
+// tpr_backward.cu
+int launch_bwd_points(const float* origins, const float* dirs, const float* dc, const float* df, int Dc, int Df,
+                      long long n_rays_total, float* pts, int sms, cudaStream_t st);
+int launch_bwd_march(const float* dc, const float* df, int Dc, int Df, const float* sigma, const float* colours,
+                     const float* g_rgb, const float* g_depth, const float* g_wsum, const float* range, int white_back,
+                     long long n_rays_total, float* gsig, float* omega, int sms, cudaStream_t st);
+int launch_bwd_decode(const float* planes, int H, int W, const float* dec, const float* pts, const float* colours,
+                      const float* gsig, const float* omega, const float* g_rgb, long long total, long long pts_per_img, int S,
+                      float box_scale, float* g_planes, float* g_dec, int sms, cudaStream_t st);
+int launch_unpack_decoder_grad(const float* gd, float g_w1, float g_b1, float g_w2, float g_b2, float* w1, float* b1, float* w2,
+                               float* b2, cudaStream_t st);
+
 // =======================================================================================
 // layout preparation
 // =======================================================================================
@@ -1119,6 +1131,88 @@ int tpr_sample_pdf(const float* bins, int32_t bins_stride, const float* weights,
                    int32_t n_weights, int32_t n_importance, float* samples, int32_t* inds, void* stream) {
   if (bins_stride < n_weights + 1) return fail(TPR_E_SHAPE, "tpr_sample_pdf: bins_stride < n_weights + 1");
   return launch_resample(1, bins, bins_stride, weights, u, n_rays, n_weights, n_importance, samples, inds, stream);
+}
+
+// ---------------------------------------------------------------------------------------
+// backward of tpr_render (kernels: tpr_backward.cu)
+// ---------------------------------------------------------------------------------------
+static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+size_t tpr_render_backward_scratch_bytes(int64_t n_img, int64_t n_rays, int32_t n_samples) {
+  if (n_img <= 0 || n_rays <= 0 || n_samples <= 0) return 0;
+  const size_t T = (size_t)n_img * (size_t)n_rays * (size_t)n_samples;
+  // points [T,3], colours [T,32], sigma [T], g_sigma [T], omega [T]
+  return align256(T * 12) + align256(T * 128) + 3 * align256(T * 4);
+}
+
+int tpr_march_backward(const float* depths_coarse, const float* depths_fine, int32_t dc, int32_t df, const float* sigma,
+                       const float* colours, const float* g_rgb, const float* g_depth, const float* g_weight_sum,
+                       const float* depth_range, int32_t white_back, int64_t n_rays_total, float* g_sigma, float* omega,
+                       void* stream) {
+  if (!depths_coarse || !sigma || !colours || !g_rgb || !g_depth || !g_weight_sum || !depth_range || !g_sigma || !omega ||
+      (df > 0 && !depths_fine))
+    return fail(TPR_E_NULL, "tpr_march_backward: NULL pointer");
+  if (n_rays_total <= 0 || dc < 2 || df < 0 || dc + df > TPR_MAX_SAMPLES) return fail(TPR_E_SHAPE, "tpr_march_backward: bad shape");
+  DeviceInfo di = device_info();
+  if (!di.ok) return fail(TPR_E_DEVICE, "tpr_march_backward: no CUDA device");
+  const int rc = launch_bwd_march(depths_coarse, depths_fine, dc, df, sigma, colours, g_rgb, g_depth, g_weight_sum, depth_range,
+                                  white_back, n_rays_total, g_sigma, omega, di.sms, (cudaStream_t)stream);
+  if (rc != 0) return cuda_fail((cudaError_t)rc, "march_backward_kernel");
+  return 0;
+}
+
+int tpr_render_backward(const float* planes_packed, int64_t n_img, int32_t height, int32_t width, const float* decoder_packed,
+                        const float* origins, const float* dirs, int64_t n_rays, const float* depths_coarse,
+                        const float* depths_fine, const float* depth_range, const TprOptions* opt, const float* g_rgb,
+                        const float* g_depth, const float* g_weight_sum, float* g_planes_packed, float* g_decoder_packed,
+                        void* scratch, size_t scratch_bytes, void* stream) {
+  if (!planes_packed || !decoder_packed || !origins || !dirs || !depths_coarse || !depth_range || !opt || !g_rgb || !g_depth ||
+      !g_weight_sum || !g_planes_packed || !g_decoder_packed || !scratch)
+    return fail(TPR_E_NULL, "tpr_render_backward: NULL pointer");
+  const int Dc = opt->depth_resolution, Df = opt->depth_resolution_importance, S = Dc + Df;
+  if (Df > 0 && !depths_fine) return fail(TPR_E_NULL, "tpr_render_backward: depths_fine is NULL but depth_resolution_importance > 0");
+  if (n_img <= 0 || n_rays <= 0 || height <= 0 || width <= 0 || Dc < 2 || Df < 0 || S > TPR_MAX_SAMPLES)
+    return fail(TPR_E_SHAPE, "tpr_render_backward: bad shape");
+  if ((long long)3 * height * width * kC >= (1ll << 32)) return fail(TPR_E_SHAPE, "tpr_render_backward: planes too large");
+  if (opt->plane_sets != 0 && opt->plane_sets != n_img) return fail(TPR_E_OPTION, "tpr_render_backward: one plane set per image only");
+  if (opt->depth_clamp_group != 0) return fail(TPR_E_OPTION, "tpr_render_backward: depth_clamp_group is not supported");
+  if (!(opt->box_warp > 0)) return fail(TPR_E_OPTION, "tpr_render_backward: box_warp must be > 0");
+  if (scratch_bytes < tpr_render_backward_scratch_bytes(n_img, n_rays, S)) return fail(TPR_E_SCRATCH, "tpr_render_backward: scratch too small");
+  DeviceInfo di = device_info();
+  if (!di.ok) return fail(TPR_E_DEVICE, "tpr_render_backward: no CUDA device");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long rays = (long long)n_img * n_rays;
+  const size_t T = (size_t)rays * S;
+  uint8_t* p = (uint8_t*)scratch;
+  float* pts = (float*)p; p += align256(T * 12);
+  float* colours = (float*)p; p += align256(T * 128);
+  float* sigma = (float*)p; p += align256(T * 4);
+  float* gsig = (float*)p; p += align256(T * 4);
+  float* omega = (float*)p;
+  int rc = launch_bwd_points(origins, dirs, depths_coarse, depths_fine, Dc, Df, rays, pts, di.sms, st);
+  if (rc != 0) return cuda_fail((cudaError_t)rc, "points_kernel");
+  // colours and densities of every sample: the forward's point query (VR/renderer.py:142-148)
+  rc = tpr_run_model(planes_packed, n_img, height, width, decoder_packed, pts, (int64_t)n_rays * S, opt->box_warp, colours, sigma,
+                     opt->flags, stream);
+  if (rc != 0) return rc;
+  rc = launch_bwd_march(depths_coarse, depths_fine, Dc, Df, sigma, colours, g_rgb, g_depth, g_weight_sum, depth_range,
+                        opt->white_back, rays, gsig, omega, di.sms, st);
+  if (rc != 0) return cuda_fail((cudaError_t)rc, "march_backward_kernel");
+  cudaError_t e = cudaMemsetAsync(g_planes_packed, 0, (size_t)n_img * 3 * height * width * kC * sizeof(float), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(g_decoder_packed, 0, kDecFloats * sizeof(float), st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+  rc = launch_bwd_decode(planes_packed, height, width, decoder_packed, pts, colours, gsig, omega, g_rgb, (long long)T,
+                         (long long)n_rays * S, S, (float)(2.0 / opt->box_warp), g_planes_packed, g_decoder_packed, di.sms, st);
+  if (rc != 0) return cuda_fail((cudaError_t)rc, "decode_backward_kernel");
+  return 0;
+}
+
+int tpr_unpack_decoder_grad(const float* g_decoder_packed, float w1_gain, float b1_gain, float w2_gain, float b2_gain, float* g_w1,
+                            float* g_b1, float* g_w2, float* g_b2, void* stream) {
+  if (!g_decoder_packed || !g_w1 || !g_b1 || !g_w2 || !g_b2) return fail(TPR_E_NULL, "tpr_unpack_decoder_grad: NULL pointer");
+  const int rc = launch_unpack_decoder_grad(g_decoder_packed, w1_gain, b1_gain, w2_gain, b2_gain, g_w1, g_b1, g_w2, g_b2,
+                                            (cudaStream_t)stream);
+  if (rc != 0) return cuda_fail((cudaError_t)rc, "unpack_decoder_grad_kernel");
+  return 0;
 }
 
 }  // extern "C"

@@ -50,8 +50,18 @@ def _require_cuda_f32(t, name, shape_tail=None):
 def _forbid_autograd(*tensors):
     if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
         raise NotImplementedError(
-            'the B200 tri-plane renderer is forward-only: call it under torch.no_grad() or with '
-            'requires_grad_(False) inputs/decoder (backward is not implemented)')
+            'this entry point of the B200 tri-plane renderer is forward-only: call it under torch.no_grad() or with '
+            'requires_grad_(False) inputs (ImportanceRenderer.forward differentiates w.r.t. planes and the decoder only)')
+
+
+def _wants_grad(planes, decoder):
+    """Does the caller expect gradients for the planes or the decoder's parameters?"""
+    if isinstance(planes, torch.Tensor) and planes.requires_grad:
+        return True
+    net = getattr(decoder, 'net', None)
+    if net is None:
+        return False
+    return any(p.requires_grad for p in decoder.parameters())
 
 
 class PackedPlanes:
@@ -80,7 +90,7 @@ def pack_planes(planes) -> PackedPlanes:
     return PackedPlanes(out, n, h, w)
 
 
-def pack_decoder(decoder) -> torch.Tensor:
+def pack_decoder(decoder, *, allow_grad=False) -> torch.Tensor:
     """Read an OSGDecoder-shaped module (training/triplane.py:113-122: net[0] = FC 32->64,
     net[1] = Softplus, net[2] = FC 64->33) and pack its parameters with the runtime gains
     (training/networks_stylegan2.py:118-119).  Anything else raises: there is no generic fallback."""
@@ -93,7 +103,8 @@ def pack_decoder(decoder) -> torch.Tensor:
     for fc, shape in ((fc1, (64, 32)), (fc2, (33, 64))):
         if tuple(fc.weight.shape) != shape or fc.bias is None or getattr(fc, 'activation', 'linear') != 'linear':
             raise RuntimeError(f'decoder layer must be a linear FullyConnectedLayer with weight {shape} and a bias')
-    _forbid_autograd(fc1.weight, fc1.bias, fc2.weight, fc2.bias)
+    if not allow_grad:
+        _forbid_autograd(fc1.weight, fc1.bias, fc2.weight, fc2.bias)
     w1 = _require_cuda_f32(fc1.weight.detach(), 'decoder.net[0].weight')
     b1 = _require_cuda_f32(fc1.bias.detach(), 'decoder.net[0].bias')
     w2 = _require_cuda_f32(fc2.weight.detach(), 'decoder.net[2].weight')
@@ -168,10 +179,24 @@ class ImportanceRenderer(torch.nn.Module):
         passes slices of its gather buffers).  ``peer_sinks`` (a ``_lib.TprPeerSinks``, built by
         ``parallel.PeerGather``): the kernel also stores every ray's outputs into the peer GPUs' gather buffers over
         NVLink and leaves the depth clamp to the caller (it needs the all-reduced range)."""
+        if torch.is_grad_enabled() and _wants_grad(planes, decoder):
+            # training / fine-tuning (training/training_loop.py:335,377): same kernels forward, CUDA backward w.r.t.
+            # planes and decoder (volumetric_rendering/backward.py)
+            from .backward import render_with_grad
+            if out is not None or peer_sinks is not None:
+                raise NotImplementedError('out= / peer_sinks= are inference-only (no autograd through them)')
+            return render_with_grad(self, planes, decoder, ray_origins, ray_directions, rendering_options, noise)
+        return self._forward_impl(planes, decoder, ray_origins, ray_directions, rendering_options, noise=noise, out=out,
+                                  peer_sinks=peer_sinks)[:3]
+
+    def _forward_impl(self, planes, decoder, ray_origins, ray_directions, rendering_options, *, noise=None, out=None,
+                      peer_sinks=None, train=False):
+        """The forward proper.  Returns (rgb, depth, weight_sum, aux); ``train=True`` (the autograd path) additionally
+        keeps what the backward needs in ``aux``: packed planes / decoder, the coarse and importance depths, the range."""
         opts = rendering_options
         ray_origins = _require_cuda_f32(ray_origins, 'ray_origins', (3,))
         ray_directions = _require_cuda_f32(ray_directions, 'ray_directions', (3,))
-        _forbid_autograd(planes if isinstance(planes, torch.Tensor) else None, ray_origins, ray_directions)
+        _forbid_autograd(None if train or not isinstance(planes, torch.Tensor) else planes, ray_origins, ray_directions)
         if opts.get('clamp_mode', None) != 'softplus':
             raise AssertionError('MipRayMarcher only supports `clamp_mode`=`softplus`!')      # VR/ray_marcher.py:35
         if opts.get('density_noise', 0) > 0:
@@ -186,7 +211,7 @@ class ImportanceRenderer(torch.nn.Module):
         layout = _layout_flag(opts)
         clamp_group = int(opts.get('depth_clamp_group', 0))
         dev = ray_origins.device
-        dec = pack_decoder(decoder)
+        dec = pack_decoder(decoder, allow_grad=train)
         dc = int(opts['depth_resolution'])
         df = int(opts['depth_resolution_importance'])
         L = _lib.lib()
@@ -238,7 +263,7 @@ class ImportanceRenderer(torch.nn.Module):
             nscratch = L.tpr_render_scratch_bytes(n, m, ctypes.byref(o))
             scratch = torch.empty(nscratch, device=dev, dtype=torch.uint8)
             fine_d = fine_i = None
-            if self.debug_outputs and df > 0:
+            if (self.debug_outputs or train) and df > 0:
                 fine_d = torch.empty((n * m, df), device=dev, dtype=torch.float32)
                 fine_i = torch.empty((n * m, df), device=dev, dtype=torch.int32)
             ev = self._timing_events          # bench.py: CUDA events bracketing the render launch on this stream
@@ -257,10 +282,17 @@ class ImportanceRenderer(torch.nn.Module):
                            'tpr_render')
             if ev is not None:
                 ev[1].record()
+            aux = None
+            if train:
+                # the coarse depths the kernel derived from `jitter` (same device function, VR/renderer.py:169-192)
+                coarse_d = torch.empty((n * m, dc), device=dev, dtype=torch.float32)
+                _lib.check(L.tpr_sample_stratified(_ptr(jitter), n * m, _ptr(rs_t), _ptr(re_t), ctypes.byref(o), _ptr(coarse_d),
+                                                   _stream()), 'tpr_sample_stratified')
+                aux = dict(packed=pp, dec=dec, coarse=coarse_d, fine=fine_d, range=rng, options=o)
         self.last_depth_range = rng
         self.last_scratch = scratch                    # TPR_PHASE_TIMING=1: int64 phase counters at byte 64
         self.last_fine = (fine_d, fine_i)
-        return rgb, depth, wsum
+        return rgb, depth, wsum, aux
 
     # ------------------------------------------------------------------ forward with host buffers
     def forward_host(self, planes, decoder, ray_origins, ray_directions, rendering_options, *, noise=None, out=None):

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TPR_ABI_VERSION 3
+#define TPR_ABI_VERSION 4
 
 /* fixed by the reference model: OSGDecoder(32 -> 64 -> 1+32), three planes
  * (training/triplane.py:42,113-122; VR/renderer.py:29-37) */
@@ -237,6 +237,38 @@ int tpr_sample_stratified(const float* jitter, int64_t n_rays, const float* ray_
 /* ---- a14: math_utils.get_ray_limits_box (VR/math_utils.py:46-98) ------------------------ */
 int tpr_ray_limits_box(const float* origins, const float* dirs, int64_t n_rays,
                        float box_side_length, float* t_min, float* t_max, void* stream);
+
+/* ---- backward of a13 (the reference gets it from autograd, used by
+ *      training/training_loop.py:335,377) ------------------------------------------------------------------------- */
+/* Gradients of L with respect to the tri-planes and the decoder, given g_rgb = dL/d(rgb) [N,M,32] (channels last),
+ * g_depth = dL/d(depth) [N,M], g_weight_sum = dL/d(weight_sum) [N,M] of one tpr_render call.
+ * depths_coarse [N*M,Dc] (tpr_sample_stratified of the forward's jitter) and depths_fine [N*M,Df] (the forward's
+ * fine_depths output; NULL when Df = 0) are the sample depths of the forward, constants of the graph exactly as in the
+ * reference (VR/renderer.py:198,210: torch.no_grad + detach); depth_range [2] (device) is the forward's depth_range_out
+ * (the clamp of VR/ray_marcher.py:50 passes gradient only inside it).  From opt: box_warp, depth_resolution,
+ * depth_resolution_importance, white_back, flags (decoder precision of the colour/density recomputation).  One plane set
+ * per image (plane_sets = 0) and one clamp range per call only.
+ * g_planes_packed [N,3,H,W,32] (the layout of tpr_pack_planes; OVERWRITTEN) and g_decoder_packed
+ * [tpr_packed_decoder_bytes()] (the layout of tpr_pack_decoder; OVERWRITTEN; convert with tpr_unpack_decoder_grad).
+ * scratch: tpr_render_backward_scratch_bytes(n_img, n_rays, Dc + Df) bytes. */
+size_t tpr_render_backward_scratch_bytes(int64_t n_img, int64_t n_rays, int32_t n_samples);
+int tpr_render_backward(const float* planes_packed, int64_t n_img, int32_t height, int32_t width,
+                        const float* decoder_packed, const float* origins, const float* dirs, int64_t n_rays,
+                        const float* depths_coarse, const float* depths_fine, const float* depth_range,
+                        const TprOptions* opt, const float* g_rgb, const float* g_depth, const float* g_weight_sum,
+                        float* g_planes_packed, float* g_decoder_packed, void* scratch, size_t scratch_bytes,
+                        void* stream);
+/* packed decoder gradient -> gradients of net.0.weight [64,32], net.0.bias [64], net.2.weight [33,64], net.2.bias [33]
+ * (the chain rule through the runtime gains, training/networks_stylegan2.py:118-127, and the plane mean's 1/3). */
+int tpr_unpack_decoder_grad(const float* g_decoder_packed, float w1_gain, float b1_gain, float w2_gain, float b2_gain,
+                            float* g_w1, float* g_b1, float* g_w2, float* g_b2, void* stream);
+/* the two stages of tpr_render_backward, stand-alone (tests): the march's backward -- sigma [R,S], colours [R,S,32] of
+ * the samples in forward order -> g_sigma [R,S] and the composite weight omega [R,S] of each sample's colour
+ * (dL/d(colour_c) = 2 * g_rgb_c * omega) */
+int tpr_march_backward(const float* depths_coarse, const float* depths_fine, int32_t dc, int32_t df, const float* sigma,
+                       const float* colours, const float* g_rgb, const float* g_depth, const float* g_weight_sum,
+                       const float* depth_range, int32_t white_back, int64_t n_rays_total, float* g_sigma, float* omega,
+                       void* stream);
 
 /* ---- measurement aid: the gather roofline ------------------------- */
 /* Fetches random 128-byte lines of buf[n_lines*32 floats] with the render kernels' access shape (8 lanes x

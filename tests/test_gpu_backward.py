@@ -1,0 +1,125 @@
+"""GPU: the renderer's backward pass through the C ABI, against
+  * the gradient fixtures the UNMODIFIED reference produced under autograd (tests/golden/bwd_*.npz), and
+  * autograd through the torch restatement (oracle/torch_oracle.py, pinned to those fixtures on CPU) on the same device
+    at sizes the fixtures do not cover.
+Tolerance: 2e-4 of the largest gradient entry of each tensor (fp32 everywhere; the decoder GEMMs run as 3xTF32 on the
+tensor cores, the plane gradient is accumulated with floating-point atomics, so the summation order differs from torch's)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from tests.cases import BWD_CASES, load_bwd_case
+from oracle import triplane_oracle as O
+from oracle import torch_oracle as TO
+from tests.test_gpu_parity import make_decoder, T, dev
+
+pytestmark = pytest.mark.gpu
+REL = 2e-4
+
+
+def rel_err(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-12))
+
+
+def run_backward(pkg, scene, opts, A, B, C):
+    dec = make_decoder(pkg, scene['dec']).requires_grad_(True)
+    planes = T(scene['planes']).requires_grad_(True)
+    R = pkg.ImportanceRenderer()
+    rgb, depth, wsum = R(planes, dec, T(scene['origins']), T(scene['dirs']), opts, noise=(T(scene['jitter']), T(scene['u'])))
+    loss = (rgb * T(A)).sum() + (depth * T(B)).sum() + (wsum * T(C)).sum()
+    loss.backward()
+    return (rgb, depth, wsum), (planes.grad, dec.net[0].weight.grad, dec.net[0].bias.grad, dec.net[2].weight.grad,
+                                dec.net[2].bias.grad)
+
+
+@pytest.mark.parametrize('name', list(BWD_CASES))
+def test_gradients_match_reference_fixture(pkg, name):
+    scene, opts, gold, (A, B, C) = load_bwd_case(name)
+    (rgb, depth, wsum), grads = run_backward(pkg, scene, opts, A, B, C)
+    assert np.abs(rgb.detach().cpu().numpy() - gold['rgb']).max() < 1e-4
+    assert np.abs(depth.detach().cpu().numpy() - gold['depth']).max() < 1e-4
+    errs = {}
+    for g, k in zip(grads, ('g_planes', 'g_w1', 'g_b1', 'g_w2', 'g_b2')):
+        assert g is not None and tuple(g.shape) == gold[k].shape, k
+        assert torch.isfinite(g).all(), k
+        errs[k] = rel_err(g.cpu().numpy(), gold[k])
+    print(name, {k: f'{v:.1e}' for k, v in errs.items()})
+    assert max(errs.values()) < REL, errs
+
+
+def test_march_backward_against_autograd(pkg):
+    """tpr_march_backward alone: d/d(sigma) and the colour weights omega of random (depth, sigma, colour) rows."""
+    torch.manual_seed(5)
+    d = dev()
+    r, dc, df = 37, 24, 16
+    s = dc + df
+    coarse = torch.sort(torch.rand(r, dc, device=d) * 0.8 + 2.3, -1).values.contiguous()
+    fine = (torch.rand(r, df, device=d) * 0.8 + 2.3).contiguous()
+    sigma = (torch.randn(r, s, device=d) * 3).requires_grad_(True)
+    col = torch.rand(r, s, 32, device=d).requires_grad_(True)
+    A, B, C = torch.randn(r, 32, device=d), torch.randn(r, device=d), torch.randn(r, device=d)
+    for white in (False, True):
+        depths = torch.cat([coarse, fine], -1)
+        d_all, order = torch.sort(depths, -1)
+        rgb, depth, w = TO.march(torch.gather(col, 1, order.unsqueeze(-1).expand(-1, -1, 32)).unsqueeze(0),
+                                 torch.gather(sigma, 1, order).unsqueeze(0).unsqueeze(-1), d_all.unsqueeze(0).unsqueeze(-1), white)
+        loss = (rgb[0] * A).sum() + (depth[0, :, 0] * B).sum() + (w.sum(2)[0, :, 0] * C).sum()
+        g_sig, g_col = torch.autograd.grad(loss, (sigma, col))
+        rng = torch.stack([depths.min(), depths.max()])
+        gs = torch.empty(r, s, device=d); om = torch.empty(r, s, device=d)
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        pkg._lib.check(pkg._lib.lib().tpr_march_backward(P(coarse), P(fine), dc, df, P(sigma.detach().contiguous()),
+                                                         P(col.detach().contiguous()), P(A), P(B), P(C), P(rng), int(white), r,
+                                                         P(gs), P(om), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                       'tpr_march_backward')
+        torch.cuda.synchronize()
+        assert rel_err(gs.cpu().numpy(), g_sig.cpu().numpy()) < 2e-5
+        want_col = g_col.cpu().numpy()
+        got_col = (2 * A.unsqueeze(1) * om.unsqueeze(-1)).cpu().numpy()
+        assert rel_err(got_col, want_col) < 2e-5
+
+
+@pytest.mark.parametrize('shape', [(1, 24, 64, 48, 48), (2, 16, 48, 96, 96), (1, 20, 40, 32, 0)])
+def test_gradients_match_autograd_through_the_torch_oracle(pkg, shape):
+    """Sizes the fixtures do not cover (a few thousand rays, 96+96 depths), against same-device autograd."""
+    n, res, pres, dc, df = shape
+    scene = O.synthetic_scene(31 + dc, n, res, pres, dc, df, 0.5)
+    opts = dict(O.FFHQ_OPTIONS, depth_resolution=dc, depth_resolution_importance=df)
+    rng = np.random.RandomState(77)
+    m = res * res
+    A, B, C = (rng.standard_normal((n, m, k)).astype(np.float32) for k in (32, 1, 1))
+    (rgb, depth, wsum), grads = run_backward(pkg, scene, opts, A, B, C)
+    (rgb_o, depth_o, wsum_o), grads_o = TO.render_grads(T(scene['planes']), TO.decoder_tuple(scene['dec'], dev()),
+                                                        T(scene['origins']), T(scene['dirs']), opts, T(scene['jitter']),
+                                                        T(scene['u']), T(A), T(B), T(C))
+    assert (rgb.detach() - rgb_o).abs().max() < 1e-4
+    errs = {k: rel_err(g.cpu().numpy(), go.cpu().numpy()) for k, g, go in zip(('planes', 'w1', 'b1', 'w2', 'b2'), grads, grads_o)}
+    print(shape, {k: f'{v:.1e}' for k, v in errs.items()})
+    assert max(errs.values()) < REL, errs
+
+
+def test_backward_is_linear_in_the_upstream_gradient_and_respects_requires_grad(pkg):
+    scene, opts, gold, (A, B, C) = load_bwd_case('bwd_ffhq')
+    _, g1 = run_backward(pkg, scene, opts, A, B, C)
+    _, g2 = run_backward(pkg, scene, opts, 2 * A, 2 * B, 2 * C)
+    for a, b in zip(g1, g2):
+        assert rel_err((2 * a).cpu().numpy(), b.cpu().numpy()) < 1e-5
+    # planes only: the decoder stays frozen and gets no .grad
+    dec = make_decoder(pkg, scene['dec'])
+    planes = T(scene['planes']).requires_grad_(True)
+    rgb, depth, wsum = pkg.ImportanceRenderer()(planes, dec, T(scene['origins']), T(scene['dirs']), opts,
+                                                noise=(T(scene['jitter']), T(scene['u'])))
+    (rgb * T(A)).sum().backward()
+    assert planes.grad is not None and dec.net[0].weight.grad is None
+    # rays that require grad are refused, not silently ignored
+    with pytest.raises(NotImplementedError):
+        pkg.ImportanceRenderer()(planes, dec, T(scene['origins']).requires_grad_(True), T(scene['dirs']), opts)
+    # under no_grad the inference path runs as before
+    with torch.no_grad():
+        out = pkg.ImportanceRenderer()(planes, dec, T(scene['origins']), T(scene['dirs']), opts,
+                                       noise=(T(scene['jitter']), T(scene['u'])))
+    assert not out[0].requires_grad
+    torch.testing.assert_close(out[0], rgb.detach(), rtol=0, atol=0)
