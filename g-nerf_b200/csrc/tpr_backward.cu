@@ -15,7 +15,7 @@
 //   (tpr_run_model)         colours and densities of those points: the forward's tcgen05 point-query kernel
 //   march_backward_kernel   one warp per ray: sort, march, and the march's backward -> per sample d(loss)/d(sigma) and
 //                           the composite weight omega of its colour (d(loss)/d(colour_c) = 2 * g_rgb_c * omega)
-//   decode_backward_kernel  per tile of 128 samples: re-gather the features, layer 1 forward, the decoder's backward
+//   decode_backward_kernel  per tile of 64 samples: re-gather the features, layer 1 forward, the decoder's backward
 //                           (three small GEMMs per sample tile + two outer-product GEMMs for the weight gradients, all
 //                           on mma.sync m16n8k8 TF32 with the 3xTF32 split, fp32 accumulation), then the bilinear
 //                           scatter of d(loss)/d(features) into the packed plane gradient with 128-bit reductions
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(128) march_backward_kernel(const MarchArgs a) 
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const bool valid = lane * E + e + 1 < S;
-      gw[e] = valid ? 0.5f * (qq[e] + qq[e + 1]) - wb + C + bscale * (dm[e] - depth_raw) : 0.0f;
+      gw[e] = valid ? 0.5f * (qq[e] + qq[e + 1]) - wb + C + (pass ? bscale * (dm[e] - depth_raw) : 0.0f) : 0.0f;
       u[e] = gw[e] * w[e];
       lane_tot += u[e];
     }
@@ -194,14 +194,15 @@ __global__ void __launch_bounds__(128) march_backward_kernel(const MarchArgs a) 
 // ---------------------------------------------------------------------------------------------------------
 // decoder backward + plane-gradient scatter
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kT = 128;                 // samples per tile
-constexpr int kBT = 256;                // threads per CTA (8 warps x 16 samples)
+constexpr int kT = 64;                  // samples per tile
+constexpr int kBT = 256;                // threads per CTA: 8 warps = 4 row blocks of 16 samples x 2 warps (column halves)
 constexpr int FS = 36, HS = 72, YS = 44, W1S = 72, W2S = kOutPad;    // shared-memory row strides (floats)
 static_assert(W2S == 36, "W2t B-fragment loads assume a row stride of 36 floats");
 
+// ~108 KB: two CTAs (16 warps) per SM.  The decoder weights are kept pre-split into their TF32 hi and lo parts.
 struct __align__(16) Smem {
-  float w1t[kC * W1S];                  // [k][j]   (W1 * gain / 3)
-  float w2t[kHid * W2S + 40];           // [j][o]   (W2 * gain), then finite padding (b2) for the K = 36..39 tail reads
+  float w1t[2][kC * W1S];               // [hi, lo][k][j]   (W1 * gain / 3)
+  float w2t[2][kHid * W2S + 40];        // [hi, lo][j][o]   (W2 * gain), then finite padding for the K = 36..39 tail reads
   float b1[kHid];
   float F[kT * FS];                     // summed plane features
   float H[kT * HS];                     // softplus(layer 1)
@@ -242,18 +243,29 @@ __device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], con
   mma_tf32(d, ah, bl);
   mma_tf32(d, ah, bh);
 }
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
-__global__ void __launch_bounds__(kBT, 1) decode_backward_kernel(const DecArgs a) {
+__global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a) {
   extern __shared__ uint8_t smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw + ((16u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 15u)) & 15u));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;           // mma fragment coordinates
   const int grp = lane >> 3, sub = lane & 7;       // gather: 8 lanes per sample
-  // ---- stage the decoder
-  for (int i = tid; i < kC * kHid; i += kBT) { const int k = i >> 6, j = i & 63; s.w1t[k * W1S + j] = __ldg(a.dec + kW1tOff + i); }
-  for (int i = tid; i < kHid * W2S + 40; i += kBT)
-    s.w2t[i] = i < kHid * W2S ? __ldg(a.dec + kW2tOff + i) : (i - kHid * W2S < kOutPad ? __ldg(a.dec + kB2Off + i - kHid * W2S) : 0.0f);
+  const int mt = warp >> 1, hf = warp & 1;         // row block of 16 samples, column half
+  const int row0 = mt * 16;
+  // ---- stage the decoder, split once
+  for (int i = tid; i < kC * kHid; i += kBT) {
+    const int k = i >> 6, j = i & 63;
+    uint32_t hi, lo; split_tf32(__ldg(a.dec + kW1tOff + i), hi, lo);
+    s.w1t[0][k * W1S + j] = __uint_as_float(hi); s.w1t[1][k * W1S + j] = __uint_as_float(lo);
+  }
+  for (int i = tid; i < kHid * W2S + 40; i += kBT) {
+    const float v = i < kHid * W2S ? __ldg(a.dec + kW2tOff + i) : (i - kHid * W2S < kOutPad ? __ldg(a.dec + kB2Off + i - kHid * W2S) : 0.0f);
+    uint32_t hi, lo; split_tf32(v, hi, lo);
+    s.w2t[0][i] = __uint_as_float(hi); s.w2t[1][i] = __uint_as_float(lo);
+  }
   if (tid < kHid) s.b1[tid] = __ldg(a.dec + kB1Off + tid);
+  for (int i = tid; i < kT * (YS - 33); i += kBT) { const int r = i / (YS - 33); s.GY[r * YS + 33 + (i - r * (YS - 33))] = 0.0f; }
   __syncthreads();
 
   // weight-gradient accumulators of this warp: output tiles q = warp + 8 i (16 tiles of gW1t [32 x 64], 20 of gW2t [64 x 40])
@@ -263,16 +275,15 @@ __global__ void __launch_bounds__(kBT, 1) decode_backward_kernel(const DecArgs a
   float bacc = 0.0f;                               // tid < 64: gb1[tid]; 64 <= tid < 104: gb2[tid - 64]
   const size_t img_stride = (size_t)3 * a.H * a.W * kC;
   const long long n_tiles = (a.total + kT - 1) / kT;
-  const int row0 = warp * 16;
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long gs0 = tile * kT;
     const long long n0 = gs0 / a.pts_per_img, rem0 = gs0 - n0 * a.pts_per_img;
     const long long ray0 = gs0 / a.S;
     const int rr0 = (int)(gs0 - ray0 * a.S);
-    // ---- taps of this warp's 16 samples x 3 planes (VR/renderer.py:39-65)
-    for (int i = lane; i < 48; i += 32) {
-      const int sl = i / 3, p = i - sl * 3, sr = row0 + sl;
+    // ---- taps of this warp's 8 samples x 3 planes (VR/renderer.py:39-65)
+    if (lane < 24) {
+      const int sl = lane / 3, p = lane - sl * 3, sr = row0 + 8 * hf + sl;
       const long long gs = gs0 + sr;
       Taps tp;
       int n = 0;
@@ -287,27 +298,21 @@ __global__ void __launch_bounds__(kBT, 1) decode_backward_kernel(const DecArgs a
         for (int k = 0; k < 4; ++k) { tp.off[k] = 0; tp.w[k] = 0.0f; }
       }
       const int po = p * a.H * a.W * kC;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { s.tap_off[sr * 12 + p * 4 + k] = (uint32_t)(tp.off[k] + po); s.tap_w[sr * 12 + p * 4 + k] = tp.w[k]; }
+      *reinterpret_cast<uint4*>(s.tap_off + sr * 12 + p * 4) = make_uint4((uint32_t)(tp.off[0] + po), (uint32_t)(tp.off[1] + po),
+                                                                          (uint32_t)(tp.off[2] + po), (uint32_t)(tp.off[3] + po));
+      *reinterpret_cast<float4*>(s.tap_w + sr * 12 + p * 4) = make_float4(tp.w[0], tp.w[1], tp.w[2], tp.w[3]);
       if (p == 0) s.simg[sr] = n;
     }
     __syncwarp();
     // ---- gather: F = sum over planes and taps (the plane mean's 1/3 is folded into W1t)
 #pragma unroll 1
-    for (int it = 0; it < 4; ++it) {
-      const int sr = row0 + it * 4 + grp;
+    for (int it = 0; it < 2; ++it) {
+      const int sr = row0 + 8 * hf + it * 4 + grp;
       const float4* img = reinterpret_cast<const float4*>(a.planes + (size_t)s.simg[sr] * img_stride) + sub;
       float4 v[12];
 #pragma unroll
       for (int k = 0; k < 12; ++k) v[k] = __ldg(img + (s.tap_off[sr * 12 + k] >> 2));
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int k = 0; k < 12; ++k) {
-        const float w = s.tap_w[sr * 12 + k];
-        acc.x = fmaf(w, v[k].x, acc.x); acc.y = fmaf(w, v[k].y, acc.y); acc.z = fmaf(w, v[k].z, acc.z); acc.w = fmaf(w, v[k].w, acc.w);
-      }
-      *reinterpret_cast<float4*>(s.F + sr * FS + 4 * sub) = acc;
-      // ---- upstream gradient of the decoder outputs of this sample
+      // ---- upstream gradient of the decoder outputs of this sample (loads overlap the texel fetches)
       const long long gs = gs0 + sr;
       float gy[4] = {0.f, 0.f, 0.f, 0.f};
       float gs_sig = 0.0f;
@@ -316,24 +321,30 @@ __global__ void __launch_bounds__(kBT, 1) decode_backward_kernel(const DecArgs a
         const float4 col = __ldg(reinterpret_cast<const float4*>(a.colours + gs * 32) + sub);
         const float4 A = __ldg(reinterpret_cast<const float4*>(a.g_rgb + ray * 32) + sub);
         const float om = __ldg(a.omega + gs) * (2.0f * 1.002f);       // rgb*2-1 (VR/ray_marcher.py:55), sigmoid*1.002 (training/triplane.py:134)
+        gs_sig = __ldg(a.gsig + gs);
         const float cc[4] = {col.x, col.y, col.z, col.w}, aa[4] = {A.x, A.y, A.z, A.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float sv = (cc[k] + 0.001f) * (1.0f / 1.002f);           // sigmoid(logit)
           gy[k] = aa[k] * om * sv * (1.0f - sv);
         }
-        gs_sig = __ldg(a.gsig + gs);
       }
       float* gyr = s.GY + sr * YS;
 #pragma unroll
       for (int k = 0; k < 4; ++k) gyr[1 + 4 * sub + k] = gy[k];
       if (sub == 0) gyr[0] = gs_sig;
-      for (int c = 33 + sub; c < YS; c += 8) gyr[c] = 0.0f;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const float w = s.tap_w[sr * 12 + k];
+        acc.x = fmaf(w, v[k].x, acc.x); acc.y = fmaf(w, v[k].y, acc.y); acc.z = fmaf(w, v[k].z, acc.z); acc.w = fmaf(w, v[k].w, acc.w);
+      }
+      *reinterpret_cast<float4*>(s.F + sr * FS + 4 * sub) = acc;
     }
-    __syncwarp();
+    pair_sync(1 + mt);                             // F and GY of the 16 rows are complete
 
-    // ---- layer 1 forward for rows row0 + {g, g+8}: a = F . W1t + b1  (training/triplane.py:126-131)
-    float sgd[8][4];                               // softplus'(a) = sigmoid(a), later d/d(a)
+    // ---- layer 1 forward for rows row0 + {g, g+8}, hidden units [32 hf, 32 hf + 32): a = F . W1t + b1
+    float sgd[4][4];                               // softplus'(a) = sigmoid(a), later d/d(a)
     {
       uint32_t ah[4][4], al[4][4];
 #pragma unroll
@@ -343,14 +354,15 @@ __global__ void __launch_bounds__(kBT, 1) decode_backward_kernel(const DecArgs a
         split_tf32(f0[4], ah[ks][2], al[ks][2]); split_tf32(f0[8 * FS + 4], ah[ks][3], al[ks][3]);
       }
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int n4 = 0; n4 < 4; ++n4) {
+        const int nt = 4 * hf + n4;
         float acc[4];
         acc[0] = acc[2] = s.b1[8 * nt + 2 * t]; acc[1] = acc[3] = s.b1[8 * nt + 2 * t + 1];
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          uint32_t bh[2], bl[2];
-          split_tf32(s.w1t[(8 * ks + t) * W1S + 8 * nt + g], bh[0], bl[0]);
-          split_tf32(s.w1t[(8 * ks + t + 4) * W1S + 8 * nt + g], bh[1], bl[1]);
+          const int o0 = (8 * ks + t) * W1S + 8 * nt + g;
+          const uint32_t bh[2] = {__float_as_uint(s.w1t[0][o0]), __float_as_uint(s.w1t[0][o0 + 4 * W1S])};
+          const uint32_t bl[2] = {__float_as_uint(s.w1t[1][o0]), __float_as_uint(s.w1t[1][o0 + 4 * W1S])};
           mma3(acc, ah[ks], al[ks], bh, bl);
         }
         float h[4];
@@ -358,7 +370,7 @@ __global__ void __launch_bounds__(kBT, 1) decode_backward_kernel(const DecArgs a
         for (int i = 0; i < 4; ++i) {
           const float e = __expf(acc[i]), d = 1.0f + e;
           h[i] = acc[i] > 20.0f ? acc[i] : __logf(d);                 // Softplus(beta=1, threshold=20)
-          sgd[nt][i] = acc[i] > 20.0f ? 1.0f : __fdividef(e, d);
+          sgd[n4][i] = acc[i] > 20.0f ? 1.0f : __fdividef(e, d);
         }
         *reinterpret_cast<float2*>(s.H + (row0 + g) * HS + 8 * nt + 2 * t) = make_float2(h[0], h[1]);
         *reinterpret_cast<float2*>(s.H + (row0 + g + 8) * HS + 8 * nt + 2 * t) = make_float2(h[2], h[3]);
@@ -374,47 +386,55 @@ __global__ void __launch_bounds__(kBT, 1) decode_backward_kernel(const DecArgs a
         split_tf32(y0[4], ah[ks][2], al[ks][2]); split_tf32(y0[8 * YS + 4], ah[ks][3], al[ks][3]);
       }
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int n4 = 0; n4 < 4; ++n4) {
+        const int nt = 4 * hf + n4;
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int ks = 0; ks < 5; ++ks) {
-          uint32_t bh[2], bl[2];
-          const float* wr = s.w2t + (8 * nt + g) * W2S + 8 * ks + t;
-          split_tf32(wr[0], bh[0], bl[0]); split_tf32(wr[4], bh[1], bl[1]);
+          const int o0 = (8 * nt + g) * W2S + 8 * ks + t;
+          const uint32_t bh[2] = {__float_as_uint(s.w2t[0][o0]), __float_as_uint(s.w2t[0][o0 + 4])};
+          const uint32_t bl[2] = {__float_as_uint(s.w2t[1][o0]), __float_as_uint(s.w2t[1][o0 + 4])};
           mma3(acc, ah[ks], al[ks], bh, bl);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) sgd[nt][i] *= acc[i];
-        *reinterpret_cast<float2*>(s.GA + (row0 + g) * HS + 8 * nt + 2 * t) = make_float2(sgd[nt][0], sgd[nt][1]);
-        *reinterpret_cast<float2*>(s.GA + (row0 + g + 8) * HS + 8 * nt + 2 * t) = make_float2(sgd[nt][2], sgd[nt][3]);
+        for (int i = 0; i < 4; ++i) sgd[n4][i] *= acc[i];
+        *reinterpret_cast<float2*>(s.GA + (row0 + g) * HS + 8 * nt + 2 * t) = make_float2(sgd[n4][0], sgd[n4][1]);
+        *reinterpret_cast<float2*>(s.GA + (row0 + g + 8) * HS + 8 * nt + 2 * t) = make_float2(sgd[n4][2], sgd[n4][3]);
       }
     }
-    // ---- d/d(features) = GA . W1t^T.  GA is still in registers in accumulator layout (row g / g+8, columns 2t, 2t+1 of
-    //      each 8-column block); it is fed back as the A operand with the K index permuted (k' = t <-> column 2t,
-    //      k' = t+4 <-> column 2t+1) and the B operand is read with the same permutation, so no shuffle is needed.
+    pair_sync(1 + mt);                             // GA of the 16 rows (both column halves) is complete
+    // ---- d/d(features) = GA . W1t^T, channels [16 hf, 16 hf + 16).  The K index (hidden unit) is permuted inside every
+    //      block of eight (k' = t <-> 2t, k' = t+4 <-> 2t+1) on both operands, so that each is one 64-bit load.
     {
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int q = 0; q < 8; ++q) {
+        const float2 a01 = *reinterpret_cast<const float2*>(s.GA + (row0 + g) * HS + 8 * q + 2 * t);
+        const float2 a23 = *reinterpret_cast<const float2*>(s.GA + (row0 + g + 8) * HS + 8 * q + 2 * t);
+        uint32_t ah[4], al[4];
+        split_tf32(a01.x, ah[0], al[0]); split_tf32(a23.x, ah[1], al[1]);
+        split_tf32(a01.y, ah[2], al[2]); split_tf32(a23.y, ah[3], al[3]);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          uint32_t ah[4], al[4], bh[2], bl[2];
-          split_tf32(sgd[q][0], ah[0], al[0]); split_tf32(sgd[q][2], ah[1], al[1]);
-          split_tf32(sgd[q][1], ah[2], al[2]); split_tf32(sgd[q][3], ah[3], al[3]);
-          const float2 wv = *reinterpret_cast<const float2*>(s.w1t + (8 * nt + g) * W1S + 8 * q + 2 * t);
-          split_tf32(wv.x, bh[0], bl[0]); split_tf32(wv.y, bh[1], bl[1]);
-          mma3(acc, ah, al, bh, bl);
+        for (int n2 = 0; n2 < 2; ++n2) {
+          const int o0 = (8 * (2 * hf + n2) + g) * W1S + 8 * q + 2 * t;
+          const float2 wh = *reinterpret_cast<const float2*>(s.w1t[0] + o0), wl = *reinterpret_cast<const float2*>(s.w1t[1] + o0);
+          const uint32_t bh[2] = {__float_as_uint(wh.x), __float_as_uint(wh.y)}, bl[2] = {__float_as_uint(wl.x), __float_as_uint(wl.y)};
+          mma3(acc[n2], ah, al, bh, bl);
         }
-        *reinterpret_cast<float2*>(s.GF + (row0 + g) * FS + 8 * nt + 2 * t) = make_float2(acc[0], acc[1]);
-        *reinterpret_cast<float2*>(s.GF + (row0 + g + 8) * FS + 8 * nt + 2 * t) = make_float2(acc[2], acc[3]);
+      }
+#pragma unroll
+      for (int n2 = 0; n2 < 2; ++n2) {
+        const int nt = 2 * hf + n2;
+        *reinterpret_cast<float2*>(s.GF + (row0 + g) * FS + 8 * nt + 2 * t) = make_float2(acc[n2][0], acc[n2][1]);
+        *reinterpret_cast<float2*>(s.GF + (row0 + g + 8) * FS + 8 * nt + 2 * t) = make_float2(acc[n2][2], acc[n2][3]);
       }
     }
-    __syncthreads();                                // F, H, GA, GY, GF of all 128 samples are in shared memory
+    __syncthreads();                                // F, H, GA, GY, GF of all 64 samples are in shared memory
 
     // ---- scatter d/d(features) to the twelve texels of each sample: the transpose of the bilinear gather
 #pragma unroll 1
-    for (int it = 0; it < 4; ++it) {
-      const int sr = row0 + it * 4 + grp;
+    for (int it = 0; it < 2; ++it) {
+      const int sr = row0 + 8 * hf + it * 4 + grp;
       const float4 gf = *reinterpret_cast<const float4*>(s.GF + sr * FS + 4 * sub);
       float4* img = reinterpret_cast<float4*>(a.g_planes + (size_t)s.simg[sr] * img_stride) + sub;
 #pragma unroll
@@ -423,20 +443,20 @@ __global__ void __launch_bounds__(kBT, 1) decode_backward_kernel(const DecArgs a
         if (w != 0.0f) atomicAdd(img + (s.tap_off[sr * 12 + k] >> 2), make_float4(w * gf.x, w * gf.y, w * gf.z, w * gf.w));
       }
     }
-    // ---- weight gradients: sums over the tile's 128 samples of F (x) GA and H (x) GY
+    // ---- weight gradients: sums over the tile's 64 samples of F (x) GA and H (x) GY
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
       const int q = warp + 8 * i;
       if (q < 36) {
         const bool first = q < 16;
         const int q2 = first ? q : q - 16;
-        const int mt = first ? q2 >> 3 : q2 / 5, nt = first ? q2 & 7 : q2 - (q2 / 5) * 5;
+        const int pm = first ? q2 >> 3 : q2 / 5, pn = first ? q2 & 7 : q2 - (q2 / 5) * 5;
         const float* As = first ? s.F : s.H; const int as = first ? FS : HS;
         const float* Bs = first ? s.GA : s.GY; const int bs = first ? HS : YS;
-        const float* ap = As + t * as + 16 * mt + g;
-        const float* bp = Bs + t * bs + 8 * nt + g;
+        const float* ap = As + t * as + 16 * pm + g;
+        const float* bp = Bs + t * bs + 8 * pn + g;
 #pragma unroll 4
-        for (int ks = 0; ks < 16; ++ks) {
+        for (int ks = 0; ks < kT / 8; ++ks) {
           uint32_t ah[4], al[4], bh[2], bl[2];
           split_tf32(ap[0], ah[0], al[0]); split_tf32(ap[8], ah[1], al[1]);
           split_tf32(ap[4 * as], ah[2], al[2]); split_tf32(ap[4 * as + 8], ah[3], al[3]);
@@ -467,10 +487,10 @@ __global__ void __launch_bounds__(kBT, 1) decode_backward_kernel(const DecArgs a
     if (q < 36) {
       const bool first = q < 16;
       const int q2 = first ? q : q - 16;
-      const int mt = first ? q2 >> 3 : q2 / 5, nt = first ? q2 & 7 : q2 - (q2 / 5) * 5;
+      const int pm = first ? q2 >> 3 : q2 / 5, pn = first ? q2 & 7 : q2 - (q2 / 5) * 5;
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        const int m = 16 * mt + g + (r >> 1) * 8, n = 8 * nt + 2 * t + (r & 1);
+        const int m = 16 * pm + g + (r >> 1) * 8, n = 8 * pn + 2 * t + (r & 1);
         if (first) atomicAdd(a.g_dec + kW1tOff + m * kHid + n, pacc[i][r]);              // gW1t[k = m][j = n]
         else if (n < kOutPad) atomicAdd(a.g_dec + kW2tOff + m * kOutPad + n, pacc[i][r]); // gW2t[j = m][o = n]
       }
@@ -536,7 +556,7 @@ int launch_bwd_decode(const float* planes, int H, int W, const float* dec, const
   cudaError_t e = cudaFuncSetAttribute(bwd::decode_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const long long n_tiles = (total + bwd::kT - 1) / bwd::kT;
-  const long long grid = n_tiles < sms ? n_tiles : sms;
+  const long long grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;      // two CTAs per SM
   bwd::decode_backward_kernel<<<(unsigned)grid, bwd::kBT, smem, st>>>(a);
   return (int)cudaGetLastError();
 }
