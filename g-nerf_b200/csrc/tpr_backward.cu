@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a
   for (int i = tid; i < kT * (YS - 33); i += kBT) { const int r = i / (YS - 33); s.GY[r * YS + 33 + (i - r * (YS - 33))] = 0.0f; }
   __syncthreads();
 
-  // weight-gradient accumulators of this warp: output tiles q = warp + 8 i (16 tiles of gW1t [32 x 64], 20 of gW2t [64 x 40])
+  // weight-gradient accumulators of this warp: one 16-row block of gW2t (5 column blocks) or of gW1t (4 column blocks)
   float pacc[5][4];
 #pragma unroll
   for (int i = 0; i < 5; ++i) { pacc[i][0] = pacc[i][1] = pacc[i][2] = pacc[i][3] = 0.0f; }
@@ -343,34 +343,46 @@ __global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a
     }
     pair_sync(1 + mt);                             // F and GY of the 16 rows are complete
 
-    // ---- layer 1 forward for rows row0 + {g, g+8}, hidden units [32 hf, 32 hf + 32): a = F . W1t + b1
+    // ---- layer 1 forward for rows row0 + {g, g+8}, hidden units [32 hf, 32 hf + 32): a = F . W1t + b1.
+    //      Four column blocks are accumulated side by side and the three TF32 passes are issued block by block, so that
+    //      consecutive HMMAs never depend on each other (each accumulator chain is 12 HMMAs long).
     float sgd[4][4];                               // softplus'(a) = sigmoid(a), later d/d(a)
     {
-      uint32_t ah[4][4], al[4][4];
+      float acc[4][4];
+#pragma unroll
+      for (int n4 = 0; n4 < 4; ++n4) {
+        const int nt = 4 * hf + n4;
+        acc[n4][0] = acc[n4][2] = s.b1[8 * nt + 2 * t]; acc[n4][1] = acc[n4][3] = s.b1[8 * nt + 2 * t + 1];
+      }
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
+        uint32_t ah[4], al[4];
         const float* f0 = s.F + (row0 + g) * FS + 8 * ks + t;
-        split_tf32(f0[0], ah[ks][0], al[ks][0]); split_tf32(f0[8 * FS], ah[ks][1], al[ks][1]);
-        split_tf32(f0[4], ah[ks][2], al[ks][2]); split_tf32(f0[8 * FS + 4], ah[ks][3], al[ks][3]);
+        split_tf32(f0[0], ah[0], al[0]); split_tf32(f0[8 * FS], ah[1], al[1]);
+        split_tf32(f0[4], ah[2], al[2]); split_tf32(f0[8 * FS + 4], ah[3], al[3]);
+        uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+        for (int n4 = 0; n4 < 4; ++n4) {
+          const int o0 = (8 * ks + t) * W1S + 8 * (4 * hf + n4) + g;
+          bh[n4][0] = __float_as_uint(s.w1t[0][o0]); bh[n4][1] = __float_as_uint(s.w1t[0][o0 + 4 * W1S]);
+          bl[n4][0] = __float_as_uint(s.w1t[1][o0]); bl[n4][1] = __float_as_uint(s.w1t[1][o0 + 4 * W1S]);
+        }
+#pragma unroll
+        for (int n4 = 0; n4 < 4; ++n4) mma_tf32(acc[n4], al, bh[n4]);
+#pragma unroll
+        for (int n4 = 0; n4 < 4; ++n4) mma_tf32(acc[n4], ah, bl[n4]);
+#pragma unroll
+        for (int n4 = 0; n4 < 4; ++n4) mma_tf32(acc[n4], ah, bh[n4]);
       }
 #pragma unroll
       for (int n4 = 0; n4 < 4; ++n4) {
         const int nt = 4 * hf + n4;
-        float acc[4];
-        acc[0] = acc[2] = s.b1[8 * nt + 2 * t]; acc[1] = acc[3] = s.b1[8 * nt + 2 * t + 1];
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const int o0 = (8 * ks + t) * W1S + 8 * nt + g;
-          const uint32_t bh[2] = {__float_as_uint(s.w1t[0][o0]), __float_as_uint(s.w1t[0][o0 + 4 * W1S])};
-          const uint32_t bl[2] = {__float_as_uint(s.w1t[1][o0]), __float_as_uint(s.w1t[1][o0 + 4 * W1S])};
-          mma3(acc, ah[ks], al[ks], bh, bl);
-        }
         float h[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float e = __expf(acc[i]), d = 1.0f + e;
-          h[i] = acc[i] > 20.0f ? acc[i] : __logf(d);                 // Softplus(beta=1, threshold=20)
-          sgd[n4][i] = acc[i] > 20.0f ? 1.0f : __fdividef(e, d);
+          const float e = __expf(acc[n4][i]), d = 1.0f + e;
+          h[i] = acc[n4][i] > 20.0f ? acc[n4][i] : __logf(d);         // Softplus(beta=1, threshold=20)
+          sgd[n4][i] = acc[n4][i] > 20.0f ? 1.0f : __fdividef(e, d);
         }
         *reinterpret_cast<float2*>(s.H + (row0 + g) * HS + 8 * nt + 2 * t) = make_float2(h[0], h[1]);
         *reinterpret_cast<float2*>(s.H + (row0 + g + 8) * HS + 8 * nt + 2 * t) = make_float2(h[2], h[3]);
@@ -378,26 +390,34 @@ __global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a
     }
     // ---- d/d(hidden) = GY . W2 (K = 40 outputs, 33 real), times softplus' -> d/d(a)
     {
-      uint32_t ah[5][4], al[5][4];
+      float acc[4][4];
+#pragma unroll
+      for (int n4 = 0; n4 < 4; ++n4) { acc[n4][0] = acc[n4][1] = acc[n4][2] = acc[n4][3] = 0.0f; }
 #pragma unroll
       for (int ks = 0; ks < 5; ++ks) {
+        uint32_t ah[4], al[4];
         const float* y0 = s.GY + (row0 + g) * YS + 8 * ks + t;
-        split_tf32(y0[0], ah[ks][0], al[ks][0]); split_tf32(y0[8 * YS], ah[ks][1], al[ks][1]);
-        split_tf32(y0[4], ah[ks][2], al[ks][2]); split_tf32(y0[8 * YS + 4], ah[ks][3], al[ks][3]);
+        split_tf32(y0[0], ah[0], al[0]); split_tf32(y0[8 * YS], ah[1], al[1]);
+        split_tf32(y0[4], ah[2], al[2]); split_tf32(y0[8 * YS + 4], ah[3], al[3]);
+        uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+        for (int n4 = 0; n4 < 4; ++n4) {
+          const int o0 = (8 * (4 * hf + n4) + g) * W2S + 8 * ks + t;
+          bh[n4][0] = __float_as_uint(s.w2t[0][o0]); bh[n4][1] = __float_as_uint(s.w2t[0][o0 + 4]);
+          bl[n4][0] = __float_as_uint(s.w2t[1][o0]); bl[n4][1] = __float_as_uint(s.w2t[1][o0 + 4]);
+        }
+#pragma unroll
+        for (int n4 = 0; n4 < 4; ++n4) mma_tf32(acc[n4], al, bh[n4]);
+#pragma unroll
+        for (int n4 = 0; n4 < 4; ++n4) mma_tf32(acc[n4], ah, bl[n4]);
+#pragma unroll
+        for (int n4 = 0; n4 < 4; ++n4) mma_tf32(acc[n4], ah, bh[n4]);
       }
 #pragma unroll
       for (int n4 = 0; n4 < 4; ++n4) {
         const int nt = 4 * hf + n4;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int ks = 0; ks < 5; ++ks) {
-          const int o0 = (8 * nt + g) * W2S + 8 * ks + t;
-          const uint32_t bh[2] = {__float_as_uint(s.w2t[0][o0]), __float_as_uint(s.w2t[0][o0 + 4])};
-          const uint32_t bl[2] = {__float_as_uint(s.w2t[1][o0]), __float_as_uint(s.w2t[1][o0 + 4])};
-          mma3(acc, ah[ks], al[ks], bh, bl);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) sgd[n4][i] *= acc[i];
+        for (int i = 0; i < 4; ++i) sgd[n4][i] *= acc[n4][i];
         *reinterpret_cast<float2*>(s.GA + (row0 + g) * HS + 8 * nt + 2 * t) = make_float2(sgd[n4][0], sgd[n4][1]);
         *reinterpret_cast<float2*>(s.GA + (row0 + g + 8) * HS + 8 * nt + 2 * t) = make_float2(sgd[n4][2], sgd[n4][3]);
       }
@@ -405,28 +425,51 @@ __global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a
     pair_sync(1 + mt);                             // GA of the 16 rows (both column halves) is complete
     // ---- d/d(features) = GA . W1t^T, channels [16 hf, 16 hf + 16).  The K index (hidden unit) is permuted inside every
     //      block of eight (k' = t <-> 2t, k' = t+4 <-> 2t+1) on both operands, so that each is one 64-bit load.
+    //      Even and odd K blocks go to separate accumulators (four independent chains).
     {
-      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      float acc[2][2][4];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float2 a01 = *reinterpret_cast<const float2*>(s.GA + (row0 + g) * HS + 8 * q + 2 * t);
-        const float2 a23 = *reinterpret_cast<const float2*>(s.GA + (row0 + g + 8) * HS + 8 * q + 2 * t);
-        uint32_t ah[4], al[4];
-        split_tf32(a01.x, ah[0], al[0]); split_tf32(a23.x, ah[1], al[1]);
-        split_tf32(a01.y, ah[2], al[2]); split_tf32(a23.y, ah[3], al[3]);
+      for (int n2 = 0; n2 < 2; ++n2)
 #pragma unroll
-        for (int n2 = 0; n2 < 2; ++n2) {
-          const int o0 = (8 * (2 * hf + n2) + g) * W1S + 8 * q + 2 * t;
-          const float2 wh = *reinterpret_cast<const float2*>(s.w1t[0] + o0), wl = *reinterpret_cast<const float2*>(s.w1t[1] + o0);
-          const uint32_t bh[2] = {__float_as_uint(wh.x), __float_as_uint(wh.y)}, bl[2] = {__float_as_uint(wl.x), __float_as_uint(wl.y)};
-          mma3(acc[n2], ah, al, bh, bl);
+        for (int par = 0; par < 2; ++par) { acc[n2][par][0] = acc[n2][par][1] = acc[n2][par][2] = acc[n2][par][3] = 0.0f; }
+#pragma unroll
+      for (int q2 = 0; q2 < 4; ++q2) {
+        uint32_t ah[2][4], al[2][4], bh[2][2][2], bl[2][2][2];
+#pragma unroll
+        for (int par = 0; par < 2; ++par) {
+          const int q = 2 * q2 + par;
+          const float2 a01 = *reinterpret_cast<const float2*>(s.GA + (row0 + g) * HS + 8 * q + 2 * t);
+          const float2 a23 = *reinterpret_cast<const float2*>(s.GA + (row0 + g + 8) * HS + 8 * q + 2 * t);
+          split_tf32(a01.x, ah[par][0], al[par][0]); split_tf32(a23.x, ah[par][1], al[par][1]);
+          split_tf32(a01.y, ah[par][2], al[par][2]); split_tf32(a23.y, ah[par][3], al[par][3]);
+#pragma unroll
+          for (int n2 = 0; n2 < 2; ++n2) {
+            const int o0 = (8 * (2 * hf + n2) + g) * W1S + 8 * q + 2 * t;
+            const float2 wh = *reinterpret_cast<const float2*>(s.w1t[0] + o0), wl = *reinterpret_cast<const float2*>(s.w1t[1] + o0);
+            bh[par][n2][0] = __float_as_uint(wh.x); bh[par][n2][1] = __float_as_uint(wh.y);
+            bl[par][n2][0] = __float_as_uint(wl.x); bl[par][n2][1] = __float_as_uint(wl.y);
+          }
         }
+#pragma unroll
+        for (int par = 0; par < 2; ++par)
+#pragma unroll
+          for (int n2 = 0; n2 < 2; ++n2) mma_tf32(acc[n2][par], al[par], bh[par][n2]);
+#pragma unroll
+        for (int par = 0; par < 2; ++par)
+#pragma unroll
+          for (int n2 = 0; n2 < 2; ++n2) mma_tf32(acc[n2][par], ah[par], bl[par][n2]);
+#pragma unroll
+        for (int par = 0; par < 2; ++par)
+#pragma unroll
+          for (int n2 = 0; n2 < 2; ++n2) mma_tf32(acc[n2][par], ah[par], bh[par][n2]);
       }
 #pragma unroll
       for (int n2 = 0; n2 < 2; ++n2) {
         const int nt = 2 * hf + n2;
-        *reinterpret_cast<float2*>(s.GF + (row0 + g) * FS + 8 * nt + 2 * t) = make_float2(acc[n2][0], acc[n2][1]);
-        *reinterpret_cast<float2*>(s.GF + (row0 + g + 8) * FS + 8 * nt + 2 * t) = make_float2(acc[n2][2], acc[n2][3]);
+        *reinterpret_cast<float2*>(s.GF + (row0 + g) * FS + 8 * nt + 2 * t) =
+            make_float2(acc[n2][0][0] + acc[n2][1][0], acc[n2][0][1] + acc[n2][1][1]);
+        *reinterpret_cast<float2*>(s.GF + (row0 + g + 8) * FS + 8 * nt + 2 * t) =
+            make_float2(acc[n2][0][2] + acc[n2][1][2], acc[n2][0][3] + acc[n2][1][3]);
       }
     }
     __syncthreads();                                // F, H, GA, GY, GF of all 64 samples are in shared memory
@@ -443,27 +486,35 @@ __global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a
         if (w != 0.0f) atomicAdd(img + (s.tap_off[sr * 12 + k] >> 2), make_float4(w * gf.x, w * gf.y, w * gf.z, w * gf.w));
       }
     }
-    // ---- weight gradients: sums over the tile's 64 samples of F (x) GA and H (x) GY
+    // ---- weight gradients: sums over the tile's 64 samples of H (x) GY (gW2t [64 x 40]: warps 0-3, 16 rows x 5 column
+    //      blocks each) and F (x) GA (gW1t [32 x 64]: warps 4-7, 16 rows x 4 column blocks each).  The A fragment of a
+    //      K step is loaded and split once for all column blocks of the warp.
+    {
+      const bool second = warp < 4;                                  // gW2t
+      const int pm = second ? warp : (warp - 4) >> 1;
+      const int pn0 = second ? 0 : 4 * ((warp - 4) & 1);
+      const float* As = second ? s.H : s.F; const int as = second ? HS : FS;
+      const float* Bs = second ? s.GY : s.GA; const int bs = second ? YS : HS;
+      const float* ap = As + t * as + 16 * pm + g;
+      const float* bp = Bs + t * bs + 8 * pn0 + g;
+#pragma unroll 2
+      for (int ks = 0; ks < kT / 8; ++ks) {
+        uint32_t ah[4], al[4], bh[5][2], bl[5][2];
+        split_tf32(ap[0], ah[0], al[0]); split_tf32(ap[8], ah[1], al[1]);
+        split_tf32(ap[4 * as], ah[2], al[2]); split_tf32(ap[4 * as + 8], ah[3], al[3]);
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      const int q = warp + 8 * i;
-      if (q < 36) {
-        const bool first = q < 16;
-        const int q2 = first ? q : q - 16;
-        const int pm = first ? q2 >> 3 : q2 / 5, pn = first ? q2 & 7 : q2 - (q2 / 5) * 5;
-        const float* As = first ? s.F : s.H; const int as = first ? FS : HS;
-        const float* Bs = first ? s.GA : s.GY; const int bs = first ? HS : YS;
-        const float* ap = As + t * as + 16 * pm + g;
-        const float* bp = Bs + t * bs + 8 * pn + g;
-#pragma unroll 4
-        for (int ks = 0; ks < kT / 8; ++ks) {
-          uint32_t ah[4], al[4], bh[2], bl[2];
-          split_tf32(ap[0], ah[0], al[0]); split_tf32(ap[8], ah[1], al[1]);
-          split_tf32(ap[4 * as], ah[2], al[2]); split_tf32(ap[4 * as + 8], ah[3], al[3]);
-          split_tf32(bp[0], bh[0], bl[0]); split_tf32(bp[4 * bs], bh[1], bl[1]);
-          mma3(pacc[i], ah, al, bh, bl);
-          ap += 8 * as; bp += 8 * bs;
-        }
+        for (int i = 0; i < 4; ++i) { split_tf32(bp[8 * i], bh[i][0], bl[i][0]); split_tf32(bp[4 * bs + 8 * i], bh[i][1], bl[i][1]); }
+        if (second) { split_tf32(bp[32], bh[4][0], bl[4][0]); split_tf32(bp[4 * bs + 32], bh[4][1], bl[4][1]); }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mma_tf32(pacc[i], al, bh[i]);
+        if (second) mma_tf32(pacc[4], al, bh[4]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mma_tf32(pacc[i], ah, bl[i]);
+        if (second) mma_tf32(pacc[4], ah, bl[4]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mma_tf32(pacc[i], ah, bh[i]);
+        if (second) mma_tf32(pacc[4], ah, bh[4]);
+        ap += 8 * as; bp += 8 * bs;
       }
     }
     if (tid < kHid) {
@@ -481,18 +532,19 @@ __global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a
   }
 
   // ---- flush this CTA's partial weight gradients
+  {
+    const bool second = warp < 4;
+    const int pm = second ? warp : (warp - 4) >> 1;
+    const int pn0 = second ? 0 : 4 * ((warp - 4) & 1);
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    const int q = warp + 8 * i;
-    if (q < 36) {
-      const bool first = q < 16;
-      const int q2 = first ? q : q - 16;
-      const int pm = first ? q2 >> 3 : q2 / 5, pn = first ? q2 & 7 : q2 - (q2 / 5) * 5;
+    for (int i = 0; i < 5; ++i) {
+      if (i < 4 || second) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int m = 16 * pm + g + (r >> 1) * 8, n = 8 * pn + 2 * t + (r & 1);
-        if (first) atomicAdd(a.g_dec + kW1tOff + m * kHid + n, pacc[i][r]);              // gW1t[k = m][j = n]
-        else if (n < kOutPad) atomicAdd(a.g_dec + kW2tOff + m * kOutPad + n, pacc[i][r]); // gW2t[j = m][o = n]
+        for (int r = 0; r < 4; ++r) {
+          const int m = 16 * pm + g + (r >> 1) * 8, n = 8 * (pn0 + i) + 2 * t + (r & 1);
+          if (!second) atomicAdd(a.g_dec + kW1tOff + m * kHid + n, pacc[i][r]);             // gW1t[k = m][j = n]
+          else if (n < kOutPad) atomicAdd(a.g_dec + kW2tOff + m * kOutPad + n, pacc[i][r]);  // gW2t[j = m][o = n]
+        }
       }
     }
   }
