@@ -187,6 +187,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--mode', default='fp32', choices=['fp32', 'bf16', 'fp32_ffma'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-train-step', action='store_true', help='skip the forward+backward timing (N = 1 only)')
     ap.add_argument('--gather', default='peer', choices=['peer', 'nccl'],
                     help='N > 1: peer = the render kernel stores into every GPU\'s gather buffers over NVLink; '
                          'nccl = render, then an in-place all-gather (A/B)')
@@ -290,6 +291,34 @@ def main():
     barrier()
     e2e_ms = f0.elapsed_time(f1) / e2e_steps
 
+    # ---- training step: forward + backward w.r.t. planes and decoder, same workload
+    train = None
+    if world == 1 and not args.no_train_step and args.mode != 'fp32_ffma':
+        planes_g = planes.detach().clone().requires_grad_(True)
+        dec_g = make_decoder(torch, pkg, dev, seed=0).requires_grad_(True)
+        ups = (torch.randn(N_IMG, m, 32, device=dev), torch.randn(N_IMG, m, 1, device=dev), torch.randn(N_IMG, m, 1, device=dev))
+
+        def train_step():
+            planes_g.grad = None
+            for prm in dec_g.parameters():
+                prm.grad = None
+            torch.autograd.backward(renderer(planes_g, dec_g, origins, dirs, opts), ups)
+        for _ in range(3):
+            train_step()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_train = max(3, min(args.steps, 10))
+        g0.record()
+        for _ in range(n_train):
+            train_step()
+        g1.record()
+        barrier()
+        tr_ms = g0.elapsed_time(g1) / n_train
+        train = {'ms_per_step': tr_ms, 'value': samples_per_step / (tr_ms * 1e-3), 'unit': METRIC, 'steps': n_train,
+                 'what': 'ImportanceRenderer.forward + backward (gradients of planes and the four decoder tensors), '
+                         'inputs resident in HBM; forward as above, backward = tpr_render_backward'}
+        del planes_g, dec_g, ups
+
     # max over ranks
     if world > 1:
         t = torch.tensor([ms, e2e_ms, kern_ms], device=dev, dtype=torch.float64)
@@ -324,6 +353,8 @@ def main():
             if world == 1 else 'pinned .to(device) + render_sharded + pinned copy back',
             'clocks': clocks,
         }
+        if train is not None:
+            line['train_step'] = train
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'], _ = cpu_baseline(48)
         print(json.dumps(line))
