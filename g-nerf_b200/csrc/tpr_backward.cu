@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <stdlib.h>
 #include "triplane_b200.h"
 #include "tpr_device.cuh"
 
@@ -225,6 +226,7 @@ struct DecArgs {
   float box_scale;
   float* g_planes;                      // packed, zero-initialised
   float* g_dec;                         // [kDecFloats], zero-initialised
+  int debug;                            // TPR_BWD_DEBUG (profiling A/B only): 1 = no scatter, 2 = no weight-gradient phase
 };
 
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
@@ -243,8 +245,16 @@ __device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], con
   mma_tf32(d, ah, bl);
   mma_tf32(d, ah, bh);
 }
+template <bool FAST>
+__device__ __forceinline__ void split_op(float x, uint32_t& hi, uint32_t& lo) {
+  if (FAST) { asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x)); lo = 0u; }
+  else split_tf32(x, hi, lo);
+}
 __device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
+// FAST = false: 3xTF32 (fp32-grade gradients, the parity mode).  FAST = true (decoder_precision = 'bf16', the caller's
+// reduced-precision mode): operands rounded to TF32 (round to nearest), one HMMA per product.
+template <bool FAST>
 __global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a) {
   extern __shared__ uint8_t smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw + ((16u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 15u)) & 15u));
@@ -256,12 +266,12 @@ __global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a
   // ---- stage the decoder, split once
   for (int i = tid; i < kC * kHid; i += kBT) {
     const int k = i >> 6, j = i & 63;
-    uint32_t hi, lo; split_tf32(__ldg(a.dec + kW1tOff + i), hi, lo);
+    uint32_t hi, lo; split_op<FAST>(__ldg(a.dec + kW1tOff + i), hi, lo);
     s.w1t[0][k * W1S + j] = __uint_as_float(hi); s.w1t[1][k * W1S + j] = __uint_as_float(lo);
   }
   for (int i = tid; i < kHid * W2S + 40; i += kBT) {
     const float v = i < kHid * W2S ? __ldg(a.dec + kW2tOff + i) : (i - kHid * W2S < kOutPad ? __ldg(a.dec + kB2Off + i - kHid * W2S) : 0.0f);
-    uint32_t hi, lo; split_tf32(v, hi, lo);
+    uint32_t hi, lo; split_op<FAST>(v, hi, lo);
     s.w2t[0][i] = __uint_as_float(hi); s.w2t[1][i] = __uint_as_float(lo);
   }
   if (tid < kHid) s.b1[tid] = __ldg(a.dec + kB1Off + tid);
@@ -358,8 +368,8 @@ __global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a
       for (int ks = 0; ks < 4; ++ks) {
         uint32_t ah[4], al[4];
         const float* f0 = s.F + (row0 + g) * FS + 8 * ks + t;
-        split_tf32(f0[0], ah[0], al[0]); split_tf32(f0[8 * FS], ah[1], al[1]);
-        split_tf32(f0[4], ah[2], al[2]); split_tf32(f0[8 * FS + 4], ah[3], al[3]);
+        split_op<FAST>(f0[0], ah[0], al[0]); split_op<FAST>(f0[8 * FS], ah[1], al[1]);
+        split_op<FAST>(f0[4], ah[2], al[2]); split_op<FAST>(f0[8 * FS + 4], ah[3], al[3]);
         uint32_t bh[4][2], bl[4][2];
 #pragma unroll
         for (int n4 = 0; n4 < 4; ++n4) {
@@ -368,9 +378,9 @@ __global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a
           bl[n4][0] = __float_as_uint(s.w1t[1][o0]); bl[n4][1] = __float_as_uint(s.w1t[1][o0 + 4 * W1S]);
         }
 #pragma unroll
-        for (int n4 = 0; n4 < 4; ++n4) mma_tf32(acc[n4], al, bh[n4]);
+        for (int n4 = 0; n4 < 4; ++n4) if (!FAST) mma_tf32(acc[n4], al, bh[n4]);
 #pragma unroll
-        for (int n4 = 0; n4 < 4; ++n4) mma_tf32(acc[n4], ah, bl[n4]);
+        for (int n4 = 0; n4 < 4; ++n4) if (!FAST) mma_tf32(acc[n4], ah, bl[n4]);
 #pragma unroll
         for (int n4 = 0; n4 < 4; ++n4) mma_tf32(acc[n4], ah, bh[n4]);
       }
@@ -397,8 +407,8 @@ __global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a
       for (int ks = 0; ks < 5; ++ks) {
         uint32_t ah[4], al[4];
         const float* y0 = s.GY + (row0 + g) * YS + 8 * ks + t;
-        split_tf32(y0[0], ah[0], al[0]); split_tf32(y0[8 * YS], ah[1], al[1]);
-        split_tf32(y0[4], ah[2], al[2]); split_tf32(y0[8 * YS + 4], ah[3], al[3]);
+        split_op<FAST>(y0[0], ah[0], al[0]); split_op<FAST>(y0[8 * YS], ah[1], al[1]);
+        split_op<FAST>(y0[4], ah[2], al[2]); split_op<FAST>(y0[8 * YS + 4], ah[3], al[3]);
         uint32_t bh[4][2], bl[4][2];
 #pragma unroll
         for (int n4 = 0; n4 < 4; ++n4) {
@@ -407,9 +417,9 @@ __global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a
           bl[n4][0] = __float_as_uint(s.w2t[1][o0]); bl[n4][1] = __float_as_uint(s.w2t[1][o0 + 4]);
         }
 #pragma unroll
-        for (int n4 = 0; n4 < 4; ++n4) mma_tf32(acc[n4], al, bh[n4]);
+        for (int n4 = 0; n4 < 4; ++n4) if (!FAST) mma_tf32(acc[n4], al, bh[n4]);
 #pragma unroll
-        for (int n4 = 0; n4 < 4; ++n4) mma_tf32(acc[n4], ah, bl[n4]);
+        for (int n4 = 0; n4 < 4; ++n4) if (!FAST) mma_tf32(acc[n4], ah, bl[n4]);
 #pragma unroll
         for (int n4 = 0; n4 < 4; ++n4) mma_tf32(acc[n4], ah, bh[n4]);
       }
@@ -440,8 +450,8 @@ __global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a
           const int q = 2 * q2 + par;
           const float2 a01 = *reinterpret_cast<const float2*>(s.GA + (row0 + g) * HS + 8 * q + 2 * t);
           const float2 a23 = *reinterpret_cast<const float2*>(s.GA + (row0 + g + 8) * HS + 8 * q + 2 * t);
-          split_tf32(a01.x, ah[par][0], al[par][0]); split_tf32(a23.x, ah[par][1], al[par][1]);
-          split_tf32(a01.y, ah[par][2], al[par][2]); split_tf32(a23.y, ah[par][3], al[par][3]);
+          split_op<FAST>(a01.x, ah[par][0], al[par][0]); split_op<FAST>(a23.x, ah[par][1], al[par][1]);
+          split_op<FAST>(a01.y, ah[par][2], al[par][2]); split_op<FAST>(a23.y, ah[par][3], al[par][3]);
 #pragma unroll
           for (int n2 = 0; n2 < 2; ++n2) {
             const int o0 = (8 * (2 * hf + n2) + g) * W1S + 8 * q + 2 * t;
@@ -453,11 +463,11 @@ __global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a
 #pragma unroll
         for (int par = 0; par < 2; ++par)
 #pragma unroll
-          for (int n2 = 0; n2 < 2; ++n2) mma_tf32(acc[n2][par], al[par], bh[par][n2]);
+          for (int n2 = 0; n2 < 2; ++n2) if (!FAST) mma_tf32(acc[n2][par], al[par], bh[par][n2]);
 #pragma unroll
         for (int par = 0; par < 2; ++par)
 #pragma unroll
-          for (int n2 = 0; n2 < 2; ++n2) mma_tf32(acc[n2][par], ah[par], bl[par][n2]);
+          for (int n2 = 0; n2 < 2; ++n2) if (!FAST) mma_tf32(acc[n2][par], ah[par], bl[par][n2]);
 #pragma unroll
         for (int par = 0; par < 2; ++par)
 #pragma unroll
@@ -483,13 +493,13 @@ __global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a
 #pragma unroll
       for (int k = 0; k < 12; ++k) {
         const float w = s.tap_w[sr * 12 + k];
-        if (w != 0.0f) atomicAdd(img + (s.tap_off[sr * 12 + k] >> 2), make_float4(w * gf.x, w * gf.y, w * gf.z, w * gf.w));
+        if (w != 0.0f && !(a.debug & 1)) atomicAdd(img + (s.tap_off[sr * 12 + k] >> 2), make_float4(w * gf.x, w * gf.y, w * gf.z, w * gf.w));
       }
     }
     // ---- weight gradients: sums over the tile's 64 samples of H (x) GY (gW2t [64 x 40]: warps 0-3, 16 rows x 5 column
     //      blocks each) and F (x) GA (gW1t [32 x 64]: warps 4-7, 16 rows x 4 column blocks each).  The A fragment of a
     //      K step is loaded and split once for all column blocks of the warp.
-    {
+    if (!(a.debug & 2)) {
       const bool second = warp < 4;                                  // gW2t
       const int pm = second ? warp : (warp - 4) >> 1;
       const int pn0 = second ? 0 : 4 * ((warp - 4) & 1);
@@ -500,17 +510,17 @@ __global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a
 #pragma unroll 2
       for (int ks = 0; ks < kT / 8; ++ks) {
         uint32_t ah[4], al[4], bh[5][2], bl[5][2];
-        split_tf32(ap[0], ah[0], al[0]); split_tf32(ap[8], ah[1], al[1]);
-        split_tf32(ap[4 * as], ah[2], al[2]); split_tf32(ap[4 * as + 8], ah[3], al[3]);
+        split_op<FAST>(ap[0], ah[0], al[0]); split_op<FAST>(ap[8], ah[1], al[1]);
+        split_op<FAST>(ap[4 * as], ah[2], al[2]); split_op<FAST>(ap[4 * as + 8], ah[3], al[3]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { split_tf32(bp[8 * i], bh[i][0], bl[i][0]); split_tf32(bp[4 * bs + 8 * i], bh[i][1], bl[i][1]); }
-        if (second) { split_tf32(bp[32], bh[4][0], bl[4][0]); split_tf32(bp[4 * bs + 32], bh[4][1], bl[4][1]); }
+        for (int i = 0; i < 4; ++i) { split_op<FAST>(bp[8 * i], bh[i][0], bl[i][0]); split_op<FAST>(bp[4 * bs + 8 * i], bh[i][1], bl[i][1]); }
+        if (second) { split_op<FAST>(bp[32], bh[4][0], bl[4][0]); split_op<FAST>(bp[4 * bs + 32], bh[4][1], bl[4][1]); }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) mma_tf32(pacc[i], al, bh[i]);
-        if (second) mma_tf32(pacc[4], al, bh[4]);
+        for (int i = 0; i < 4; ++i) if (!FAST) mma_tf32(pacc[i], al, bh[i]);
+        if (second) if (!FAST) mma_tf32(pacc[4], al, bh[4]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) mma_tf32(pacc[i], ah, bl[i]);
-        if (second) mma_tf32(pacc[4], ah, bl[4]);
+        for (int i = 0; i < 4; ++i) if (!FAST) mma_tf32(pacc[i], ah, bl[i]);
+        if (second) if (!FAST) mma_tf32(pacc[4], ah, bl[4]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) mma_tf32(pacc[i], ah, bh[i]);
         if (second) mma_tf32(pacc[4], ah, bh[4]);
@@ -599,17 +609,19 @@ int launch_bwd_march(const float* dc, const float* df, int Dc, int Df, const flo
 
 int launch_bwd_decode(const float* planes, int H, int W, const float* dec, const float* pts, const float* colours,
                       const float* gsig, const float* omega, const float* g_rgb, long long total, long long pts_per_img, int S,
-                      float box_scale, float* g_planes, float* g_dec, int sms, cudaStream_t st) {
+                      float box_scale, float* g_planes, float* g_dec, int fast, int sms, cudaStream_t st) {
   bwd::DecArgs a;
   a.planes = planes; a.H = H; a.W = W; a.dec = dec; a.pts = pts; a.colours = colours; a.gsig = gsig; a.omega = omega;
   a.g_rgb = g_rgb; a.total = total; a.pts_per_img = pts_per_img; a.S = S; a.box_scale = box_scale; a.g_planes = g_planes;
   a.g_dec = g_dec;
+  { const char* e = getenv("TPR_BWD_DEBUG"); a.debug = e ? atoi(e) : 0; }
   const size_t smem = sizeof(bwd::Smem) + 16;
-  cudaError_t e = cudaFuncSetAttribute(bwd::decode_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  void (*kern)(const bwd::DecArgs) = fast ? bwd::decode_backward_kernel<true> : bwd::decode_backward_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const long long n_tiles = (total + bwd::kT - 1) / bwd::kT;
   const long long grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;      // two CTAs per SM
-  bwd::decode_backward_kernel<<<(unsigned)grid, bwd::kBT, smem, st>>>(a);
+  kern<<<(unsigned)grid, bwd::kBT, smem, st>>>(a);
   return (int)cudaGetLastError();
 }
 

@@ -35,7 +35,7 @@ int launch_bwd_march(const float* dc, const float* df, int Dc, int Df, const flo
                      long long n_rays_total, float* gsig, float* omega, int sms, cudaStream_t st);
 int launch_bwd_decode(const float* planes, int H, int W, const float* dec, const float* pts, const float* colours,
                       const float* gsig, const float* omega, const float* g_rgb, long long total, long long pts_per_img, int S,
-                      float box_scale, float* g_planes, float* g_dec, int sms, cudaStream_t st);
+                      float box_scale, float* g_planes, float* g_dec, int fast, int sms, cudaStream_t st);
 int launch_unpack_decoder_grad(const float* gd, float g_w1, float g_b1, float g_w2, float g_b2, float* w1, float* b1, float* w2,
                                float* b2, cudaStream_t st);
 
@@ -1201,7 +1201,8 @@ int tpr_render_backward(const float* planes_packed, int64_t n_img, int32_t heigh
   if (e == cudaSuccess) e = cudaMemsetAsync(g_decoder_packed, 0, kDecFloats * sizeof(float), st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
   rc = launch_bwd_decode(planes_packed, height, width, decoder_packed, pts, colours, gsig, omega, g_rgb, (long long)T,
-                         (long long)n_rays * S, S, (float)(2.0 / opt->box_warp), g_planes_packed, g_decoder_packed, di.sms, st);
+                         (long long)n_rays * S, S, (float)(2.0 / opt->box_warp), g_planes_packed, g_decoder_packed,
+                         opt->flags == TPR_MLP_BF16, di.sms, st);
   if (rc != 0) return cuda_fail((cudaError_t)rc, "decode_backward_kernel");
   return 0;
 }

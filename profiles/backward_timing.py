@@ -9,7 +9,7 @@ import bench
 from oracle import torch_oracle as TO
 pkg = importlib.import_module('g-nerf_b200')
 ap = argparse.ArgumentParser(); ap.add_argument('--n-img', type=int, default=8); ap.add_argument('--eager-img', type=int, default=1)
-ap.add_argument('--reps', type=int, default=10)
+ap.add_argument('--reps', type=int, default=10); ap.add_argument('--mode', default='fp32')
 args = ap.parse_args()
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = torch.device('cuda:0')
@@ -17,7 +17,7 @@ planes_h, c2w, K = bench.make_inputs(torch, dev, 100, n_img=args.n_img)
 planes = planes_h.to(dev).requires_grad_(True)
 dec = bench.make_decoder(torch, pkg, dev, 0).requires_grad_(True)
 o, d = pkg.RaySampler()(c2w.to(dev), K.to(dev), bench.RES)
-opts = dict(bench.OPTS)
+opts = dict(bench.OPTS, decoder_precision=args.mode)
 n, m = o.shape[:2]
 R = pkg.ImportanceRenderer()
 A, B, C = torch.randn(n, m, 32, device=dev), torch.randn(n, m, 1, device=dev), torch.randn(n, m, 1, device=dev)
@@ -47,7 +47,7 @@ def fused_fwd():
 
 
 samples = n * m * (bench.DC + bench.DF)
-out = {'workload': f'{n} x {bench.RES}^2 rays x ({bench.DC}+{bench.DF}) samples, fp32'}
+out = {'workload': f'{n} x {bench.RES}^2 rays x ({bench.DC}+{bench.DF}) samples, ' + args.mode}
 ms_f = timed(fused_fwd)
 torch.cuda.reset_peak_memory_stats()
 ms_fb = timed(fused_step)

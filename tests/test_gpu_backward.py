@@ -123,3 +123,15 @@ def test_backward_is_linear_in_the_upstream_gradient_and_respects_requires_grad(
                                        noise=(T(scene['jitter']), T(scene['u'])))
     assert not out[0].requires_grad
     torch.testing.assert_close(out[0], rgb.detach(), rtol=0, atol=0)
+
+
+@pytest.mark.parametrize('name', ['bwd_ffhq', 'bwd_white'])
+def test_reduced_precision_mode_gradients(pkg, name):
+    """decoder_precision='bf16' (the caller's >= 50 dB mode): bf16 decoder operands in the forward / point query, one
+    TF32 HMMA per product (round-to-nearest operands) in the backward.  No gate is stated for gradients in that mode;
+    the test pins the measured accuracy class: 1 % of the largest entry."""
+    scene, opts, gold, (A, B, C) = load_bwd_case(name)
+    _, grads = run_backward(pkg, scene, dict(opts, decoder_precision='bf16'), A, B, C)
+    errs = {k: rel_err(g.cpu().numpy(), gold[k]) for g, k in zip(grads, ('g_planes', 'g_w1', 'g_b1', 'g_w2', 'g_b2'))}
+    print(name, 'bf16 mode', {k: f'{v:.1e}' for k, v in errs.items()})
+    assert max(errs.values()) < 1e-2, errs
