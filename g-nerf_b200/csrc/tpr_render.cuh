@@ -313,6 +313,84 @@ __device__ __forceinline__ bool pair_rank_scatter(const float* z, const float* s
   return ok;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Sorting a ray's S = Dc + Df depths as a MERGE (R = 4 groups of the warp-specialised kernel, 96+96 samples: there the
+// rank count above -- even shared by two warps -- was 13 of the ray warps' 41 k cycles per group and the critical path):
+//   * the Dc coarse depths are ascending already (VR/renderer.py:169-192; checked, not assumed);
+//   * an importance depth is a monotone function of its uniform draw (the inverse CDF, VR/renderer.py:240-252), so the
+//     order of the Df importance depths among themselves is the order of their draws u -- known a whole pipeline step
+//     before the depths exist.  warp_rank_draws ranks the draws (the four ray warps that have no ray to resample do
+//     it while the other four resample); warp_merge_scatter then needs, per importance depth, one binary search in the
+//     coarse row (c = number of smaller coarse depths; rank = rank of its draw + c) and, per coarse depth, a prefix sum
+//     of the histogram of c (number of smaller importance depths).  ~200 instructions per warp instead of ~900.
+// Float rounding can break the monotonicity by an ulp at a bin edge, so the scattered row is verified to be ascending;
+// if it is not (or two draws are equal), the caller falls back to the rank count.
+// ---------------------------------------------------------------------------------------------------------------
+// rk[j] = number of draws smaller than u[j]; rk[0] = -1 if two draws are equal.  Df % 4 == 0, u 16-byte aligned.
+template <int ROWS>
+__device__ __forceinline__ void warp_rank_draws_rows(const float* u, int* rk, int Df, int lane) {
+  float ue[ROWS]; int cnt[ROWS];
+#pragma unroll
+  for (int e = 0; e < ROWS; ++e) { const int j = e * 32 + lane; ue[e] = j < Df ? u[j] : __int_as_float(0x7f800000); cnt[e] = 0; }
+#pragma unroll 2
+  for (int j = 0; j < Df; j += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(u + j);
+#pragma unroll
+    for (int e = 0; e < ROWS; ++e)
+      cnt[e] += (int)(v.x < ue[e]) + (int)(v.y < ue[e]) + (int)(v.z < ue[e]) + (int)(v.w < ue[e]);
+  }
+  int rsum = 0;
+#pragma unroll
+  for (int e = 0; e < ROWS; ++e) { const int j = e * 32 + lane; if (j < Df) { rk[j] = cnt[e]; rsum += cnt[e]; } }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(kFull, rsum, o);
+  __syncwarp();
+  if (lane == 0 && rsum != Df * (Df - 1) / 2) rk[0] = -1;
+}
+__device__ __forceinline__ void warp_rank_draws(const float* u, int* rk, int Df, int lane) {
+  const int rows = (Df + 31) >> 5;
+  if (rows <= 1) warp_rank_draws_rows<1>(u, rk, Df, lane);
+  else if (rows == 2) warp_rank_draws_rows<2>(u, rk, Df, lane);
+  else if (rows == 3) warp_rank_draws_rows<3>(u, rk, Df, lane);
+  else if (rows == 4) warp_rank_draws_rows<4>(u, rk, Df, lane);
+  else warp_rank_draws_rows<7>(u, rk, Df, lane);
+}
+// Scatter (depth, sigma, index) of the ray into sorted order: tmp[0..S) depths, tmp[S..2S) sigmas, om[0..S) indices (what
+// warp_sort_and_weights(pre_ranked) reads).  hist: Dc + 1 ints of scratch.  Returns whether the result is a sorted row.
+__device__ __forceinline__ bool warp_merge_scatter(const float* z, const float* sg, const int* rk, float* om, float* tmp,
+                                                   int* hist, int S, int Dc, int lane) {
+  const int Df = S - Dc;
+  float* zs = tmp; float* ss = tmp + S; int* is = reinterpret_cast<int*>(om);
+  bool ok = true;
+  for (int k = lane; k <= Dc; k += 32) { hist[k] = 0; if (k + 1 < Dc) ok &= z[k] <= z[k + 1]; }
+  __syncwarp();
+  for (int j = lane; j < Df; j += 32) {
+    const float f = z[Dc + j];
+    int lo = 0, hi = Dc;                           // c = number of coarse depths < f
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (z[mid] < f) lo = mid + 1; else hi = mid; }
+    atomicAdd(hist + lo, 1);
+    const int r = rk[j] + lo;
+    zs[r] = f; ss[r] = sg[Dc + j]; is[r] = Dc + j;
+  }
+  __syncwarp();
+  {   // coarse depth k goes to k + (number of importance depths with c <= k)
+    const int per = (Dc + 31) >> 5, k0 = lane * per;
+    int loc = 0;
+    for (int e = 0; e < per; ++e) if (k0 + e < Dc) loc += hist[k0 + e];
+    int run = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, run, o); if (lane >= o) run += t; }
+    run -= loc;
+    for (int e = 0; e < per; ++e) {
+      const int k = k0 + e;
+      if (k < Dc) { run += hist[k]; const int r = k + run; zs[r] = z[k]; ss[r] = sg[k]; is[r] = k; }
+    }
+  }
+  __syncwarp();
+  for (int p = lane; p + 1 < S; p += 32) ok &= zs[p] <= zs[p + 1];
+  return __all_sync(kFull, ok);
+}
+
 // one warp: coarse weights -> smoothed pdf -> CDF -> Df inverse-CDF draws (VR/renderer.py:194-253).
 // z, sg: the ray's coarse depths / densities (S-strided row); w, pw, cdf: scratch rows; fine: output row;
 // urow: the ray's Df uniform draws (global or shared memory).

@@ -49,7 +49,7 @@ struct Barriers {
 };
 
 // per-group shared-memory context
-struct Ctx { float* dep; float* sig; float* u; float* ray; };
+struct Ctx { float* dep; float* sig; float* u; float* ray; int* rk; };
 
 struct Geom { long long ray0; int n, rstride, nr; };
 // Which rays form group `grp`.  Column mode (rays are a col_w-wide image, x fastest, VR/ray_sampler.py:44):
@@ -135,11 +135,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
   const int R = a.R, Dc = a.Dc, Df = a.Df, S = Dc + Df;
   const int dpt_shift = R == 8 ? 4 : 5, dpt = 1 << dpt_shift;
   // contexts: dep [R*S], sig [R*S], u [R*Df], ray [R*8]
-  const int ctx_floats = 2 * R * S + R * Df + R * 8;
+  const int ctx_floats = 2 * R * S + R * Df + R * 8 + (R == 4 ? R * Df : 0);      // (+ rk [R*Df]: ranks of the draws, R = 4)
   float* scratch = fl + kCtx * ctx_floats;            // ray-warp scratch: wa, wb, wc [R*S] each, rayw [R]
   auto ctx_of = [&](int gi) {
     float* p = fl + (gi & (kCtx - 1)) * ctx_floats;
-    Ctx c; c.dep = p; c.sig = p + R * S; c.u = c.sig + R * S; c.ray = c.u + R * Df;
+    Ctx c; c.dep = p; c.sig = p + R * S; c.u = c.sig + R * S; c.ray = c.u + R * Df; c.rk = reinterpret_cast<int*>(c.ray + R * 8);
     return c;
   };
   __shared__ Barriers bars;
@@ -329,6 +329,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
     // nothing to overlap them inside setup, so they are fetched with cp.async into a staging area one step ahead;
     // each thread later converts exactly the elements it copied itself (no barrier needed, only wait_group).
     float* stg_jit = rayw + R; float* stg_u = stg_jit + R * Dc; float* stg_ray = stg_u + R * Df;
+    int* hist = reinterpret_cast<int*>(stg_ray + R * 8 + 8);      // [R][Dc + 4] (R = 4: warp_merge_scatter)
+    // R = 4 (more than 64 samples per pass): a ray's samples are merged instead of rank-counted (tpr_render.cuh)
+    const bool merge = R == 4 && nf > 0 && (Df & 3) == 0 && a.variant != 3;
     auto prefetch = [&](int gi) {
       const Geom gg = group_geom(a, blockIdx.x + (unsigned)gi * gridDim.x, R);
       if (rtid < gg.nr * 6) {
@@ -375,6 +378,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
       for (int r = rw; r < gg.nr; r += kRayWarps)
         warp_resample_ray(a, cx.dep + r * S, cx.sig + r * S, wa + r * S, wb + r * S, wc + r * S, cx.dep + r * S + Dc,
                           gg.ray0 + (long long)r * gg.rstride, lane, cx.u + r * Df);
+      // R = 4: warps 4-7 have no ray to resample; they rank the group's uniform draws for the merge of the next step
+      if (merge && rw >= 4 && rw - 4 < gg.nr) warp_rank_draws(cx.u + (rw - 4) * Df, cx.rk + (rw - 4) * Df, Df, lane);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.fine_ready[gi & 3]);
       PROF_ADD(14, pl);
@@ -390,12 +395,21 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
       // ---- sort + final march: omega per sample (scattered to original order), depth, weight sum
       // R = 4: two warps per ray share the rank count (pair_rank_scatter); warp rw < 4 then runs the march alone
       const bool pairs = R == 4 && nf > 0 && (Dc & 31) == 0 && (Df & 7) == 0;
-      for (int r = pairs ? (rw & 3) : rw; r < gg.nr; r += kRayWarps) {
+      for (int r = (pairs || merge) ? (rw & 3) : rw; r < gg.nr; r += kRayWarps) {
         float wsum, dnum;
         bool pre = false;
-        if (pairs) {
+        const bool mg = merge && cx.rk[r * Df] >= 0;   // (both warps of the ray read the same verdict on the draws)
+        if (mg) {
+          if (rw >= 4) break;
+          pre = warp_merge_scatter(cx.dep + r * S, cx.sig + r * S, cx.rk + r * Df, wa + r * S, wb + r * 2 * S, hist + r * (Dc + 4),
+                                   S, Dc, lane);
+          PROF_ADD(18, pl);
+        } else if (!pairs && merge && rw >= 4) {
+          break;
+        } else if (pairs) {
           pre = pair_rank_scatter<ER>(cx.dep + r * S, cx.sig + r * S, wa + r * S, wb + r * 2 * S, S, Dc, lane, rw >> 2, 7 + r);
           if (rw >= 4) break;
+          PROF_ADD(18, pl);                            // (profiling build: the rank count's share of sort+march)
         }
         warp_sort_and_weights<E, true, ER>(cx.dep + r * S, cx.sig + r * S, wa + r * S, nullptr, S, lane, wsum, dnum, smn, smx,
                                        wb + r * 2 * S, pre);     // wb and wc are contiguous: 2*S floats per ray
@@ -521,7 +535,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
 template <int MODE>
 static size_t smem_bytes(int R, int S, int Df) {
   return 1024 + sizeof(Tiles<MODE>) + sizeof(Tap2) * kGatherWarps * 24 +
-         sizeof(float) * ((size_t)kCtx * (2 * R * S + R * Df + R * 8) + (size_t)3 * R * S + R + (size_t)R * S + R * 8 + 8);
+         sizeof(float) * ((size_t)kCtx * (2 * R * S + R * Df + R * 8 + (R == 4 ? R * Df : 0)) + (size_t)3 * R * S + R +
+                          (size_t)R * S + R * 8 + 8 + (R == 4 ? R * (S - Df + 4) : 0));
 }
 
 typedef void (*Kernel)(const RenderArgs);
