@@ -271,13 +271,13 @@ def main():
         if world == 1:
             renderer.forward_host(planes_pin, decoder, o_pin, d_pin, opts, out=out_pin)
             return
-        # N > 1: the depth clamp needs the all-reduced range before depth can leave the device
-        p = planes_pin.to(dev, non_blocking=True)
-        o = o_pin.to(dev, non_blocking=True)
-        d = d_pin.to(dev, non_blocking=True)
-        outs = pkg.parallel.render_sharded(renderer, p, decoder, o, d, opts, gather=False)
-        for dst, src in zip(out_pin, outs):
-            dst.copy_(src, non_blocking=True)
+        # N > 1: the same per-image pipeline; the depth clamp needs the all-reduced range, so depth leaves the device last
+        renderer.forward_host(planes_pin, decoder, o_pin, d_pin, opts, out=out_pin, defer_depth=True)
+        rng = renderer.last_depth_range
+        lo, hi = rng[0:1].clone(), rng[1:2].clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        renderer.finish_host_depth(torch.cat([lo, hi]))
 
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
@@ -350,7 +350,7 @@ def main():
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': 5 * args.steps,                    # pack_planes, pack_decoder, range_init, render_ws, finish
             'e2e_api': 'ImportanceRenderer.forward_host (tpr_render_host: per-image H2D / repack+render / D2H pipeline)'
-            if world == 1 else 'pinned .to(device) + render_sharded + pinned copy back',
+            if world == 1 else 'ImportanceRenderer.forward_host(defer_depth) + 2-float all-reduce + finish_host_depth',
             'clocks': clocks,
         }
         if train is not None:

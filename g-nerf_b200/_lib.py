@@ -55,6 +55,7 @@ _SIGNATURES = {
     'tpr_render_host_workspace_bytes': (c_size_t, [c_int64, c_int32, c_int32, c_int64]),
     'tpr_render_host': (ctypes.c_int, [_P, c_int64, c_int32, c_int32, _P, _P, _P, c_int64, _P, _P,
                                        ctypes.POINTER(TprOptions), _P, _P, _P, _P, _P, c_size_t, _P]),
+    'tpr_render_host_depth': (ctypes.c_int, [_P, c_size_t, c_int64, c_int32, c_int32, c_int64, _P, _P, _P]),
     'tpr_ray_march': (ctypes.c_int, [_P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, _P, c_int32, _P]),
     'tpr_sample_importance': (ctypes.c_int, [_P, _P, _P, c_int64, c_int32, c_int32, _P, _P, _P]),
     'tpr_sample_pdf': (ctypes.c_int, [_P, c_int32, _P, _P, c_int64, c_int32, c_int32, _P, _P, _P]),

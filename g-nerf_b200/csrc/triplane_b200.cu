@@ -1002,9 +1002,9 @@ int tpr_render_host(const float* planes_host, int64_t n_img, int32_t height, int
                     const float* origins_host, const float* dirs_host, int64_t n_rays, const float* jitter, const float* u,
                     const TprOptions* opt, float* rgb_host, float* depth_host, float* weight_sum_host, float* depth_range_io,
                     void* workspace, size_t workspace_bytes, void* stream) {
-  if (!planes_host || !decoder_packed || !origins_host || !dirs_host || !jitter || !opt || !rgb_host || !depth_host ||
-      !weight_sum_host || !workspace)
+  if (!planes_host || !decoder_packed || !origins_host || !dirs_host || !jitter || !opt || !rgb_host || !weight_sum_host || !workspace)
     return fail(TPR_E_NULL, "tpr_render_host: NULL pointer");
+  if (!depth_host && !depth_range_io) return fail(TPR_E_NULL, "tpr_render_host: deferred depth (depth_host = NULL) needs depth_range_io");
   if (n_img <= 0 || n_rays <= 0 || height <= 0 || width <= 0 || (int64_t)height * width > (1 << 24))
     return fail(TPR_E_SHAPE, "tpr_render_host: bad shape");
   if (opt->depth_resolution_importance > 0 && !u) return fail(TPR_E_NULL, "tpr_render_host: NULL u");
@@ -1061,13 +1061,33 @@ int tpr_render_host(const float* planes_host, int64_t n_img, int32_t height, int
   }
   DeviceInfo di = device_info();
   const long long total = (long long)n_img * n_rays;
+  // depth_host = NULL: the caller shards rays over GPUs and owes the clamp an all-reduced range -- only decode this GPU's
+  // range; tpr_render_host_depth finishes the job
   finish_kernel<<<grid_for(total, 256, di.sms, 4), 256, 0, st>>>(reinterpret_cast<unsigned*>(ws + w.scratch), depth_range_io,
-                                                                 d_depth, total, 1, 0);
+                                                                 d_depth, total, depth_host ? 1 : 0, 0);
   TPR_CHECK_LAUNCH("finish_kernel");
-  TPR_CUDA(cudaMemcpyAsync(depth_host, d_depth, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(depth)");
+  if (depth_host)
+    TPR_CUDA(cudaMemcpyAsync(depth_host, d_depth, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(depth)");
   // the caller's stream completes only when every output has landed
   TPR_CUDA(cudaEventRecord(ev[3], hp->out), "cudaEventRecord");
   TPR_CUDA(cudaStreamWaitEvent(st, ev[3], 0), "cudaStreamWaitEvent");
+  return 0;
+}
+
+int tpr_render_host_depth(void* workspace, size_t workspace_bytes, int64_t n_img, int32_t height, int32_t width, int64_t n_rays,
+                          const float* depth_range, float* depth_host, void* stream) {
+  if (!workspace || !depth_range || !depth_host) return fail(TPR_E_NULL, "tpr_render_host_depth: NULL pointer");
+  if (n_img <= 0 || n_rays <= 0 || height <= 0 || width <= 0) return fail(TPR_E_SHAPE, "tpr_render_host_depth: bad shape");
+  const HostWs w = host_ws_layout(n_img, height, width, n_rays);
+  if (workspace_bytes < w.total) return fail(TPR_E_SCRATCH, "tpr_render_host_depth: workspace too small");
+  DeviceInfo di = device_info();
+  if (!di.ok) return fail(TPR_E_DEVICE, "tpr_render_host_depth: no CUDA device");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* d_depth = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + w.depth);
+  const long long total = (long long)n_img * n_rays;
+  clamp_depth_kernel<<<grid_for(total, 256, di.sms, 4), 256, 0, st>>>(d_depth, total, depth_range);
+  TPR_CHECK_LAUNCH("clamp_depth_kernel");
+  TPR_CUDA(cudaMemcpyAsync(depth_host, d_depth, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(depth)");
   return 0;
 }
 

@@ -295,12 +295,15 @@ class ImportanceRenderer(torch.nn.Module):
         return rgb, depth, wsum, aux
 
     # ------------------------------------------------------------------ forward with host buffers
-    def forward_host(self, planes, decoder, ray_origins, ray_directions, rendering_options, *, noise=None, out=None):
+    def forward_host(self, planes, decoder, ray_origins, ray_directions, rendering_options, *, noise=None, out=None,
+                     defer_depth=False):
         """``forward`` for a caller whose tensors live in (pinned) HOST memory: ``planes`` [N,3,32,H,W],
         ``ray_origins`` / ``ray_directions`` [N,M,3] are CPU tensors and the three outputs are returned as pinned CPU
         tensors (or written into ``out``).  The library pipelines H2D copy, repack + render and D2H copy image by
         image (tpr_render_host), so the call costs about max(PCIe time, render time) instead of their sum.  The
-        result is complete once the current CUDA stream has been synchronised.  Scalar ray limits only."""
+        result is complete once the current CUDA stream has been synchronised.  Scalar ray limits only.
+        ``defer_depth=True`` (rays sharded over GPUs): depth is left unclamped on the device and ``last_depth_range`` holds
+        this GPU's range; all-reduce it (MIN, MAX) and call ``finish_host_depth(range)`` to clamp and fetch ``out[1]``."""
         opts = rendering_options
         for t, name in ((planes, 'planes'), (ray_origins, 'ray_origins'), (ray_directions, 'ray_directions')):
             if not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
@@ -346,10 +349,26 @@ class ImportanceRenderer(torch.nn.Module):
                 ws = self._host_ws = torch.empty(nws, device=dev, dtype=torch.uint8)
             rng = torch.empty(2, device=dev, dtype=torch.float32)
             _lib.check(L.tpr_render_host(_ptr(planes), n, h, w, _ptr(dec), _ptr(ray_origins), _ptr(ray_directions), m,
-                                         _ptr(jitter), _ptr(u), ctypes.byref(o), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
-                                         _ptr(rng), _ptr(ws), ws.numel(), _stream()), 'tpr_render_host')
+                                         _ptr(jitter), _ptr(u), ctypes.byref(o), _ptr(out[0]), None if defer_depth else _ptr(out[1]),
+                                         _ptr(out[2]), _ptr(rng), _ptr(ws), ws.numel(), _stream()), 'tpr_render_host')
             self._host_keepalive = (dec, jitter, u, planes, ray_origins, ray_directions)    # until the next call
         self.last_depth_range = rng
+        self._host_pending = (n, h, w, m, out) if defer_depth else None
+        return out
+
+    def finish_host_depth(self, depth_range):
+        """Second half of ``forward_host(defer_depth=True)``: clamp the depth left on the device against ``depth_range``
+        (a device tensor [2]: the all-reduced (min, max) of every rank's ``last_depth_range``) and copy it into ``out[1]``."""
+        if getattr(self, '_host_pending', None) is None:
+            raise RuntimeError('finish_host_depth: no forward_host(defer_depth=True) call is pending')
+        n, h, w, m, out = self._host_pending
+        rr = _require_cuda_f32(depth_range, 'depth_range').reshape(2)
+        ws = self._host_ws
+        with torch.cuda.device(ws.device):
+            _lib.check(_lib.lib().tpr_render_host_depth(_ptr(ws), ws.numel(), n, h, w, m, _ptr(rr), _ptr(out[1]), _stream()),
+                       'tpr_render_host_depth')
+        self._host_pending = None
+        self._host_keepalive = self._host_keepalive + (rr,)
         return out
 
     # ------------------------------------------------------------------ run_model (VR/renderer.py:142-148)

@@ -197,7 +197,8 @@ int tpr_render_peers(const float* planes_packed, int64_t n_img, int32_t height, 
  * device, the only state the library keeps) and `stream`: H2D of image i+1, repack + render of image i and D2H of
  * image i-1 overlap.  `workspace` is a DEVICE buffer of tpr_render_host_workspace_bytes() bytes.
  * Asynchronous like every other entry: the outputs are complete when `stream` has drained.
- * depth_range_io: DEVICE [2], receives the global depth range (may be NULL).  opt->cameras_per_plane_set must be 0 or 1
+ * depth_range_io: DEVICE [2], receives the global depth range (may be NULL unless depth_host is NULL, see
+ * tpr_render_host_depth).  opt->cameras_per_plane_set must be 0 or 1
  * (every image brings its own planes across PCIe). */
 size_t tpr_render_host_workspace_bytes(int64_t n_img, int32_t height, int32_t width, int64_t n_rays);
 int tpr_render_host(const float* planes_host, int64_t n_img, int32_t height, int32_t width,
@@ -206,6 +207,13 @@ int tpr_render_host(const float* planes_host, int64_t n_img, int32_t height, int
                     const float* jitter, const float* u, const TprOptions* opt,
                     float* rgb_host, float* depth_host, float* weight_sum_host, float* depth_range_io,
                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Rays sharded over several GPUs: the clamp of VR/ray_marcher.py:50 needs the range of ALL ranks'
+ * depths.  Call tpr_render_host with depth_host = NULL (depth stays, unclamped, in the workspace; depth_range_io receives
+ * this GPU's range), all-reduce the two floats (MIN, MAX), then this: clamp with the global range and copy depth
+ * [N,M] to the host.  Same workspace and shape as the tpr_render_host call before it. */
+int tpr_render_host_depth(void* workspace, size_t workspace_bytes, int64_t n_img, int32_t height, int32_t width,
+                          int64_t n_rays, const float* depth_range /*[2] device*/, float* depth_host, void* stream);
 
 /* ---- a9: MipRayMarcher2.forward (VR/ray_marcher.py:25-57), stand-alone ------------------ */
 /* colors [R,S,C], densities [R,S], depths [R,S] in the given (not re-sorted) order ->

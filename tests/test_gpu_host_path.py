@@ -50,3 +50,30 @@ def test_render_host_argument_errors(pkg):
     assert L.tpr_render_host_workspace_bytes(2, 64, 64, 16) > 2 * 2 * 3 * 32 * 64 * 64 * 4
     rc = L.tpr_render_host(None, 1, 64, 64, None, None, None, 16, None, None, None, None, None, None, None, None, 0, None)
     assert rc == -1 and b'NULL' in L.tpr_last_error()
+
+
+def test_forward_host_deferred_depth(pkg):
+    """Rays sharded over GPUs: depth stays on the device until the caller supplies the all-reduced range.  With this
+    GPU's own range the result must be forward_host's; with a narrower range the clamp must follow it."""
+    scene = O.synthetic_scene(41, 3, 12, 64, 48, 48, 0.5)
+    opts = dict(O.FFHQ_OPTIONS, depth_resolution=48, depth_resolution_importance=48)
+    R, dec = pkg.ImportanceRenderer(), make_decoder(pkg, scene['dec'])
+    noise = (T(scene['jitter']), T(scene['u']))
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    args = (pin(scene['planes']), dec, pin(scene['origins']), pin(scene['dirs']), opts)
+    res = R.forward_host(*args, noise=noise)
+    torch.cuda.current_stream().synchronize()            # the outputs land asynchronously
+    want = tuple(t.clone() for t in res)
+    got = R.forward_host(*args, noise=noise, defer_depth=True)
+    rng = R.last_depth_range.clone()
+    R.finish_host_depth(rng)
+    torch.cuda.current_stream().synchronize()
+    for g, w in zip(got, want):
+        torch.testing.assert_close(g, w, rtol=0, atol=0)
+    got = R.forward_host(*args, noise=noise, defer_depth=True)
+    narrow = torch.tensor([2.6, 2.9], device=rng.device)
+    R.finish_host_depth(narrow)
+    torch.cuda.current_stream().synchronize()
+    torch.testing.assert_close(got[1], want[1].clamp(2.6, 2.9), rtol=0, atol=0)
+    with pytest.raises(RuntimeError):
+        R.finish_host_depth(narrow)                      # nothing pending any more
