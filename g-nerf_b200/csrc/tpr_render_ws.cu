@@ -125,7 +125,10 @@ __device__ __forceinline__ void gather_tile(const RenderArgs& a, float* a1_hi, f
 // ---------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
-template <int MODE, int E, int ER, bool PROF>
+// TRAIN: the composite also writes every sample's colours (and the sort every sample's sigma) to HBM for the backward
+// (tpr_render_train).  A template parameter, not a run-time branch: the extra address arithmetic in the composite loop
+// costs the inference kernel 3 % at its 64-register budget when it is merely predicated off.
+template <int MODE, int E, int ER, bool PROF, bool TRAIN = false>
 __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -413,6 +416,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
         }
         warp_sort_and_weights<E, true, ER>(cx.dep + r * S, cx.sig + r * S, wa + r * S, nullptr, S, lane, wsum, dnum, smn, smx,
                                        wb + r * 2 * S, pre);     // wb and wc are contiguous: 2*S floats per ray
+        if (TRAIN && a.sample_sigma != nullptr) {    // training: the backward reads sigma of every sample instead of recomputing it
+          float* dst = a.sample_sigma + (gg.ray0 + (long long)r * gg.rstride) * S;
+          for (int p = lane; p < S; p += 32) dst[p] = cx.sig[r * S + p];
+        }
         if (lane == 0) {
           const long long g = gg.ray0 + (long long)r * gg.rstride;
           rayw[r] = wsum;
@@ -445,9 +452,15 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
         // rows outside the group (om = 0) still hold finite values: the operand tiles start zeroed and only ever
         // receive finite features, so no select is needed to keep NaNs out of the sum
         const uint64_t om2 = pack2(om, om);
+        // training: this lane's sixteen colours of the sample also go to HBM (64 contiguous bytes), in the forward's
+        // sample order (ray-major, coarse then importance) -- what tpr_render_backward reads instead of re-running the decoder
+        ulonglong2* cdst = (TRAIN && a.sample_colours != nullptr && valid)
+            ? reinterpret_cast<ulonglong2*>(a.sample_colours + ((gg.ray0 + (long long)r * gg.rstride) * S + (fine ? Dc : 0) + di) * 32 + 16 * hc)
+            : nullptr;
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           const ulonglong2 bz = *reinterpret_cast<const ulonglong2*>(tl.bias2 + 16 * hc + 4 * c4);
+          ulonglong2 cpair;
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
             const int c = 4 * c4 + 2 * h2;
@@ -459,7 +472,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
             unpack2(den, d0, d1);
             const uint64_t col = fma2(pack2(rcp_fast(d0), rcp_fast(d1)), kScale2, kShift2);
             acc2[c >> 1] = fma2(om2, col, acc2[c >> 1]);
+            if (h2 == 0) cpair.x = col; else cpair.y = col;
           }
+          if (TRAIN && cdst != nullptr) cdst[c4] = cpair;
         }
       }
       float acc[16];
@@ -541,7 +556,8 @@ static size_t smem_bytes(int R, int S, int Df) {
 
 typedef void (*Kernel)(const RenderArgs);
 template <int MODE>
-static Kernel pick_kernel(int S, bool prof) {
+static Kernel pick_kernel(int S, bool prof, bool train) {
+  if (train && !prof && S > 64 && S <= 96) return render_ws_kernel<MODE, 4, 3, false, true>;
   if (prof && S > 64 && S <= 96) return render_ws_kernel<MODE, 4, 3, true>;      // TPR_PHASE_TIMING=1 (profiles/phase_timing.py)
   if (prof && S > 128 && S <= 192) return render_ws_kernel<MODE, 8, 6, true>;                 // (192 samples: TPR_PT_DEPTH=96)
   return S <= 64 ? render_ws_kernel<MODE, 2, 2, false> : S <= 96 ? render_ws_kernel<MODE, 4, 3, false>
@@ -563,6 +579,9 @@ int ws_rays_per_group(int Dc, int Df, int bf16) {
   return 0;
 }
 
+// Sample counts for which a TRAIN instantiation exists (the reference's training depths, 48+48: train.py:312-313).
+bool ws_keeps_samples(int Dc, int Df) { const int S = Dc + Df; return S > 64 && S <= 96 && ws_rays_per_group(Dc, Df, 0) == 8; }
+
 // Launch; returns cudaError_t (0 = ok), or -1 if the configuration does not fit (the caller falls back).
 int launch_render_ws(RenderArgs a, int bf16, int sms, int smem_optin, long long n_img, long long n_rays, cudaStream_t st) {
   const int S = a.Dc + a.Df;
@@ -572,7 +591,9 @@ int launch_render_ws(RenderArgs a, int bf16, int sms, int smem_optin, long long 
   a.tiles_per_img = (n_rays + a.R - 1) / a.R;
   a.n_tiles = a.tiles_per_img * n_img;
   if (a.n_tiles >= (1ll << 31) || n_rays >= (1ll << 31)) return -1;      // group_geom works in 32 bits
-  ws::Kernel k = bf16 ? ws::pick_kernel<1>(S, a.dbg != nullptr) : ws::pick_kernel<0>(S, a.dbg != nullptr);
+  const bool train = a.sample_colours != nullptr && a.sample_sigma != nullptr;
+  if (train && !ws_keeps_samples(a.Dc, a.Df)) return -1;
+  ws::Kernel k = bf16 ? ws::pick_kernel<1>(S, a.dbg != nullptr, train) : ws::pick_kernel<0>(S, a.dbg != nullptr, train);
   const size_t smem = bf16 ? ws::smem_bytes<1>(a.R, S, a.Df) : ws::smem_bytes<0>(a.R, S, a.Df);
   cudaFuncAttributes fa;
   cudaError_t e = cudaFuncGetAttributes(&fa, k);

@@ -22,6 +22,7 @@ int tc_rays_per_group(int Dc, int Df);
 int launch_render_tc(RenderArgs a, int bf16, int sms, int smem_optin, long long n_img, long long n_rays, cudaStream_t st);
 // warp-specialised tensor-core render path (tpr_render_ws.cu)
 int ws_rays_per_group(int Dc, int Df, int bf16);
+bool ws_keeps_samples(int Dc, int Df);
 int launch_render_ws(RenderArgs a, int bf16, int sms, int smem_optin, long long n_img, long long n_rays, cudaStream_t st);
 // tpr_run_model_ws.cu
 int launch_run_model_ws(const float* planes, long long n_img, int H, int W, const float* dec, const float* xyz, long long n_pts,
@@ -755,7 +756,8 @@ static int render_impl(const float* planes_packed, int64_t n_img, int32_t height
                        const float* ray_start_per_ray, const float* ray_end_per_ray, const TprOptions* opt, float* rgb,
                        float* depth, float* weight_sum, float* fine_depths, int32_t* fine_inds, float* depth_range_io,
                        int32_t clamp_depth, void* scratch, size_t scratch_bytes, void* stream, int phases,
-                       const TprPeerSinks* peers = nullptr) {
+                       const TprPeerSinks* peers = nullptr, float* sample_colours = nullptr, float* sample_sigma = nullptr,
+                       int32_t* samples_saved = nullptr) {
   if (!planes_packed || !decoder_packed || !origins || !dirs || !jitter || !opt || !rgb || !depth || !weight_sum || !scratch)
     return fail(TPR_E_NULL, "tpr_render: NULL pointer");
   if ((ray_start_per_ray == nullptr) != (ray_end_per_ray == nullptr))
@@ -825,10 +827,14 @@ static int render_impl(const float* planes_packed, int64_t n_img, int32_t height
   bool done = false;
   if (opt->flags != TPR_MLP_FFMA && impl != 1 && !env_int("TPR_FORCE_FFMA", 0) &&
       ws_rays_per_group(Dc, Df, opt->flags == TPR_MLP_BF16) > 0) {
+    const bool keep = sample_colours && sample_sigma && ws_keeps_samples(Dc, Df) && !a.dbg;
+    if (keep) { a.sample_colours = sample_colours; a.sample_sigma = sample_sigma; }      // (only this kernel can keep them)
     int rc = launch_render_ws(a, opt->flags == TPR_MLP_BF16, di.sms, di.smem_optin, n_img, n_rays, st);
     if (rc > 0) return cuda_fail((cudaError_t)rc, "render_ws_kernel");
     done = rc == 0;                       // < 0: does not fit shared memory, fall through
+    a.sample_colours = nullptr; a.sample_sigma = nullptr;
   }
+  if (samples_saved) *samples_saved = (done && sample_colours && sample_sigma && ws_keeps_samples(Dc, Df) && !a.dbg) ? 1 : 0;
   const bool kernel_stores_to_peers = done;     // only the warp-specialised kernel has the peer stores in its epilogue
   if (done) {
   } else if (use_tc) {
@@ -883,6 +889,18 @@ int tpr_render(const float* planes_packed, int64_t n_img, int32_t height, int32_
   return render_impl(planes_packed, n_img, height, width, decoder_packed, origins, dirs, n_rays, jitter, u, ray_start_per_ray,
                      ray_end_per_ray, opt, rgb, depth, weight_sum, fine_depths, fine_inds, depth_range_io, clamp_depth, scratch,
                      scratch_bytes, stream, kRangeInit | kFinish);
+}
+
+int tpr_render_train(const float* planes_packed, int64_t n_img, int32_t height, int32_t width, const float* decoder_packed,
+                     const float* origins, const float* dirs, int64_t n_rays, const float* jitter, const float* u,
+                     const float* ray_start_per_ray, const float* ray_end_per_ray, const TprOptions* opt, float* rgb,
+                     float* depth, float* weight_sum, float* fine_depths, float* depth_range_io, float* sample_colours,
+                     float* sample_sigma, int32_t* samples_saved, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!sample_colours || !sample_sigma || !samples_saved) return fail(TPR_E_NULL, "tpr_render_train: NULL pointer");
+  if (opt && opt->depth_resolution_importance > 0 && !fine_depths) return fail(TPR_E_NULL, "tpr_render_train: NULL fine_depths");
+  return render_impl(planes_packed, n_img, height, width, decoder_packed, origins, dirs, n_rays, jitter, u, ray_start_per_ray,
+                     ray_end_per_ray, opt, rgb, depth, weight_sum, fine_depths, nullptr, depth_range_io, 1, scratch, scratch_bytes,
+                     stream, kRangeInit | kFinish, nullptr, sample_colours, sample_sigma, samples_saved);
 }
 
 int tpr_render_peers(const float* planes_packed, int64_t n_img, int32_t height, int32_t width, const float* decoder_packed,
@@ -1183,8 +1201,10 @@ int tpr_march_backward(const float* depths_coarse, const float* depths_fine, int
 int tpr_render_backward(const float* planes_packed, int64_t n_img, int32_t height, int32_t width, const float* decoder_packed,
                         const float* origins, const float* dirs, int64_t n_rays, const float* depths_coarse,
                         const float* depths_fine, const float* depth_range, const TprOptions* opt, const float* g_rgb,
-                        const float* g_depth, const float* g_weight_sum, float* g_planes_packed, float* g_decoder_packed,
-                        void* scratch, size_t scratch_bytes, void* stream) {
+                        const float* g_depth, const float* g_weight_sum, const float* sample_colours, const float* sample_sigma,
+                        float* g_planes_packed, float* g_decoder_packed, void* scratch, size_t scratch_bytes, void* stream) {
+  if ((sample_colours == nullptr) != (sample_sigma == nullptr))
+    return fail(TPR_E_NULL, "tpr_render_backward: sample_colours and sample_sigma come together");
   if (!planes_packed || !decoder_packed || !origins || !dirs || !depths_coarse || !depth_range || !opt || !g_rgb || !g_depth ||
       !g_weight_sum || !g_planes_packed || !g_decoder_packed || !scratch)
     return fail(TPR_E_NULL, "tpr_render_backward: NULL pointer");
@@ -1210,17 +1230,22 @@ int tpr_render_backward(const float* planes_packed, int64_t n_img, int32_t heigh
   float* omega = (float*)p;
   int rc = launch_bwd_points(origins, dirs, depths_coarse, depths_fine, Dc, Df, rays, pts, di.sms, st);
   if (rc != 0) return cuda_fail((cudaError_t)rc, "points_kernel");
-  // colours and densities of every sample: the forward's point query (VR/renderer.py:142-148)
-  rc = tpr_run_model(planes_packed, n_img, height, width, decoder_packed, pts, (int64_t)n_rays * S, opt->box_warp, colours, sigma,
-                     opt->flags, stream);
-  if (rc != 0) return rc;
-  rc = launch_bwd_march(depths_coarse, depths_fine, Dc, Df, sigma, colours, g_rgb, g_depth, g_weight_sum, depth_range,
+  const float* col_in = sample_colours; const float* sig_in = sample_sigma;
+  if (!col_in) {
+    // not kept by the forward (tpr_render_train): colours and densities of every sample through the forward's point query
+    // (VR/renderer.py:142-148)
+    rc = tpr_run_model(planes_packed, n_img, height, width, decoder_packed, pts, (int64_t)n_rays * S, opt->box_warp, colours, sigma,
+                       opt->flags, stream);
+    if (rc != 0) return rc;
+    col_in = colours; sig_in = sigma;
+  }
+  rc = launch_bwd_march(depths_coarse, depths_fine, Dc, Df, sig_in, col_in, g_rgb, g_depth, g_weight_sum, depth_range,
                         opt->white_back, rays, gsig, omega, di.sms, st);
   if (rc != 0) return cuda_fail((cudaError_t)rc, "march_backward_kernel");
   cudaError_t e = cudaMemsetAsync(g_planes_packed, 0, (size_t)n_img * 3 * height * width * kC * sizeof(float), st);
   if (e == cudaSuccess) e = cudaMemsetAsync(g_decoder_packed, 0, kDecFloats * sizeof(float), st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
-  rc = launch_bwd_decode(planes_packed, height, width, decoder_packed, pts, colours, gsig, omega, g_rgb, (long long)T,
+  rc = launch_bwd_decode(planes_packed, height, width, decoder_packed, pts, col_in, gsig, omega, g_rgb, (long long)T,
                          (long long)n_rays * S, S, (float)(2.0 / opt->box_warp), g_planes_packed, g_decoder_packed,
                          opt->flags == TPR_MLP_BF16, di.sms, st);
   if (rc != 0) return cuda_fail((cudaError_t)rc, "decode_backward_kernel");

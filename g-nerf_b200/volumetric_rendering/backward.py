@@ -5,7 +5,8 @@ FFHQ training shape; training back-propagates through th
 training/training_loop.py:335,377.  Here the forward is the fused kernel (nothing per-sample is saved) and the backward is
 ``tpr_render_backward`` (csrc/tpr_backward.cu): it re-evaluates colours / densities at the forward's sample depths and
 runs the march, the decoder and the bilinear gather backwards.  Saved between the two: the packed planes, the packed
-decoder, the rays, the S sample depths per ray and the depth range -- 4 * (Dc + Df) bytes per ray.
+decoder, the rays, the S sample depths per ray, the depth range and -- written by the forward kernel's composite on its
+way -- the 32 colours and sigma of every sample (132 B per sample; eager autograd keeps ~800 B per sample).
 
 The graph is the reference's: importance depths are constants (VR/renderer.py:198,210: no_grad + detach), so is the
 jitter; ray origins / directions are not differentiated (they raise if they require grad).
@@ -30,13 +31,15 @@ class _Render(torch.autograd.Function):
         ctx.shape = tuple(origins.shape[:2])
         fine = aux['fine'] if aux['fine'] is not None else torch.empty(0, device=rgb.device)
         ctx.has_fine = aux['fine'] is not None
+        ctx.has_saved = aux['saved'] is not None
+        s_col, s_sig = aux['saved'] if ctx.has_saved else (torch.empty(0, device=rgb.device),) * 2
         ctx.save_for_backward(aux['packed'].data, aux['dec'], origins.contiguous(), dirs.contiguous(), aux['coarse'], fine,
-                              aux['range'])
+                              aux['range'], s_col, s_sig)
         return rgb, depth, wsum
 
     @staticmethod
     def backward(ctx, g_rgb, g_depth, g_wsum):
-        packed, dec, origins, dirs, coarse, fine, rng = ctx.saved_tensors
+        packed, dec, origins, dirs, coarse, fine, rng, s_col, s_sig = ctx.saved_tensors
         n, m = ctx.shape
         pp, o = ctx.packed, ctx.opts
         dev = packed.device
@@ -55,7 +58,8 @@ class _Render(torch.autograd.Function):
             o2.plane_sets, o2.depth_clamp_group = 0, 0
             _lib.check(L.tpr_render_backward(p(packed), n, pp.height, pp.width, p(dec), p(origins), p(dirs), m, p(coarse),
                                              p(fine) if ctx.has_fine else None, p(rng), ctypes.byref(o2), p(g_rgb), p(g_depth),
-                                             p(g_wsum), p(g_planes), p(g_dec), p(scratch), nbytes, st()),
+                                             p(g_wsum), p(s_col) if ctx.has_saved else None, p(s_sig) if ctx.has_saved else None,
+                                             p(g_planes), p(g_dec), p(scratch), nbytes, st()),
                        'tpr_render_backward')
             g_w1 = torch.empty((64, 32), device=dev, dtype=torch.float32)
             g_b1 = torch.empty(64, device=dev, dtype=torch.float32)

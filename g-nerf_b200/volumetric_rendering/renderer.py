@@ -155,6 +155,9 @@ class ImportanceRenderer(torch.nn.Module):
         # keeps passing the same, unmodified tensor (gen_videos.py renders 120 frames of one identity)
         self.cache_packed_planes = False
         self._plane_cache = None
+        # training: let the forward kernel keep every sample's colours / sigma for the backward (132 B per sample);
+        # False = keep nothing per sample, the backward re-evaluates them (3 ms more at config 2)
+        self.keep_samples = True
 
     def _packed(self, planes):
         """pack_planes with a one-entry cache.  A hit needs the same storage address, shape and version counter; the
@@ -269,7 +272,21 @@ class ImportanceRenderer(torch.nn.Module):
             ev = self._timing_events          # bench.py: CUDA events bracketing the render launch on this stream
             if ev is not None:
                 ev[0].record()
-            if peer_sinks is not None:
+            saved = None
+            if train and getattr(self, 'keep_samples', True):
+                # keep every sample's colours / sigma for the backward (tpr_render_train); `kept` says whether the kernel that
+                # ran could (the warp-specialised one), otherwise the backward re-evaluates them
+                s_tot = dc + df
+                s_col = torch.empty((n * m * s_tot, 32), device=dev, dtype=torch.float32)
+                s_sig = torch.empty((n * m * s_tot,), device=dev, dtype=torch.float32)
+                kept = ctypes.c_int32(0)
+                _lib.check(L.tpr_render_train(_ptr(pp.data), n, pp.height, pp.width, _ptr(dec), _ptr(ray_origins),
+                                              _ptr(ray_directions), m, _ptr(jitter), _ptr(u), _ptr(rs_t), _ptr(re_t),
+                                              ctypes.byref(o), _ptr(rgb), _ptr(depth), _ptr(wsum), _ptr(fine_d), _ptr(rng),
+                                              _ptr(s_col), _ptr(s_sig), ctypes.byref(kept), _ptr(scratch), nscratch, _stream()),
+                           'tpr_render_train')
+                saved = (s_col, s_sig) if kept.value else None
+            elif peer_sinks is not None:
                 _lib.check(L.tpr_render_peers(_ptr(pp.data), n, pp.height, pp.width, _ptr(dec), _ptr(ray_origins),
                                               _ptr(ray_directions), m, _ptr(jitter), _ptr(u), _ptr(rs_t), _ptr(re_t),
                                               ctypes.byref(o), _ptr(rgb), _ptr(depth), _ptr(wsum), _ptr(rng), _ptr(scratch),
@@ -288,7 +305,7 @@ class ImportanceRenderer(torch.nn.Module):
                 coarse_d = torch.empty((n * m, dc), device=dev, dtype=torch.float32)
                 _lib.check(L.tpr_sample_stratified(_ptr(jitter), n * m, _ptr(rs_t), _ptr(re_t), ctypes.byref(o), _ptr(coarse_d),
                                                    _stream()), 'tpr_sample_stratified')
-                aux = dict(packed=pp, dec=dec, coarse=coarse_d, fine=fine_d, range=rng, options=o)
+                aux = dict(packed=pp, dec=dec, coarse=coarse_d, fine=fine_d, range=rng, options=o, saved=saved)
         self.last_depth_range = rng
         self.last_scratch = scratch                    # TPR_PHASE_TIMING=1: int64 phase counters at byte 64
         self.last_fine = (fine_d, fine_i)

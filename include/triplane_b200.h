@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TPR_ABI_VERSION 4
+#define TPR_ABI_VERSION 5
 
 /* fixed by the reference model: OSGDecoder(32 -> 64 -> 1+32), three planes
  * (training/triplane.py:42,113-122; VR/renderer.py:29-37) */
@@ -258,14 +258,27 @@ int tpr_ray_limits_box(const float* origins, const float* dirs, int64_t n_rays,
  * per image (plane_sets = 0) and one clamp range per call only.
  * g_planes_packed [N,3,H,W,32] (the layout of tpr_pack_planes; OVERWRITTEN) and g_decoder_packed
  * [tpr_packed_decoder_bytes()] (the layout of tpr_pack_decoder; OVERWRITTEN; convert with tpr_unpack_decoder_grad).
- * scratch: tpr_render_backward_scratch_bytes(n_img, n_rays, Dc + Df) bytes. */
+ * scratch: tpr_render_backward_scratch_bytes(n_img, n_rays, Dc + Df) bytes.
+ * sample_colours [N*M,S,32] / sample_sigma [N*M,S]: the per-sample decoder outputs kept by tpr_render_train (both or
+ * neither); NULL = re-evaluate them here with the point-query kernel (tpr_run_model), 3 ms more at config 2. */
 size_t tpr_render_backward_scratch_bytes(int64_t n_img, int64_t n_rays, int32_t n_samples);
 int tpr_render_backward(const float* planes_packed, int64_t n_img, int32_t height, int32_t width,
                         const float* decoder_packed, const float* origins, const float* dirs, int64_t n_rays,
                         const float* depths_coarse, const float* depths_fine, const float* depth_range,
                         const TprOptions* opt, const float* g_rgb, const float* g_depth, const float* g_weight_sum,
+                        const float* sample_colours, const float* sample_sigma,
                         float* g_planes_packed, float* g_decoder_packed, void* scratch, size_t scratch_bytes,
                         void* stream);
+/* tpr_render for a caller that will ask for gradients: additionally keeps every sample's colours [N*M,S,32] and sigma
+ * [N*M,S] (the forward's sample order: ray-major, coarse then importance samples) and the importance depths fine_depths
+ * [N*M,Df].  *samples_saved (host) = 1 if the kernel that ran kept them (the warp-specialised kernel), 0 if the sample
+ * counts forced another kernel -- then pass NULL for them to tpr_render_backward.  The depth clamp is applied. */
+int tpr_render_train(const float* planes_packed, int64_t n_img, int32_t height, int32_t width,
+                     const float* decoder_packed, const float* origins, const float* dirs, int64_t n_rays,
+                     const float* jitter, const float* u, const float* ray_start_per_ray, const float* ray_end_per_ray,
+                     const TprOptions* opt, float* rgb, float* depth, float* weight_sum, float* fine_depths,
+                     float* depth_range_io, float* sample_colours, float* sample_sigma, int32_t* samples_saved,
+                     void* scratch, size_t scratch_bytes, void* stream);
 /* packed decoder gradient -> gradients of net.0.weight [64,32], net.0.bias [64], net.2.weight [33,64], net.2.bias [33]
  * (the chain rule through the runtime gains, training/networks_stylegan2.py:118-127, and the plane mean's 1/3). */
 int tpr_unpack_decoder_grad(const float* g_decoder_packed, float w1_gain, float b1_gain, float w2_gain, float b2_gain,

@@ -24,10 +24,11 @@ def rel_err(got, want):
     return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-12))
 
 
-def run_backward(pkg, scene, opts, A, B, C):
+def run_backward(pkg, scene, opts, A, B, C, keep_samples=True):
     dec = make_decoder(pkg, scene['dec']).requires_grad_(True)
     planes = T(scene['planes']).requires_grad_(True)
     R = pkg.ImportanceRenderer()
+    R.keep_samples = keep_samples
     rgb, depth, wsum = R(planes, dec, T(scene['origins']), T(scene['dirs']), opts, noise=(T(scene['jitter']), T(scene['u'])))
     loss = (rgb * T(A)).sum() + (depth * T(B)).sum() + (wsum * T(C)).sum()
     loss.backward()
@@ -135,3 +136,16 @@ def test_reduced_precision_mode_gradients(pkg, name):
     errs = {k: rel_err(g.cpu().numpy(), gold[k]) for g, k in zip(grads, ('g_planes', 'g_w1', 'g_b1', 'g_w2', 'g_b2'))}
     print(name, 'bf16 mode', {k: f'{v:.1e}' for k, v in errs.items()})
     assert max(errs.values()) < 1e-2, errs
+
+
+@pytest.mark.parametrize('name', list(BWD_CASES))
+def test_gradients_without_kept_samples(pkg, name):
+    """keep_samples=False: the forward keeps nothing per sample and the backward re-evaluates colours / sigma with the
+    point-query kernel -- same gate, and the two paths agree closely."""
+    scene, opts, gold, (A, B, C) = load_bwd_case(name)
+    _, g_keep = run_backward(pkg, scene, opts, A, B, C, keep_samples=True)
+    _, g_eval = run_backward(pkg, scene, opts, A, B, C, keep_samples=False)
+    for g, k in zip(g_eval, ('g_planes', 'g_w1', 'g_b1', 'g_w2', 'g_b2')):
+        assert rel_err(g.cpu().numpy(), gold[k]) < REL, k
+    for a, b in zip(g_keep, g_eval):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 5e-5
