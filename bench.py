@@ -46,6 +46,17 @@ def ncu_traffic(mode):
     return tot or None
 
 
+def l2_gather_peak():
+    """Best random-128-byte-line gather bandwidth measured on this pod's B200 with the working set in L2 (one image's
+    planes): tpr_gather_microbench via profiles/gather_roofline.py -> profiles/r01_gather_roofline.json.  None if absent."""
+    path = os.path.join(ROOT, 'profiles', 'r01_gather_roofline.json')
+    try:
+        d = json.load(open(path))
+        return max(v for row in d['one_cta_per_sm_25MB_warps_x_lines_in_flight'].values() for v in row.values())
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -345,7 +356,11 @@ def main():
                          'traffic_note': 'DRAM bytes per launch (ncu --set full, profiles/): one image\'s 25 MB of planes stays '
                                          'L2-resident, so the 1536 B/sample are L2/L1 traffic and frac can exceed 1',
                          'kernel': ('render_kernel' if args.mode == 'fp32_ffma' else 'render_ws_kernel') + ' (tpr_render: +2 helper launches of ~2 us)', 'kernel_ms': kern_ms,
-                         'algorithmic_bytes_per_launch': samples_per_step * BYTES_PER_SAMPLE},
+                         'algorithmic_bytes_per_launch': samples_per_step * BYTES_PER_SAMPLE,
+                         'l2_gather_peak': l2_gather_peak(),
+                         'frac_of_l2_gather': (achieved / l2_gather_peak()) if l2_gather_peak() else None,
+                         'l2_gather_note': 'second ceiling (SURVEY.md section 8(d)): random 128-B line gather out of L2, '
+                                           'tpr_gather_microbench on this pod (profiles/r01_gather_roofline.json), GB/s'},
             'e2e': {'value': world * samples_per_step / (e2e_ms * 1e-3), 'unit': METRIC, 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': 5 * args.steps,                    # pack_planes, pack_decoder, range_init, render_ws, finish

@@ -226,7 +226,8 @@ struct DecArgs {
   float box_scale;
   float* g_planes;                      // packed, zero-initialised
   float* g_dec;                         // [kDecFloats], zero-initialised
-  int debug;                            // TPR_BWD_DEBUG (profiling A/B only): 1 = no scatter, 2 = no weight-gradient phase
+  int debug;                            // bit 0: no plane-gradient scatter, bit 1: no weight-gradient phase (the caller does not want
+                                        // that gradient; TPR_BWD_DEBUG ORs into it for profiling A/B runs)
 };
 
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
@@ -527,7 +528,8 @@ __global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a
         ap += 8 * as; bp += 8 * bs;
       }
     }
-    if (tid < kHid) {
+    if (a.debug & 2) {
+    } else if (tid < kHid) {
       float acc = 0.0f;
 #pragma unroll 8
       for (int r = 0; r < kT; ++r) acc += s.GA[r * HS + tid];
@@ -542,6 +544,7 @@ __global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a
   }
 
   // ---- flush this CTA's partial weight gradients
+  if (a.debug & 2) return;
   {
     const bool second = warp < 4;
     const int pm = second ? warp : (warp - 4) >> 1;
@@ -609,12 +612,12 @@ int launch_bwd_march(const float* dc, const float* df, int Dc, int Df, const flo
 
 int launch_bwd_decode(const float* planes, int H, int W, const float* dec, const float* pts, const float* colours,
                       const float* gsig, const float* omega, const float* g_rgb, long long total, long long pts_per_img, int S,
-                      float box_scale, float* g_planes, float* g_dec, int fast, int sms, cudaStream_t st) {
+                      float box_scale, float* g_planes, float* g_dec, int fast, int skip, int sms, cudaStream_t st) {
   bwd::DecArgs a;
   a.planes = planes; a.H = H; a.W = W; a.dec = dec; a.pts = pts; a.colours = colours; a.gsig = gsig; a.omega = omega;
   a.g_rgb = g_rgb; a.total = total; a.pts_per_img = pts_per_img; a.S = S; a.box_scale = box_scale; a.g_planes = g_planes;
   a.g_dec = g_dec;
-  { const char* e = getenv("TPR_BWD_DEBUG"); a.debug = e ? atoi(e) : 0; }
+  { const char* e = getenv("TPR_BWD_DEBUG"); a.debug = skip | (e ? atoi(e) : 0); }
   const size_t smem = sizeof(bwd::Smem) + 16;
   void (*kern)(const bwd::DecArgs) = fast ? bwd::decode_backward_kernel<true> : bwd::decode_backward_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -36,7 +36,7 @@ int launch_bwd_march(const float* dc, const float* df, int Dc, int Df, const flo
                      long long n_rays_total, float* gsig, float* omega, int sms, cudaStream_t st);
 int launch_bwd_decode(const float* planes, int H, int W, const float* dec, const float* pts, const float* colours,
                       const float* gsig, const float* omega, const float* g_rgb, long long total, long long pts_per_img, int S,
-                      float box_scale, float* g_planes, float* g_dec, int fast, int sms, cudaStream_t st);
+                      float box_scale, float* g_planes, float* g_dec, int fast, int skip, int sms, cudaStream_t st);
 int launch_unpack_decoder_grad(const float* gd, float g_w1, float g_b1, float g_w2, float g_b2, float* w1, float* b1, float* w2,
                                float* b2, cudaStream_t st);
 
@@ -1206,7 +1206,7 @@ int tpr_render_backward(const float* planes_packed, int64_t n_img, int32_t heigh
   if ((sample_colours == nullptr) != (sample_sigma == nullptr))
     return fail(TPR_E_NULL, "tpr_render_backward: sample_colours and sample_sigma come together");
   if (!planes_packed || !decoder_packed || !origins || !dirs || !depths_coarse || !depth_range || !opt || !g_rgb || !g_depth ||
-      !g_weight_sum || !g_planes_packed || !g_decoder_packed || !scratch)
+      !g_weight_sum || (!g_planes_packed && !g_decoder_packed) || !scratch)
     return fail(TPR_E_NULL, "tpr_render_backward: NULL pointer");
   const int Dc = opt->depth_resolution, Df = opt->depth_resolution_importance, S = Dc + Df;
   if (Df > 0 && !depths_fine) return fail(TPR_E_NULL, "tpr_render_backward: depths_fine is NULL but depth_resolution_importance > 0");
@@ -1242,12 +1242,14 @@ int tpr_render_backward(const float* planes_packed, int64_t n_img, int32_t heigh
   rc = launch_bwd_march(depths_coarse, depths_fine, Dc, Df, sig_in, col_in, g_rgb, g_depth, g_weight_sum, depth_range,
                         opt->white_back, rays, gsig, omega, di.sms, st);
   if (rc != 0) return cuda_fail((cudaError_t)rc, "march_backward_kernel");
-  cudaError_t e = cudaMemsetAsync(g_planes_packed, 0, (size_t)n_img * 3 * height * width * kC * sizeof(float), st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(g_decoder_packed, 0, kDecFloats * sizeof(float), st);
+  cudaError_t e = cudaSuccess;
+  if (g_planes_packed) e = cudaMemsetAsync(g_planes_packed, 0, (size_t)n_img * 3 * height * width * kC * sizeof(float), st);
+  if (e == cudaSuccess && g_decoder_packed) e = cudaMemsetAsync(g_decoder_packed, 0, kDecFloats * sizeof(float), st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+  float* g_dec_out = g_decoder_packed ? g_decoder_packed : reinterpret_cast<float*>(scratch);      // (never written when skipped)
   rc = launch_bwd_decode(planes_packed, height, width, decoder_packed, pts, col_in, gsig, omega, g_rgb, (long long)T,
-                         (long long)n_rays * S, S, (float)(2.0 / opt->box_warp), g_planes_packed, g_decoder_packed,
-                         opt->flags == TPR_MLP_BF16, di.sms, st);
+                         (long long)n_rays * S, S, (float)(2.0 / opt->box_warp), g_planes_packed, g_dec_out,
+                         opt->flags == TPR_MLP_BF16, (g_planes_packed ? 0 : 1) | (g_decoder_packed ? 0 : 2), di.sms, st);
   if (rc != 0) return cuda_fail((cudaError_t)rc, "decode_backward_kernel");
   return 0;
 }

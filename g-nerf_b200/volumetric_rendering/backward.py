@@ -49,9 +49,11 @@ class _Render(torch.autograd.Function):
         g_rgb = g_rgb.contiguous().float() if g_rgb is not None else zeros((n, m, 32))
         g_depth = g_depth.contiguous().float() if g_depth is not None else zeros((n, m, 1))
         g_wsum = g_wsum.contiguous().float() if g_wsum is not None else zeros((n, m, 1))
+        need = ctx.needs_input_grad
+        want_planes, want_dec = need[4], any(need[5:9])
         with torch.cuda.device(dev):
-            g_planes = torch.empty_like(packed)
-            g_dec = torch.empty_like(dec)
+            g_planes = torch.empty_like(packed) if want_planes else None
+            g_dec = torch.empty_like(dec) if want_dec else None
             nbytes = L.tpr_render_backward_scratch_bytes(n, m, o.depth_resolution + o.depth_resolution_importance)
             scratch = torch.empty(nbytes, device=dev, dtype=torch.uint8)
             o2 = _lib.TprOptions.from_buffer_copy(o)
@@ -61,14 +63,15 @@ class _Render(torch.autograd.Function):
                                              p(g_wsum), p(s_col) if ctx.has_saved else None, p(s_sig) if ctx.has_saved else None,
                                              p(g_planes), p(g_dec), p(scratch), nbytes, st()),
                        'tpr_render_backward')
-            g_w1 = torch.empty((64, 32), device=dev, dtype=torch.float32)
-            g_b1 = torch.empty(64, device=dev, dtype=torch.float32)
-            g_w2 = torch.empty((33, 64), device=dev, dtype=torch.float32)
-            g_b2 = torch.empty(33, device=dev, dtype=torch.float32)
-            _lib.check(L.tpr_unpack_decoder_grad(p(g_dec), *ctx.gains, p(g_w1), p(g_b1), p(g_w2), p(g_b2), st()),
-                       'tpr_unpack_decoder_grad')
+            g_w1 = g_b1 = g_w2 = g_b2 = None
+            if want_dec:
+                g_w1 = torch.empty((64, 32), device=dev, dtype=torch.float32)
+                g_b1 = torch.empty(64, device=dev, dtype=torch.float32)
+                g_w2 = torch.empty((33, 64), device=dev, dtype=torch.float32)
+                g_b2 = torch.empty(33, device=dev, dtype=torch.float32)
+                _lib.check(L.tpr_unpack_decoder_grad(p(g_dec), *ctx.gains, p(g_w1), p(g_b1), p(g_w2), p(g_b2), st()),
+                           'tpr_unpack_decoder_grad')
         # the plane gradient lives in the packed layout [N,3,H,W,32]; hand autograd its [N,3,32,H,W] view (no copy)
-        need = ctx.needs_input_grad
         return (None, None, None, None, g_planes.permute(0, 1, 4, 2, 3) if need[4] else None,
                 g_w1 if need[5] else None, g_b1 if need[6] else None, g_w2 if need[7] else None, g_b2 if need[8] else None,
                 None, None)

@@ -256,6 +256,7 @@ int tpr_ray_limits_box(const float* origins, const float* dirs, int64_t n_rays,
  * (the clamp of VR/ray_marcher.py:50 passes gradient only inside it).  From opt: box_warp, depth_resolution,
  * depth_resolution_importance, white_back, flags (decoder precision of the colour/density recomputation).  One plane set
  * per image (plane_sets = 0) and one clamp range per call only.
+ * Either output may be NULL when the caller does not need that gradient (its phase of the kernel is skipped).
  * g_planes_packed [N,3,H,W,32] (the layout of tpr_pack_planes; OVERWRITTEN) and g_decoder_packed
  * [tpr_packed_decoder_bytes()] (the layout of tpr_pack_decoder; OVERWRITTEN; convert with tpr_unpack_decoder_grad).
  * scratch: tpr_render_backward_scratch_bytes(n_img, n_rays, Dc + Df) bytes.

@@ -14,7 +14,7 @@ planes = planes_h.to(dev); o, d = S(c2w.to(dev), K.to(dev), 128)
 WS = ['GATHER wait coarse_ready', 'GATHER wait fine_ready', 'GATHER wait a1_free', 'GATHER gather+publish',
       'DECODE wait a1_full (issuer)', 'DECODE issue M1 + slot', 'DECODE wait d1_full', 'DECODE epilogue1', 'DECODE wait a2_full (issuer)',
       'DECODE issue M2', 'DECODE wait m2_done', 'DECODE sigma readback', 'RAYS setup', 'RAYS wait csig', 'RAYS resample',
-      'RAYS wait fsig', 'RAYS sort+march', 'RAYS composite', 'RAYS   (pair rank count, part of sort+march; sort+march then excludes it)']
+      'RAYS wait fsig', 'RAYS sort+march', 'RAYS composite', 'RAYS   (merge / pair rank count at 96+96: part of the sort, not counted in sort+march)']
 TC = ['setup', 'G0+sync', 'issueM1', 'G(t+1)', 'wait bar1/2', 'E1+sync', 'issueM2', 'pass-end wait+sigma', 'resample', 'sort', 'composite']
 D = int(os.environ.get('TPR_PT_DEPTH', '48'))          # samples per pass (96 = gen_videos / config 4)
 RPG = 8 if D <= 48 else 4                                # rays per group the kernel picks

@@ -149,3 +149,20 @@ def test_gradients_without_kept_samples(pkg, name):
         assert rel_err(g.cpu().numpy(), gold[k]) < REL, k
     for a, b in zip(g_keep, g_eval):
         assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 5e-5
+
+
+def test_only_the_requested_gradients_are_computed(pkg):
+    """Frozen decoder / frozen planes: the corresponding phase of the backward kernel is skipped (NULL output in the C ABI)
+    and the remaining gradient is unchanged."""
+    scene, opts, gold, (A, B, C) = load_bwd_case('bwd_ffhq')
+    _, full = run_backward(pkg, scene, opts, A, B, C)
+    args = (T(scene['origins']), T(scene['dirs']), opts)
+    noise = (T(scene['jitter']), T(scene['u']))
+    loss = lambda out: (out[0] * T(A)).sum() + (out[1] * T(B)).sum() + (out[2] * T(C)).sum()
+    planes = T(scene['planes']).requires_grad_(True)
+    loss(pkg.ImportanceRenderer()(planes, make_decoder(pkg, scene['dec']), *args, noise=noise)).backward()
+    assert rel_err(planes.grad.cpu().numpy(), full[0].cpu().numpy()) < 1e-5
+    dec = make_decoder(pkg, scene['dec']).requires_grad_(True)
+    loss(pkg.ImportanceRenderer()(T(scene['planes']), dec, *args, noise=noise)).backward()
+    for got, want in zip((dec.net[0].weight.grad, dec.net[0].bias.grad, dec.net[2].weight.grad, dec.net[2].bias.grad), full[1:]):
+        assert rel_err(got.cpu().numpy(), want.cpu().numpy()) < 1e-5
