@@ -9,7 +9,7 @@ from ctypes import c_char_p, c_double, c_float, c_int32, c_int64, c_size_t, c_vo
 
 from .build import LIB_PATH
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MLP_FP32, MLP_BF16, MLP_FFMA = 0, 1, 2
 LAYOUT_CHANNELS_LAST, LAYOUT_CHANNELS_FIRST = 0, 1
 
@@ -63,9 +63,9 @@ _SIGNATURES = {
     'tpr_ray_limits_box': (ctypes.c_int, [_P, _P, c_int64, c_float, _P, _P, _P]),
     'tpr_render_backward_scratch_bytes': (c_size_t, [c_int64, c_int64, c_int32]),
     'tpr_render_backward': (ctypes.c_int, [_P, c_int64, c_int32, c_int32, _P, _P, _P, c_int64, _P, _P, _P,
-                                           ctypes.POINTER(TprOptions), _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+                                           ctypes.POINTER(TprOptions), _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     'tpr_render_train': (ctypes.c_int, [_P, c_int64, c_int32, c_int32, _P, _P, _P, c_int64, _P, _P, _P, _P,
-                                        ctypes.POINTER(TprOptions), _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(c_int32), _P,
+                                        ctypes.POINTER(TprOptions), _P, _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(c_int32), _P,
                                         c_size_t, _P]),
     'tpr_unpack_decoder_grad': (ctypes.c_int, [_P, c_float, c_float, c_float, c_float, _P, _P, _P, _P, _P]),
     'tpr_march_backward': (ctypes.c_int, [_P, _P, c_int32, c_int32, _P, _P, _P, _P, _P, _P, c_int32, c_int64, _P, _P, _P]),

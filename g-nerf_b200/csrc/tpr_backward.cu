@@ -220,6 +220,7 @@ struct DecArgs {
   const float* dec;                     // packed decoder
   const float* pts;                     // [T,3]
   const float* colours;                 // [T,32]
+  const float* features;                // [T,32] summed plane features kept by the forward, or NULL: gather them again
   const float* gsig; const float* omega;// [T]
   const float* g_rgb;                   // [rays,32]
   long long total, pts_per_img; int S;
@@ -319,10 +320,17 @@ __global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a
 #pragma unroll 1
     for (int it = 0; it < 2; ++it) {
       const int sr = row0 + 8 * hf + it * 4 + grp;
+      const long long gsf = gs0 + sr;
+      const bool kept = a.features != nullptr;
       const float4* img = reinterpret_cast<const float4*>(a.planes + (size_t)s.simg[sr] * img_stride) + sub;
       float4 v[12];
+      float4 fk = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kept) {
+        if (gsf < a.total) fk = __ldg(reinterpret_cast<const float4*>(a.features + gsf * 32) + sub);
+      } else {
 #pragma unroll
-      for (int k = 0; k < 12; ++k) v[k] = __ldg(img + (s.tap_off[sr * 12 + k] >> 2));
+        for (int k = 0; k < 12; ++k) v[k] = __ldg(img + (s.tap_off[sr * 12 + k] >> 2));
+      }
       // ---- upstream gradient of the decoder outputs of this sample (loads overlap the texel fetches)
       const long long gs = gs0 + sr;
       float gy[4] = {0.f, 0.f, 0.f, 0.f};
@@ -344,11 +352,13 @@ __global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a
 #pragma unroll
       for (int k = 0; k < 4; ++k) gyr[1 + 4 * sub + k] = gy[k];
       if (sub == 0) gyr[0] = gs_sig;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 acc = fk;
+      if (!kept) {
 #pragma unroll
-      for (int k = 0; k < 12; ++k) {
-        const float w = s.tap_w[sr * 12 + k];
-        acc.x = fmaf(w, v[k].x, acc.x); acc.y = fmaf(w, v[k].y, acc.y); acc.z = fmaf(w, v[k].z, acc.z); acc.w = fmaf(w, v[k].w, acc.w);
+        for (int k = 0; k < 12; ++k) {
+          const float w = s.tap_w[sr * 12 + k];
+          acc.x = fmaf(w, v[k].x, acc.x); acc.y = fmaf(w, v[k].y, acc.y); acc.z = fmaf(w, v[k].z, acc.z); acc.w = fmaf(w, v[k].w, acc.w);
+        }
       }
       *reinterpret_cast<float4*>(s.F + sr * FS + 4 * sub) = acc;
     }
@@ -611,10 +621,10 @@ int launch_bwd_march(const float* dc, const float* df, int Dc, int Df, const flo
 }
 
 int launch_bwd_decode(const float* planes, int H, int W, const float* dec, const float* pts, const float* colours,
-                      const float* gsig, const float* omega, const float* g_rgb, long long total, long long pts_per_img, int S,
+                      const float* features, const float* gsig, const float* omega, const float* g_rgb, long long total, long long pts_per_img, int S,
                       float box_scale, float* g_planes, float* g_dec, int fast, int skip, int sms, cudaStream_t st) {
   bwd::DecArgs a;
-  a.planes = planes; a.H = H; a.W = W; a.dec = dec; a.pts = pts; a.colours = colours; a.gsig = gsig; a.omega = omega;
+  a.planes = planes; a.H = H; a.W = W; a.dec = dec; a.pts = pts; a.colours = colours; a.features = features; a.gsig = gsig; a.omega = omega;
   a.g_rgb = g_rgb; a.total = total; a.pts_per_img = pts_per_img; a.S = S; a.box_scale = box_scale; a.g_planes = g_planes;
   a.g_dec = g_dec;
   { const char* e = getenv("TPR_BWD_DEBUG"); a.debug = skip | (e ? atoi(e) : 0); }

@@ -30,6 +30,7 @@ struct RenderArgs {
   int clamp_group;                       // k > 0: images [j*k, (j+1)*k) share a depth-clamp range (slot j); 0: one range
   PeerSinks peers;                       // n > 0: every output store is repeated into these peer buffers
   float* sample_colours; float* sample_sigma;   // training: per-sample colours [rays,S,32] / sigma [rays,S] kept for the backward
+  float* sample_features;                       // training: per-sample summed plane features [rays,S,32] (optional)
 };
 
 // Depth ranges in the scratch block (unsigned words, ordered-uint encoded): [0..1] whole call, then from

@@ -78,10 +78,10 @@ __device__ __forceinline__ Geom group_geom(const RenderArgs& a, unsigned grp, in
 //         at a time: tpr_gather_microbench (profiles/) shows that on B200 a shallow queue per thread and many
 //         warps sustains more random-line bandwidth than twelve loads in flight per thread.
 // ---------------------------------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, bool TRAIN = false>
 __device__ __forceinline__ void gather_tile(const RenderArgs& a, float* a1_hi, float* a1_lo, const float* __restrict__ img,
                                             const Ctx& cx, Tap2* tw, int nr, int Dx, int off, int S, int t, int dpt_shift,
-                                            int warp, int lane) {
+                                            int warp, int lane, long long ray0 = 0, int rstride = 0) {
   const int grp = lane >> 3, sub = lane & 7;
   const int dpt = 1 << dpt_shift;
   {
@@ -116,7 +116,10 @@ __device__ __forceinline__ void gather_tile(const RenderArgs& a, float* a1_hi, f
     const int r = row >> dpt_shift, di = t * dpt + (row & (dpt - 1));
     if (r < nr && di < Dx) {
       const Tap2* te = tw + s * 3;
-      blend_sample<MODE>(a1_hi, a1_lo, base, te, row, sub);
+      // training: the summed features of the sample are kept for the backward (128 contiguous bytes per sample)
+      float4* keep = (TRAIN && a.sample_features != nullptr)
+          ? reinterpret_cast<float4*>(a.sample_features + ((ray0 + (long long)r * rstride) * S + off + di) * 32) + sub : nullptr;
+      blend_sample<MODE>(a1_hi, a1_lo, base, te, row, sub, keep);
     }
   }
   __syncwarp();           // the tap table is rewritten by the next tile
@@ -216,7 +219,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
         for (int t = 0; t < T; ++t) {
           mbar_wait_parked(&bars.a1_free[b], ph ^ 1u);      // passes immediately the first time round
           PROF_ADD(2, tid == 0);
-          gather_tile<MODE>(a, tl.a1[b][0], tl.a1[b][MODE == 0 ? 1 : 0], img, cx, tw, gg.nr, Dx, off, S, t, dpt_shift, warp, lane);
+          gather_tile<MODE, TRAIN>(a, tl.a1[b][0], tl.a1[b][MODE == 0 ? 1 : 0], img, cx, tw, gg.nr, Dx, off, S, t, dpt_shift, warp, lane,
+                                   gg.ray0, gg.rstride);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars.a1_full[b]);

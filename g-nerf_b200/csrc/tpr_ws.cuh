@@ -100,7 +100,9 @@ struct __align__(16) Tap2 { uint32_t off[4]; float w2[8]; };
 // more random-line bandwidth than twelve loads in flight per thread -- sums the planes and writes its 16 bytes of
 // row `row` of the A1 operand tile (hi / lo tf32 copies, or packed bf16).
 template <int MODE>
-__device__ __forceinline__ void blend_sample(float* a1_hi, float* a1_lo, const ulonglong2* base, const Tap2* te, int row, int sub) {
+// `keep` (training only): where this lane's four summed features also go in HBM.
+__device__ __forceinline__ void blend_sample(float* a1_hi, float* a1_lo, const ulonglong2* base, const Tap2* te, int row, int sub,
+                                             float4* keep = nullptr) {
   uint64_t f01 = 0ull, f23 = 0ull;           // channels (0,1) and (2,3) of this lane, summed over the planes
 #pragma unroll 1
   for (int p = 0; p < 3; ++p) {
@@ -115,6 +117,7 @@ __device__ __forceinline__ void blend_sample(float* a1_hi, float* a1_lo, const u
   }
   float4 f;
   unpack2(f01, f.x, f.y); unpack2(f23, f.z, f.w);
+  if (keep != nullptr) *keep = f;
   if (MODE == 1) {
     uint2 pk = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
     uint8_t* dst = reinterpret_cast<uint8_t*>(a1_hi) + row * 128 + ((((sub >> 1) ^ (row & 7)) << 4) | ((sub & 1) << 3));

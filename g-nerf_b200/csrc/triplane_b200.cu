@@ -35,7 +35,7 @@ int launch_bwd_march(const float* dc, const float* df, int Dc, int Df, const flo
                      const float* g_rgb, const float* g_depth, const float* g_wsum, const float* range, int white_back,
                      long long n_rays_total, float* gsig, float* omega, int sms, cudaStream_t st);
 int launch_bwd_decode(const float* planes, int H, int W, const float* dec, const float* pts, const float* colours,
-                      const float* gsig, const float* omega, const float* g_rgb, long long total, long long pts_per_img, int S,
+                      const float* features, const float* gsig, const float* omega, const float* g_rgb, long long total, long long pts_per_img, int S,
                       float box_scale, float* g_planes, float* g_dec, int fast, int skip, int sms, cudaStream_t st);
 int launch_unpack_decoder_grad(const float* gd, float g_w1, float g_b1, float g_w2, float g_b2, float* w1, float* b1, float* w2,
                                float* b2, cudaStream_t st);
@@ -757,7 +757,7 @@ static int render_impl(const float* planes_packed, int64_t n_img, int32_t height
                        float* depth, float* weight_sum, float* fine_depths, int32_t* fine_inds, float* depth_range_io,
                        int32_t clamp_depth, void* scratch, size_t scratch_bytes, void* stream, int phases,
                        const TprPeerSinks* peers = nullptr, float* sample_colours = nullptr, float* sample_sigma = nullptr,
-                       int32_t* samples_saved = nullptr) {
+                       int32_t* samples_saved = nullptr, float* sample_features = nullptr) {
   if (!planes_packed || !decoder_packed || !origins || !dirs || !jitter || !opt || !rgb || !depth || !weight_sum || !scratch)
     return fail(TPR_E_NULL, "tpr_render: NULL pointer");
   if ((ray_start_per_ray == nullptr) != (ray_end_per_ray == nullptr))
@@ -828,11 +828,11 @@ static int render_impl(const float* planes_packed, int64_t n_img, int32_t height
   if (opt->flags != TPR_MLP_FFMA && impl != 1 && !env_int("TPR_FORCE_FFMA", 0) &&
       ws_rays_per_group(Dc, Df, opt->flags == TPR_MLP_BF16) > 0) {
     const bool keep = sample_colours && sample_sigma && ws_keeps_samples(Dc, Df) && !a.dbg;
-    if (keep) { a.sample_colours = sample_colours; a.sample_sigma = sample_sigma; }      // (only this kernel can keep them)
+    if (keep) { a.sample_colours = sample_colours; a.sample_sigma = sample_sigma; a.sample_features = sample_features; }   // (only this kernel can keep them)
     int rc = launch_render_ws(a, opt->flags == TPR_MLP_BF16, di.sms, di.smem_optin, n_img, n_rays, st);
     if (rc > 0) return cuda_fail((cudaError_t)rc, "render_ws_kernel");
     done = rc == 0;                       // < 0: does not fit shared memory, fall through
-    a.sample_colours = nullptr; a.sample_sigma = nullptr;
+    a.sample_colours = nullptr; a.sample_sigma = nullptr; a.sample_features = nullptr;
   }
   if (samples_saved) *samples_saved = (done && sample_colours && sample_sigma && ws_keeps_samples(Dc, Df) && !a.dbg) ? 1 : 0;
   const bool kernel_stores_to_peers = done;     // only the warp-specialised kernel has the peer stores in its epilogue
@@ -895,12 +895,13 @@ int tpr_render_train(const float* planes_packed, int64_t n_img, int32_t height, 
                      const float* origins, const float* dirs, int64_t n_rays, const float* jitter, const float* u,
                      const float* ray_start_per_ray, const float* ray_end_per_ray, const TprOptions* opt, float* rgb,
                      float* depth, float* weight_sum, float* fine_depths, float* depth_range_io, float* sample_colours,
-                     float* sample_sigma, int32_t* samples_saved, void* scratch, size_t scratch_bytes, void* stream) {
+                     float* sample_sigma, float* sample_features, int32_t* samples_saved, void* scratch, size_t scratch_bytes,
+                     void* stream) {
   if (!sample_colours || !sample_sigma || !samples_saved) return fail(TPR_E_NULL, "tpr_render_train: NULL pointer");
   if (opt && opt->depth_resolution_importance > 0 && !fine_depths) return fail(TPR_E_NULL, "tpr_render_train: NULL fine_depths");
   return render_impl(planes_packed, n_img, height, width, decoder_packed, origins, dirs, n_rays, jitter, u, ray_start_per_ray,
                      ray_end_per_ray, opt, rgb, depth, weight_sum, fine_depths, nullptr, depth_range_io, 1, scratch, scratch_bytes,
-                     stream, kRangeInit | kFinish, nullptr, sample_colours, sample_sigma, samples_saved);
+                     stream, kRangeInit | kFinish, nullptr, sample_colours, sample_sigma, samples_saved, sample_features);
 }
 
 int tpr_render_peers(const float* planes_packed, int64_t n_img, int32_t height, int32_t width, const float* decoder_packed,
@@ -1202,7 +1203,7 @@ int tpr_render_backward(const float* planes_packed, int64_t n_img, int32_t heigh
                         const float* origins, const float* dirs, int64_t n_rays, const float* depths_coarse,
                         const float* depths_fine, const float* depth_range, const TprOptions* opt, const float* g_rgb,
                         const float* g_depth, const float* g_weight_sum, const float* sample_colours, const float* sample_sigma,
-                        float* g_planes_packed, float* g_decoder_packed, void* scratch, size_t scratch_bytes, void* stream) {
+                        const float* sample_features, float* g_planes_packed, float* g_decoder_packed, void* scratch, size_t scratch_bytes, void* stream) {
   if ((sample_colours == nullptr) != (sample_sigma == nullptr))
     return fail(TPR_E_NULL, "tpr_render_backward: sample_colours and sample_sigma come together");
   if (!planes_packed || !decoder_packed || !origins || !dirs || !depths_coarse || !depth_range || !opt || !g_rgb || !g_depth ||
@@ -1247,7 +1248,7 @@ int tpr_render_backward(const float* planes_packed, int64_t n_img, int32_t heigh
   if (e == cudaSuccess && g_decoder_packed) e = cudaMemsetAsync(g_decoder_packed, 0, kDecFloats * sizeof(float), st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
   float* g_dec_out = g_decoder_packed ? g_decoder_packed : reinterpret_cast<float*>(scratch);      // (never written when skipped)
-  rc = launch_bwd_decode(planes_packed, height, width, decoder_packed, pts, col_in, gsig, omega, g_rgb, (long long)T,
+  rc = launch_bwd_decode(planes_packed, height, width, decoder_packed, pts, col_in, sample_features, gsig, omega, g_rgb, (long long)T,
                          (long long)n_rays * S, S, (float)(2.0 / opt->box_warp), g_planes_packed, g_dec_out,
                          opt->flags == TPR_MLP_BF16, (g_planes_packed ? 0 : 1) | (g_decoder_packed ? 0 : 2), di.sms, st);
   if (rc != 0) return cuda_fail((cudaError_t)rc, "decode_backward_kernel");

@@ -32,14 +32,17 @@ class _Render(torch.autograd.Function):
         fine = aux['fine'] if aux['fine'] is not None else torch.empty(0, device=rgb.device)
         ctx.has_fine = aux['fine'] is not None
         ctx.has_saved = aux['saved'] is not None
-        s_col, s_sig = aux['saved'] if ctx.has_saved else (torch.empty(0, device=rgb.device),) * 2
+        s_col, s_sig, s_feat = aux['saved'] if ctx.has_saved else (None, None, None)
+        ctx.has_feat = s_feat is not None
+        empty = torch.empty(0, device=rgb.device)
         ctx.save_for_backward(aux['packed'].data, aux['dec'], origins.contiguous(), dirs.contiguous(), aux['coarse'], fine,
-                              aux['range'], s_col, s_sig)
+                              aux['range'], s_col if ctx.has_saved else empty, s_sig if ctx.has_saved else empty,
+                              s_feat if ctx.has_feat else empty)
         return rgb, depth, wsum
 
     @staticmethod
     def backward(ctx, g_rgb, g_depth, g_wsum):
-        packed, dec, origins, dirs, coarse, fine, rng, s_col, s_sig = ctx.saved_tensors
+        packed, dec, origins, dirs, coarse, fine, rng, s_col, s_sig, s_feat = ctx.saved_tensors
         n, m = ctx.shape
         pp, o = ctx.packed, ctx.opts
         dev = packed.device
@@ -61,6 +64,7 @@ class _Render(torch.autograd.Function):
             _lib.check(L.tpr_render_backward(p(packed), n, pp.height, pp.width, p(dec), p(origins), p(dirs), m, p(coarse),
                                              p(fine) if ctx.has_fine else None, p(rng), ctypes.byref(o2), p(g_rgb), p(g_depth),
                                              p(g_wsum), p(s_col) if ctx.has_saved else None, p(s_sig) if ctx.has_saved else None,
+                                             p(s_feat) if ctx.has_feat else None,
                                              p(g_planes), p(g_dec), p(scratch), nbytes, st()),
                        'tpr_render_backward')
             g_w1 = g_b1 = g_w2 = g_b2 = None

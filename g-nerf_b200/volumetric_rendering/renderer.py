@@ -158,6 +158,7 @@ class ImportanceRenderer(torch.nn.Module):
         # training: let the forward kernel keep every sample's colours / sigma for the backward (132 B per sample);
         # False = keep nothing per sample, the backward re-evaluates them (3 ms more at config 2)
         self.keep_samples = True
+        self.keep_features = True          # ... and its 32 summed plane features (128 B more per sample): no second gather
 
     def _packed(self, planes):
         """pack_planes with a one-entry cache.  A hit needs the same storage address, shape and version counter; the
@@ -279,13 +280,16 @@ class ImportanceRenderer(torch.nn.Module):
                 s_tot = dc + df
                 s_col = torch.empty((n * m * s_tot, 32), device=dev, dtype=torch.float32)
                 s_sig = torch.empty((n * m * s_tot,), device=dev, dtype=torch.float32)
+                s_feat = (torch.empty((n * m * s_tot, 32), device=dev, dtype=torch.float32)
+                          if getattr(self, 'keep_features', True) else None)
                 kept = ctypes.c_int32(0)
                 _lib.check(L.tpr_render_train(_ptr(pp.data), n, pp.height, pp.width, _ptr(dec), _ptr(ray_origins),
                                               _ptr(ray_directions), m, _ptr(jitter), _ptr(u), _ptr(rs_t), _ptr(re_t),
                                               ctypes.byref(o), _ptr(rgb), _ptr(depth), _ptr(wsum), _ptr(fine_d), _ptr(rng),
-                                              _ptr(s_col), _ptr(s_sig), ctypes.byref(kept), _ptr(scratch), nscratch, _stream()),
+                                              _ptr(s_col), _ptr(s_sig), _ptr(s_feat), ctypes.byref(kept), _ptr(scratch), nscratch,
+                                              _stream()),
                            'tpr_render_train')
-                saved = (s_col, s_sig) if kept.value else None
+                saved = (s_col, s_sig, s_feat) if kept.value else None
             elif peer_sinks is not None:
                 _lib.check(L.tpr_render_peers(_ptr(pp.data), n, pp.height, pp.width, _ptr(dec), _ptr(ray_origins),
                                               _ptr(ray_directions), m, _ptr(jitter), _ptr(u), _ptr(rs_t), _ptr(re_t),

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TPR_ABI_VERSION 5
+#define TPR_ABI_VERSION 6
 
 /* fixed by the reference model: OSGDecoder(32 -> 64 -> 1+32), three planes
  * (training/triplane.py:42,113-122; VR/renderer.py:29-37) */
@@ -261,13 +261,15 @@ int tpr_ray_limits_box(const float* origins, const float* dirs, int64_t n_rays,
  * [tpr_packed_decoder_bytes()] (the layout of tpr_pack_decoder; OVERWRITTEN; convert with tpr_unpack_decoder_grad).
  * scratch: tpr_render_backward_scratch_bytes(n_img, n_rays, Dc + Df) bytes.
  * sample_colours [N*M,S,32] / sample_sigma [N*M,S]: the per-sample decoder outputs kept by tpr_render_train (both or
- * neither); NULL = re-evaluate them here with the point-query kernel (tpr_run_model), 3 ms more at config 2. */
+ * neither); NULL = re-evaluate them here with the point-query kernel (tpr_run_model), 3 ms more at config 2.
+ * sample_features [N*M,S,32]: the summed plane features of every sample, also kept by tpr_render_train; NULL = gather
+ * them again. */
 size_t tpr_render_backward_scratch_bytes(int64_t n_img, int64_t n_rays, int32_t n_samples);
 int tpr_render_backward(const float* planes_packed, int64_t n_img, int32_t height, int32_t width,
                         const float* decoder_packed, const float* origins, const float* dirs, int64_t n_rays,
                         const float* depths_coarse, const float* depths_fine, const float* depth_range,
                         const TprOptions* opt, const float* g_rgb, const float* g_depth, const float* g_weight_sum,
-                        const float* sample_colours, const float* sample_sigma,
+                        const float* sample_colours, const float* sample_sigma, const float* sample_features,
                         float* g_planes_packed, float* g_decoder_packed, void* scratch, size_t scratch_bytes,
                         void* stream);
 /* tpr_render for a caller that will ask for gradients: additionally keeps every sample's colours [N*M,S,32] and sigma
@@ -278,7 +280,8 @@ int tpr_render_train(const float* planes_packed, int64_t n_img, int32_t height, 
                      const float* decoder_packed, const float* origins, const float* dirs, int64_t n_rays,
                      const float* jitter, const float* u, const float* ray_start_per_ray, const float* ray_end_per_ray,
                      const TprOptions* opt, float* rgb, float* depth, float* weight_sum, float* fine_depths,
-                     float* depth_range_io, float* sample_colours, float* sample_sigma, int32_t* samples_saved,
+                     float* depth_range_io, float* sample_colours, float* sample_sigma,
+                     float* sample_features /* [N*M,S,32] or NULL */, int32_t* samples_saved,
                      void* scratch, size_t scratch_bytes, void* stream);
 /* packed decoder gradient -> gradients of net.0.weight [64,32], net.0.bias [64], net.2.weight [33,64], net.2.bias [33]
  * (the chain rule through the runtime gains, training/networks_stylegan2.py:118-127, and the plane mean's 1/3). */

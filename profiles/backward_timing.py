@@ -9,7 +9,7 @@ import bench
 from oracle import torch_oracle as TO
 pkg = importlib.import_module('g-nerf_b200')
 ap = argparse.ArgumentParser(); ap.add_argument('--n-img', type=int, default=8); ap.add_argument('--eager-img', type=int, default=1)
-ap.add_argument('--reps', type=int, default=10); ap.add_argument('--mode', default='fp32'); ap.add_argument('--no-keep', action='store_true')
+ap.add_argument('--reps', type=int, default=10); ap.add_argument('--mode', default='fp32'); ap.add_argument('--no-keep', action='store_true'); ap.add_argument('--no-keep-features', action='store_true')
 args = ap.parse_args()
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = torch.device('cuda:0')
@@ -21,6 +21,7 @@ opts = dict(bench.OPTS, decoder_precision=args.mode)
 n, m = o.shape[:2]
 R = pkg.ImportanceRenderer()
 R.keep_samples = not args.no_keep
+R.keep_features = not args.no_keep_features
 A, B, C = torch.randn(n, m, 32, device=dev), torch.randn(n, m, 1, device=dev), torch.randn(n, m, 1, device=dev)
 
 

@@ -24,11 +24,12 @@ def rel_err(got, want):
     return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-12))
 
 
-def run_backward(pkg, scene, opts, A, B, C, keep_samples=True):
+def run_backward(pkg, scene, opts, A, B, C, keep_samples=True, keep_features=True):
     dec = make_decoder(pkg, scene['dec']).requires_grad_(True)
     planes = T(scene['planes']).requires_grad_(True)
     R = pkg.ImportanceRenderer()
     R.keep_samples = keep_samples
+    R.keep_features = keep_features
     rgb, depth, wsum = R(planes, dec, T(scene['origins']), T(scene['dirs']), opts, noise=(T(scene['jitter']), T(scene['u'])))
     loss = (rgb * T(A)).sum() + (depth * T(B)).sum() + (wsum * T(C)).sum()
     loss.backward()
@@ -145,10 +146,12 @@ def test_gradients_without_kept_samples(pkg, name):
     scene, opts, gold, (A, B, C) = load_bwd_case(name)
     _, g_keep = run_backward(pkg, scene, opts, A, B, C, keep_samples=True)
     _, g_eval = run_backward(pkg, scene, opts, A, B, C, keep_samples=False)
-    for g, k in zip(g_eval, ('g_planes', 'g_w1', 'g_b1', 'g_w2', 'g_b2')):
-        assert rel_err(g.cpu().numpy(), gold[k]) < REL, k
-    for a, b in zip(g_keep, g_eval):
-        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 5e-5
+    _, g_half = run_backward(pkg, scene, opts, A, B, C, keep_samples=True, keep_features=False)    # colours kept, features re-gathered
+    for grads in (g_eval, g_half):
+        for g, k in zip(grads, ('g_planes', 'g_w1', 'g_b1', 'g_w2', 'g_b2')):
+            assert rel_err(g.cpu().numpy(), gold[k]) < REL, k
+        for a, b in zip(g_keep, grads):
+            assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 5e-5
 
 
 def test_only_the_requested_gradients_are_computed(pkg):
