@@ -169,3 +169,25 @@ def test_only_the_requested_gradients_are_computed(pkg):
     loss(pkg.ImportanceRenderer()(T(scene['planes']), dec, *args, noise=noise)).backward()
     for got, want in zip((dec.net[0].weight.grad, dec.net[0].bias.grad, dec.net[2].weight.grad, dec.net[2].bias.grad), full[1:]):
         assert rel_err(got.cpu().numpy(), want.cpu().numpy()) < 1e-5
+
+
+def test_gradients_with_disparity_sampling_and_auto_limits(pkg):
+    """The other two coarse-depth branches (VR/renderer.py:174-186): disparity-space sampling against same-device autograd
+    through the torch oracle; per-ray 'auto' limits (no oracle for that branch): the two backward paths (kept samples /
+    re-evaluated samples) must agree and be finite."""
+    n, res, pres, dc, df = 1, 12, 40, 32, 32
+    scene = O.synthetic_scene(57, n, res, pres, dc, df, 0.5)
+    rng = np.random.RandomState(78)
+    A, B, C = (rng.standard_normal((n, res * res, k)).astype(np.float32) for k in (32, 1, 1))
+    opts = dict(O.FFHQ_OPTIONS, depth_resolution=dc, depth_resolution_importance=df, disparity_space_sampling=True)
+    _, grads = run_backward(pkg, scene, opts, A, B, C)
+    _, grads_o = TO.render_grads(T(scene['planes']), TO.decoder_tuple(scene['dec'], dev()), T(scene['origins']), T(scene['dirs']),
+                                 opts, T(scene['jitter']), T(scene['u']), T(A), T(B), T(C))
+    for g, go in zip(grads, grads_o):
+        assert rel_err(g.cpu().numpy(), go.cpu().numpy()) < REL
+    auto = dict(O.FFHQ_OPTIONS, depth_resolution=dc, depth_resolution_importance=df, ray_start='auto', ray_end='auto')
+    _, g1 = run_backward(pkg, scene, auto, A, B, C, keep_samples=True)
+    _, g2 = run_backward(pkg, scene, auto, A, B, C, keep_samples=False)
+    for a, b in zip(g1, g2):
+        assert torch.isfinite(a).all() and a.abs().max() > 0
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 5e-5
