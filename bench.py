@@ -187,6 +187,27 @@ def run_reference(args):
     return 0
 
 
+def bind_to_gpu_numa_node(torch, index):
+    """Pin this process to the CPU cores of the NUMA node its GPU hangs off, so that the pinned host buffers of the e2e path
+    are allocated next to the GPU's PCIe root (torchrun does not bind ranks).  Returns the node, or None if unknown."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        dev = f'{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0'
+        node = int(open(f'/sys/bus/pci/devices/{dev}/numa_node').read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f'/sys/devices/system/node/node{node}/cpulist').read().strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
@@ -214,6 +235,11 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device: the renderer has no CPU path')
+    # stdout carries the ONE JSON line and nothing else: libraries that print there (NCCL's version banner) go to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(torch, local)       # before any pinned allocation: first touch decides the node
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
@@ -371,8 +397,10 @@ def main():
         if train is not None:
             line['train_step'] = train
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)            # the CPU baseline uses every host core
             line['cpu_baseline'], _ = cpu_baseline(48)
-        print(json.dumps(line))
+        line['host_numa_node'] = numa
+        os.write(real_stdout, (json.dumps(line) + '\n').encode())
     if peer is not None:
         peer.close()
     if world > 1:
