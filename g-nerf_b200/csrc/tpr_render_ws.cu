@@ -17,8 +17,9 @@
 //   RAYS step g:              resample(g)  setup(g+2)  sort+composite(g-1)
 // so the importance resampling of group g hides behind the coarse gather of group g+1 and its sort/composite
 // behind the next jobs.  Layer-2 colour outputs stay in TMEM until the group's composite: a pool of 32-column
-// slots (11 in 3xTF32 mode, 12 in bf16 mode) with flow control (a slot is reused only after the composite of
-// the group that owned it); sigma goes through its own 16-column block and is copied to shared memory per tile.
+// slots (12 in 3xTF32 mode, 13 in bf16 mode) with flow control (a slot is reused only after the composite of
+// the group that owned it); sigma is the epilogue's fp32 dot product with the sigma row of layer 2 and goes to shared
+// memory per tile.
 // mbarriers carry every hand-off; nothing per-sample ever touches HBM.
 //
 // Citations relative to /root/reference/g_nerf/ (VR/ = training/volumetric_rendering/).
