@@ -2,14 +2,16 @@
 
 The library is prebuilt for sm_100a by ``build.py``; there is no fallback of any kind: if the
 shared object is missing or fails to load, importing this module's ``lib()`` raises.
+``bench_lib()`` binds the separate measurement library (include/triplane_b200_bench.h: gather / tcgen05.mma
+microbenchmarks, the raw tcgen05 layer test); the renderer never loads it.
 """
 import ctypes
 import os
 from ctypes import c_char_p, c_double, c_float, c_int32, c_int64, c_size_t, c_void_p
 
-from .build import LIB_PATH
+from .build import LIB_PATH, BENCH_LIB_PATH
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MLP_FP32, MLP_BF16, MLP_FFMA = 0, 1, 2
 LAYOUT_CHANNELS_LAST, LAYOUT_CHANNELS_FIRST = 0, 1
 
@@ -19,7 +21,8 @@ class TprOptions(ctypes.Structure):
                 ('depth_resolution', c_int32), ('depth_resolution_importance', c_int32),
                 ('disparity_space_sampling', c_int32), ('white_back', c_int32),
                 ('flags', c_int32), ('tile_width', c_int32), ('plane_sets', c_int32),
-                ('output_layout', c_int32), ('depth_clamp_group', c_int32), ('reserved', c_int32 * 2)]
+                ('output_layout', c_int32), ('depth_clamp_group', c_int32), ('reserved', c_int32),
+                ('density_noise', c_double), ('density_noise_coarse', c_void_p), ('density_noise_fine', c_void_p)]
 
 
 MAX_PEERS, PEER_HANDLE_BYTES = 15, 64
@@ -69,11 +72,19 @@ _SIGNATURES = {
                                         c_size_t, _P]),
     'tpr_unpack_decoder_grad': (ctypes.c_int, [_P, c_float, c_float, c_float, c_float, _P, _P, _P, _P, _P]),
     'tpr_march_backward': (ctypes.c_int, [_P, _P, c_int32, c_int32, _P, _P, _P, _P, _P, _P, c_int32, c_int64, _P, _P, _P]),
+    'tpr_sample_planes': (ctypes.c_int, [_P, c_int64, c_int32, c_int32, _P, c_int64, c_double, _P, _P]),
+    'tpr_add_density_noise': (ctypes.c_int, [_P, _P, c_int64, c_double, _P]),
+    'tpr_sort_samples': (ctypes.c_int, [_P, _P, _P, c_int64, c_int32, c_int32, _P, _P, _P, _P]),
+    'tpr_sample_3dgrid': (ctypes.c_int, [_P, c_int64, c_int32, c_int32, c_int32, c_int32, _P, c_int64, c_int64, _P, _P]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+_BENCH_SIGNATURES = {
     'tpr_gather_microbench': (c_int64, [_P, c_int64, c_int32, c_int32, _P, _P]),
     'tpr_mma_microbench': (ctypes.c_int, [c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     'tpr_gather_microbench_ex': (c_int64, [_P, c_int64, c_int32, c_int32, c_int32, c_int32, _P, _P]),
+    'tpr_debug_tc_decode': (ctypes.c_int, [_P, c_int64, _P, c_int32, _P, _P, _P]),
 }
-EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+BENCH_EXPORTED_SYMBOLS = tuple(_BENCH_SIGNATURES)
 
 _lib = None
 
@@ -96,6 +107,23 @@ def lib() -> ctypes.CDLL:
             raise RuntimeError(f'libtriplane_b200 ABI version {got}, binding expects {ABI_VERSION}: rebuild')
         _lib = handle
     return _lib
+
+
+_bench = None
+
+
+def bench_lib() -> ctypes.CDLL:
+    """The measurement library (bench.py, profiles/, tests/test_gpu_tc_debug.py).  Not used by the renderer."""
+    global _bench
+    if _bench is None:
+        if not os.path.exists(BENCH_LIB_PATH):
+            raise RuntimeError(f'{BENCH_LIB_PATH} is missing: run `python -c "import __graft_entry__ as g; g.build()"`')
+        handle = ctypes.CDLL(BENCH_LIB_PATH)
+        for name, (res, args) in _BENCH_SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _bench = handle
+    return _bench
 
 
 def check(code: int, what: str) -> None:

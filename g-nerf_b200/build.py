@@ -1,5 +1,7 @@
-"""Build libtriplane_b200.so in-tree with nvcc for sm_100a (no JIT cache, no torch extension:
-the library is a plain C-ABI shared object, see include/triplane_b200.h)."""
+"""Build the two C-ABI shared objects in-tree with nvcc for sm_100a (no JIT cache, no torch extension):
+  lib/libtriplane_b200.so        the product: include/triplane_b200.h
+  lib/libtriplane_b200_bench.so  measurement / bring-up aids only (gather and tcgen05.mma microbenchmarks, the raw
+                                 tcgen05 layer test): include/triplane_b200_bench.h.  Never loaded by the renderer."""
 import hashlib
 import os
 import subprocess
@@ -9,8 +11,12 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, 'csrc')
 LIB_DIR = os.path.join(PKG, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libtriplane_b200.so')
-SOURCES = ['triplane_b200.cu', 'tpr_tc_debug.cu', 'tpr_render_tc.cu', 'tpr_render_ws.cu', 'tpr_run_model_ws.cu', 'tpr_microbench.cu', 'tpr_backward.cu']
-HEADERS = [os.path.join(CSRC, 'tpr_device.cuh'), os.path.join(CSRC, 'tpr_render.cuh'), os.path.join(CSRC, 'tpr_tc.cuh'), os.path.join(CSRC, 'tpr_ws.cuh'), os.path.join(ROOT, 'include', 'triplane_b200.h')]
+BENCH_LIB_PATH = os.path.join(LIB_DIR, 'libtriplane_b200_bench.so')
+SOURCES = ['triplane_b200.cu', 'tpr_render_ws.cu', 'tpr_run_model_ws.cu', 'tpr_backward.cu', 'tpr_standalone.cu']
+BENCH_SOURCES = ['tpr_microbench.cu', 'tpr_tc_debug.cu']
+HEADERS = [os.path.join(CSRC, 'tpr_device.cuh'), os.path.join(CSRC, 'tpr_render.cuh'), os.path.join(CSRC, 'tpr_tc.cuh'),
+           os.path.join(CSRC, 'tpr_ws.cuh'), os.path.join(CSRC, 'tpr_host.h'), os.path.join(ROOT, 'include', 'triplane_b200.h'),
+           os.path.join(ROOT, 'include', 'triplane_b200_bench.h')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC']
@@ -27,23 +33,25 @@ def _digest(paths):
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile what changed since the last build (one object per source, compiled in parallel, then linked);
-    return the library path."""
+    """Compile what changed since the last build (one object per source, compiled in parallel, then linked into the
+    product library and the measurement library); return the product library's path."""
     os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    jobs, objs = [], []
-    for src in SOURCES:
-        path = os.path.join(CSRC, src)
-        obj = os.path.join(OBJ_DIR, src[:-3] + '.o')
-        stamp = obj + '.sha256'
-        dig = _digest([path] + HEADERS)
-        objs.append(obj)
-        if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
-            continue
-        cmd = [nvcc] + NVCC_FLAGS + ['-I', os.path.join(ROOT, 'include'), '-I', CSRC] + (['-Xptxas', '-v'] if verbose else []) + \
-              ['-c', path, '-o', obj]
-        jobs.append((src, stamp, dig, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    for src, stamp, dig, proc in jobs:
+    jobs, objs = [], {LIB_PATH: [], BENCH_LIB_PATH: []}
+    for lib, sources in ((LIB_PATH, SOURCES), (BENCH_LIB_PATH, BENCH_SOURCES)):
+        for src in sources:
+            path = os.path.join(CSRC, src)
+            obj = os.path.join(OBJ_DIR, src[:-3] + '.o')
+            stamp = obj + '.sha256'
+            dig = _digest([path] + HEADERS)
+            objs[lib].append(obj)
+            if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+                continue
+            cmd = [nvcc] + NVCC_FLAGS + ['-I', os.path.join(ROOT, 'include'), '-I', CSRC] + \
+                  (['-Xptxas', '-v'] if verbose else []) + ['-c', path, '-o', obj]
+            jobs.append((lib, src, stamp, dig, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    relink = set()
+    for lib, src, stamp, dig, proc in jobs:
         out, _ = proc.communicate()
         if proc.returncode != 0:
             raise RuntimeError(f'nvcc failed on {src}:\n{out}')
@@ -51,11 +59,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(out)
         with open(stamp, 'w') as fh:
             fh.write(dig)
-    if jobs or not os.path.exists(LIB_PATH):
-        res = subprocess.run([nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a'] + objs + ['-o', LIB_PATH],
-                             capture_output=True, text=True)
-        if res.returncode != 0:
-            raise RuntimeError('link failed:\n' + res.stdout + res.stderr)
+        relink.add(lib)
+    for lib, lib_objs in objs.items():
+        # the link stamp catches a changed source LIST (an object dropped from or added to the library)
+        link_stamp = lib + '.sha256'
+        want = ' '.join(sorted(os.path.basename(o) for o in lib_objs))
+        stale = not os.path.exists(link_stamp) or open(link_stamp).read().strip() != want
+        if lib in relink or stale or not os.path.exists(lib):
+            res = subprocess.run([nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a'] + lib_objs + ['-o', lib],
+                                 capture_output=True, text=True)
+            if res.returncode != 0:
+                raise RuntimeError('link failed:\n' + res.stdout + res.stderr)
+            with open(link_stamp, 'w') as fh:
+                fh.write(want)
     return LIB_PATH
 
 

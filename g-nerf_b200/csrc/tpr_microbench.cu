@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "triplane_b200.h"
+#include "triplane_b200_bench.h"
 
 namespace tpr {
 

@@ -31,7 +31,20 @@ struct RenderArgs {
   PeerSinks peers;                       // n > 0: every output store is repeated into these peer buffers
   float* sample_colours; float* sample_sigma;   // training: per-sample colours [rays,S,32] / sigma [rays,S] kept for the backward
   float* sample_features;                       // training: per-sample summed plane features [rays,S,32] (optional)
+  // density_noise > 0 (VR/renderer.py:146): standard-normal draws [rays,Dc] / [rays,Df], added to sigma times density_noise
+  const float* noise_c; const float* noise_f; float density_noise;
 };
+
+// sigma += randn * density_noise (VR/renderer.py:146) for the `count` = nr * Dx samples of a ray group's pass, by `nthreads`
+// cooperating threads; sig rows are S-strided, the noise is laid out like the pass's sigma tensor [N, M*Dx, 1].
+__device__ __forceinline__ void add_density_noise(const RenderArgs& a, const float* __restrict__ noise, float* sig, int S, int off,
+                                                  int Dx, int count, long long ray0, int rstride, int tid, int nthreads) {
+  for (int s = tid; s < count; s += nthreads) {
+    const int r = s / Dx, k = s - r * Dx;
+    const long long g = ray0 + (long long)r * rstride;
+    sig[r * S + off + k] = __fadd_rn(sig[r * S + off + k], __fmul_rn(__ldg(noise + g * Dx + k), a.density_noise));
+  }
+}
 
 // Depth ranges in the scratch block (unsigned words, ordered-uint encoded): [0..1] whole call, then from
 // kRangeSlotOff one (min, max) pair per clamp slot.  Bytes 64..191 hold the optional phase counters.

@@ -382,6 +382,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
       PROF_T0();
       mbar_wait_parked(&bars.csig_ready[gi & 3], (uint32_t)(gi >> 2) & 1u);
       PROF_ADD(13, pl);
+      if (a.noise_c != nullptr) {     // density_noise (VR/renderer.py:146), coarse pass
+        add_density_noise(a, a.noise_c, cx.sig, S, 0, Dc, gg.nr * Dc, gg.ray0, gg.rstride, rtid, kRayThreads);
+        RAY_SYNC();
+      }
       // the uniform draws were staged by other warps in setup(); coarse_ready has completed (the coarse pass ran)
       for (int r = rw; r < gg.nr; r += kRayWarps)
         warp_resample_ray(a, cx.dep + r * S, cx.sig + r * S, wa + r * S, wb + r * S, wc + r * S, cx.dep + r * S + Dc,
@@ -399,6 +403,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
       PROF_T0();
       mbar_wait_parked(nf > 0 ? &bars.fsig_ready[gi & 3] : &bars.csig_ready[gi & 3], (uint32_t)(gi >> 2) & 1u);
       PROF_ADD(15, pl);
+      if (a.noise_c != nullptr) {     // density_noise (VR/renderer.py:146): the pass whose sigma has just arrived
+        if (nf > 0) add_density_noise(a, a.noise_f, cx.sig, S, Dc, Df, gg.nr * Df, gg.ray0, gg.rstride, rtid, kRayThreads);
+        else add_density_noise(a, a.noise_c, cx.sig, S, 0, Dc, gg.nr * Dc, gg.ray0, gg.rstride, rtid, kRayThreads);
+        RAY_SYNC();
+      }
       if (range_slot(a, gg.n) != cur_slot) { range_fold(a, cur_slot, smn, smx, mn, mx, lane); cur_slot = range_slot(a, gg.n); }
       // ---- sort + final march: omega per sample (scattered to original order), depth, weight sum
       // R = 4: two warps per ray share the rank count (pair_rank_scatter); warp rw < 4 then runs the march alone

@@ -7,6 +7,7 @@
 #include <string>
 #include <cuda_bf16.h>
 #include "triplane_b200.h"
+#include "triplane_b200_bench.h"
 #include "tpr_device.cuh"
 #include "tpr_tc.cuh"
 

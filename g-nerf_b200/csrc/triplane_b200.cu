@@ -14,12 +14,10 @@
 #include "triplane_b200.h"
 #include "tpr_device.cuh"
 #include "tpr_render.cuh"
+#include "tpr_host.h"
 
 namespace tpr {
 
-// tensor-core render path (tpr_render_tc.cu)
-int tc_rays_per_group(int Dc, int Df);
-int launch_render_tc(RenderArgs a, int bf16, int sms, int smem_optin, long long n_img, long long n_rays, cudaStream_t st);
 // warp-specialised tensor-core render path (tpr_render_ws.cu)
 int ws_rays_per_group(int Dc, int Df, int bf16);
 bool ws_keeps_samples(int Dc, int Df);
@@ -371,6 +369,11 @@ __global__ void __launch_bounds__(kRenderMaxThreads, 1) render_kernel(const Rend
       // ---- A / C: gather + decode the coarse (pass 0) or fine (pass 1) samples
       tile_pass(a, sm, img, nr, pass == 0 ? Dc : Df, pass == 0 ? 0 : Dc, S);
       __syncthreads();
+      if (a.noise_c != nullptr) {     // density_noise (VR/renderer.py:146)
+        if (pass == 0) add_density_noise(a, a.noise_c, sm.sig, S, 0, Dc, nr * Dc, g0, 1, threadIdx.x, blockDim.x);
+        else add_density_noise(a, a.noise_f, sm.sig, S, Dc, Df, nr * Df, g0, 1, threadIdx.x, blockDim.x);
+        __syncthreads();
+      }
     }
     // ---- D: merge + final march
     for (int r = warp; r < nr; r += nwarps) ray_composite<E>(a, sm, r, g0 + r, (int)n, S, smn, smx);
@@ -527,8 +530,9 @@ __global__ void __launch_bounds__(kPdfWarps * 32) resample_kernel(
 // =======================================================================================
 static thread_local std::string g_err;
 
-static int fail(int code, const char* msg) { g_err = msg; return code; }
-static int cuda_fail(cudaError_t e, const char* what) {
+// (shared with the other translation units through tpr_host.h)
+int fail(int code, const char* msg) { g_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char* what) {
   g_err = std::string(what) + ": " + cudaGetErrorString(e);
   (void)cudaGetLastError();                 // clear the (non-sticky) error so later calls start clean
   return (int)e > 0 ? (int)e : 999;
@@ -539,8 +543,7 @@ static int cuda_fail(cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cuda_fail(e__, what);         \
   } while (0)
 
-struct DeviceInfo { int sms = 0; int smem_optin = 0; bool ok = false; };
-static DeviceInfo device_info() {
+DeviceInfo device_info() {
   static std::mutex mu;
   static DeviceInfo cache[64];
   int dev = 0;
@@ -559,7 +562,7 @@ static int env_int(const char* name, int dflt) {
   return v && *v ? atoi(v) : dflt;
 }
 
-static int grid_for(long long work_items, int per_block, int sms, int waves) {
+int grid_for(long long work_items, int per_block, int sms, int waves) {
   long long blocks = (work_items + per_block - 1) / per_block;
   long long cap = (long long)sms * waves;
   if (blocks > cap) blocks = cap;
@@ -778,6 +781,14 @@ static int render_impl(const float* planes_packed, int64_t n_img, int32_t height
   if (opt->depth_clamp_group < 0) return fail(TPR_E_OPTION, "tpr_render: depth_clamp_group < 0");
   if (opt->output_layout != TPR_LAYOUT_CHANNELS_LAST && opt->output_layout != TPR_LAYOUT_CHANNELS_FIRST)
     return fail(TPR_E_OPTION, "tpr_render: unknown output_layout");
+  // the reference's disparity branch (VR/renderer.py:174-181) divides python floats; with per-ray tensors it fails on shapes
+  if (ray_start_per_ray && opt->disparity_space_sampling)
+    return fail(TPR_E_OPTION, "tpr_render: disparity_space_sampling takes scalar ray limits, not per-ray ('auto') limits");
+  if (!ray_start_per_ray && opt->disparity_space_sampling && !(opt->ray_start > 0.0 && opt->ray_end > 0.0))
+    return fail(TPR_E_OPTION, "tpr_render: disparity_space_sampling needs ray_start > 0 and ray_end > 0");
+  if (opt->density_noise < 0.0) return fail(TPR_E_OPTION, "tpr_render: density_noise < 0");
+  if (opt->density_noise > 0.0 && (!opt->density_noise_coarse || (Df > 0 && !opt->density_noise_fine)))
+    return fail(TPR_E_NULL, "tpr_render: density_noise > 0 needs the standard-normal draws (density_noise_coarse / _fine)");
   DeviceInfo di = device_info();
   if (!di.ok) return fail(TPR_E_DEVICE, "tpr_render: no CUDA device");
 
@@ -793,6 +804,9 @@ static int render_impl(const float* planes_packed, int64_t n_img, int32_t height
   a.plane_sets = opt->plane_sets > 0 ? opt->plane_sets : (int)n_img;
   a.nchw = opt->output_layout == TPR_LAYOUT_CHANNELS_FIRST;
   a.clamp_group = opt->depth_clamp_group;
+  if (opt->density_noise > 0.0) {                                                       // VR/renderer.py:146
+    a.noise_c = opt->density_noise_coarse; a.noise_f = opt->density_noise_fine; a.density_noise = (float)opt->density_noise;
+  }
   const int n_slots = a.clamp_group > 0 ? (int)((n_img + a.clamp_group - 1) / a.clamp_group) : 0;
   a.rgb = rgb; a.depth = depth; a.wsum = weight_sum; a.fine_depths = fine_depths; a.fine_inds = fine_inds;
   a.range_enc = reinterpret_cast<unsigned*>(scratch);
@@ -821,12 +835,10 @@ static int render_impl(const float* planes_packed, int64_t n_img, int32_t height
     TPR_CHECK_LAUNCH("range_init_kernel");
   }
 
-  const bool use_tc = opt->flags != TPR_MLP_FFMA && tc_rays_per_group(Dc, Df) > 0 && !env_int("TPR_FORCE_FFMA", 0);
-  // TPR_RENDER_IMPL: 0 = pick (default), 1 = turn-taking tensor-core kernel, 2 = warp-specialised kernel (A/B runs)
-  const int impl = env_int("TPR_RENDER_IMPL", 0);
+  // Dispatch: the warp-specialised tcgen05 kernel whenever the sample counts fit its TMEM colour-slot pool (every depth
+  // pair any G-NeRF configuration uses), else -- or with TPR_MLP_FFMA -- the fp32 FFMA kernel, which takes any S <= 256.
   bool done = false;
-  if (opt->flags != TPR_MLP_FFMA && impl != 1 && !env_int("TPR_FORCE_FFMA", 0) &&
-      ws_rays_per_group(Dc, Df, opt->flags == TPR_MLP_BF16) > 0) {
+  if (opt->flags != TPR_MLP_FFMA && !env_int("TPR_FORCE_FFMA", 0) && ws_rays_per_group(Dc, Df, opt->flags == TPR_MLP_BF16) > 0) {
     const bool keep = sample_colours && sample_sigma && ws_keeps_samples(Dc, Df) && !a.dbg;
     if (keep) { a.sample_colours = sample_colours; a.sample_sigma = sample_sigma; a.sample_features = sample_features; }   // (only this kernel can keep them)
     int rc = launch_render_ws(a, opt->flags == TPR_MLP_BF16, di.sms, di.smem_optin, n_img, n_rays, st);
@@ -836,12 +848,7 @@ static int render_impl(const float* planes_packed, int64_t n_img, int32_t height
   }
   if (samples_saved) *samples_saved = (done && sample_colours && sample_sigma && ws_keeps_samples(Dc, Df) && !a.dbg) ? 1 : 0;
   const bool kernel_stores_to_peers = done;     // only the warp-specialised kernel has the peer stores in its epilogue
-  if (done) {
-  } else if (use_tc) {
-    // decoder on the tensor cores: 3xTF32 for the fp32 parity mode, bf16 operands for the PSNR mode
-    int rc = launch_render_tc(a, opt->flags == TPR_MLP_BF16, di.sms, di.smem_optin, n_img, n_rays, st);
-    if (rc != 0) return cuda_fail((cudaError_t)rc, "render_tc_kernel");
-  } else {
+  if (!done) {
     void (*kern)(const RenderArgs) = (Dc + Df <= 64) ? render_kernel<2> : (Dc + Df <= 128) ? render_kernel<4> : render_kernel<8>;
     cudaFuncAttributes fa;
     {
@@ -1032,6 +1039,11 @@ int tpr_render_host(const float* planes_host, int64_t n_img, int32_t height, int
   if (opt->depth_clamp_group != 0) return fail(TPR_E_OPTION, "tpr_render_host: depth_clamp_group must be 0");
   const HostWs w = host_ws_layout(n_img, height, width, n_rays);
   if (workspace_bytes < w.total) return fail(TPR_E_SCRATCH, "tpr_render_host: workspace too small");
+  // One caller at a time per process while the pipeline is ENQUEUED: the copy streams and the events are per-device state
+  // shared by every caller.  A cudaStreamWaitEvent captures the event's most recent record at the time of the call, so once
+  // this call's record / wait pairs are enqueued a later caller re-recording the same events cannot disturb them.
+  static std::mutex enqueue_mu;
+  std::lock_guard<std::mutex> enqueue_lock(enqueue_mu);
   HostPipe* hp = host_pipe((int)(2 * n_img + 4));
   if (!hp) return fail(TPR_E_DEVICE, "tpr_render_host: cannot create copy streams / events");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1067,8 +1079,11 @@ int tpr_render_host(const float* planes_host, int64_t n_img, int32_t height, int
     if (rc != 0) return rc;
     TPR_CUDA(cudaEventRecord(ev[1 + b], st), "cudaEventRecord");
     const size_t ro = (size_t)i * n_rays;
+    TprOptions oi = *opt;                          // this image's slice of the density-noise draws
+    if (opt->density_noise > 0.0 && opt->density_noise_coarse) oi.density_noise_coarse = opt->density_noise_coarse + ro * Dc;
+    if (opt->density_noise > 0.0 && opt->density_noise_fine) oi.density_noise_fine = opt->density_noise_fine + ro * Df;
     rc = render_impl(packed, 1, height, width, decoder_packed, d_orig + ro * 3, d_dirs + ro * 3, n_rays, jitter + ro * Dc,
-                     u ? u + ro * Df : nullptr, nullptr, nullptr, opt, d_rgb + ro * TPR_CHANNELS, d_depth + ro, d_wsum + ro,
+                     u ? u + ro * Df : nullptr, nullptr, nullptr, &oi, d_rgb + ro * TPR_CHANNELS, d_depth + ro, d_wsum + ro,
                      nullptr, nullptr, nullptr, 0, ws + w.scratch, 1024, st, i == 0 ? kRangeInit : 0);
     if (rc != 0) return rc;
     TPR_CUDA(cudaEventRecord(ev[5 + 2 * i], st), "cudaEventRecord");

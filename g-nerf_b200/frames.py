@@ -16,16 +16,25 @@ from .volumetric_rendering import renderer as _r
 from .volumetric_rendering.ray_sampler import RaySampler
 
 
-def draw_frame_noise(n_frames, batch, n_rays, dc, df, device):
+def draw_frame_noise(n_frames, batch, n_rays, dc, df, device, density_noise=0.0):
     """jitter [F*P,M,Dc,1] and u [F*P*M,Df] drawn frame by frame in the reference's order: rand[P,M,Dc,1] then rand[P*M,Df]
-    per forward (VR/renderer.py:190,237), straight into the frame's slice of the batch buffers."""
+    per forward (VR/renderer.py:190,237), straight into the frame's slice of the batch buffers.  With density_noise > 0 a
+    forward also draws randn[P,M*Dc,1] after the jitter and randn[P,M*Df,1] after u (VR/renderer.py:146); the tuple then has
+    those two tensors ([F*P,M*Dc,1], [F*P,M*Df,1]) as well."""
     jitter = torch.empty((n_frames * batch, n_rays, dc, 1), device=device, dtype=torch.float32)
     u = torch.empty((n_frames * batch * n_rays, df), device=device, dtype=torch.float32) if df > 0 else None
+    dn = density_noise > 0
+    nz_c = torch.empty((n_frames * batch, n_rays * dc, 1), device=device, dtype=torch.float32) if dn else None
+    nz_f = torch.empty((n_frames * batch, n_rays * df, 1), device=device, dtype=torch.float32) if dn and df > 0 else None
     for f in range(n_frames):
         torch.rand((batch, n_rays, dc, 1), device=device, dtype=torch.float32, out=jitter[f * batch:(f + 1) * batch])
+        if dn:
+            torch.randn((batch, n_rays * dc, 1), device=device, dtype=torch.float32, out=nz_c[f * batch:(f + 1) * batch])
         if df > 0:
             torch.rand(batch * n_rays, df, device=device, out=u[f * batch * n_rays:(f + 1) * batch * n_rays])
-    return jitter, u
+            if dn:
+                torch.randn((batch, n_rays * df, 1), device=device, dtype=torch.float32, out=nz_f[f * batch:(f + 1) * batch])
+    return (jitter, u, nz_c, nz_f) if dn else (jitter, u)
 
 
 def render_frames(renderer, planes, decoder, cam2world, intrinsics, resolution, rendering_options, *,
@@ -68,14 +77,16 @@ def render_frames(renderer, planes, decoder, cam2world, intrinsics, resolution, 
     step = F if not frames_per_call else max(1, int(frames_per_call))
     with torch.cuda.device(dev):
         if noise is None:
-            noise = draw_frame_noise(F, P, m, dc, df, dev)
-        jitter, u = noise
+            noise = draw_frame_noise(F, P, m, dc, df, dev, float(rendering_options.get('density_noise', 0) or 0))
+        jitter, u = noise[0], noise[1]
         for f0 in range(0, F, step):
             f1 = min(F, f0 + step)
             n = (f1 - f0) * P
             o, d = sampler(cam2world[f0:f1].reshape(n, 4, 4).contiguous(), intrinsics[f0:f1].reshape(n, 3, 3).contiguous(), res)
             out = (feat[f0:f1].view(n, 32, m).permute(0, 2, 1), depth[f0:f1].view(n, m, 1), wsum[f0:f1].view(n, m, 1))
             nz = (jitter[f0 * P:f1 * P], u[f0 * P * m:f1 * P * m] if u is not None else None)
+            if len(noise) == 4:
+                nz = nz + (noise[2][f0 * P:f1 * P], noise[3][f0 * P:f1 * P] if noise[3] is not None else None)
             _r.ImportanceRenderer.forward(renderer, pp, decoder, o, d, opts, noise=nz, out=out)
     return {'feature_image': feat, 'depth_image': depth, 'weights_image': wsum}
 

@@ -75,18 +75,22 @@ class _DeviceBlock:
 class PeerGather:
     """Gather buffers of one rank, mapped into every other rank of the node (NVLink / NVSwitch peer access).
 
-    Holds ``sets`` (default 2, used alternately) groups of three buffers -- rgb [world,n,m,32], depth [world,n,m,1],
+    Holds ``sets`` (default 3, used round-robin) groups of three buffers -- rgb [world,n,m,32], depth [world,n,m,1],
     weight_sum [world,n,m,1] -- in ONE peer-mappable allocation (tpr_peer_alloc), exchanges the 64-byte IPC handles
     with ``all_gather_object`` and maps every peer's allocation (tpr_peer_open).  ``sinks(k)`` is the TprPeerSinks
     the render kernel needs to store this rank's slice into every peer; ``views(k)`` are this rank's own buffers.
 
-    Why two sets: rank A's render of step s+1 writes into rank B's buffers while B may still be reading step s.
-    With alternating sets a buffer is rewritten at step s+2, and A can only start that render after B has entered
-    the all-reduce of step s+1, i.e. after B's stream has passed everything B enqueued for step s.  The tensors
-    ``render_sharded`` returns therefore stay valid until the call after the next one.
+    Lifetime of what ``render_sharded`` returns (the tensors ARE the gather buffers, no copy).  Rank A's render of step
+    s+k (k = ``sets``) stores into the set that holds rank B's step-s outputs.  A can only launch that render after its
+    all-reduce of step s+k-1 has completed, which needs B's all-reduce of step s+k-1 to be running on B's stream, i.e.
+    everything B enqueued on that stream BEFORE its call s+k-1 has finished.  So: the outputs of call s may be read by
+    work enqueued (on the stream the calls are made on) before this rank's call s+k-1 -- with the default three sets
+    "until the call after the next one", with two sets only until the next call.  Reads enqueued later race with the
+    peers' NVLink stores and see torn data; ``render_sharded`` therefore refuses fewer than two sets, and callers that
+    keep results longer must clone them.
     """
 
-    def __init__(self, n_local: int, n_rays: int, *, group=None, device=None, sets: int = 2):
+    def __init__(self, n_local: int, n_rays: int, *, group=None, device=None, sets: int = 3):
         import ctypes
         from . import _lib
         if not dist.is_initialized():
@@ -95,6 +99,8 @@ class PeerGather:
         if self.world - 1 > _lib.MAX_PEERS:
             raise RuntimeError(f'PeerGather supports at most {_lib.MAX_PEERS + 1} ranks')
         self.n, self.m, self.sets = int(n_local), int(n_rays), int(sets)
+        if self.sets < 2:
+            raise ValueError('PeerGather needs at least two buffer sets (a peer renders step s+1 into this rank while step s is read)')
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self._step = 0
         self._lib, self._ctypes = _lib, ctypes

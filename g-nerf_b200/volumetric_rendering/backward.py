@@ -41,6 +41,7 @@ class _Render(torch.autograd.Function):
         return rgb, depth, wsum
 
     @staticmethod
+    @torch.autograd.function.once_differentiable          # raw CUDA kernels: a double backward must raise, not detach silently
     def backward(ctx, g_rgb, g_depth, g_wsum):
         packed, dec, origins, dirs, coarse, fine, rng, s_col, s_sig, s_feat = ctx.saved_tensors
         n, m = ctx.shape

@@ -30,6 +30,56 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+def project_onto_planes(planes, coordinates):
+    """plane axes [n_planes,3,3], coordinates [N,M,3] -> projections [N*n_planes,M,2] (VR/renderer.py:39-53): the first two
+    components of the point in each plane's basis.  forward() never calls this (the kernels hard-code the three
+    resulting index pairs); kept because it is a public name of the reference module.  A handful of floats per plane, so
+    it is plain tensor algebra on whatever device the inputs live on."""
+    n, m, _ = coordinates.shape
+    n_planes = planes.shape[0]
+    basis = torch.linalg.inv(planes.to(coordinates))                       # [n_planes,3,3]
+    return torch.einsum('nmc,pcd->npmd', coordinates, basis)[..., :2].reshape(n * n_planes, m, 2)
+
+
+def sample_from_planes(plane_axes, plane_features, coordinates, mode='bilinear', padding_mode='zeros', box_warp=None):
+    """plane_features [N,3,32,H,W] (or PackedPlanes), coordinates [N,M,3] -> [N,3,M,32]: the bilinear lookups on the three
+    planes, not summed (VR/renderer.py:55-65) -- the tensor OSGDecoder.forward takes.  ``plane_axes`` must be the
+    reference's three planes (generate_planes()): the kernel hard-codes their projection."""
+    assert padding_mode == 'zeros'                                          # VR/renderer.py:56
+    if mode != 'bilinear':
+        raise NotImplementedError("sample_from_planes: only mode='bilinear' (what the reference's renderer uses)")
+    if plane_axes is not None and not torch.equal(torch.as_tensor(plane_axes).detach().float().cpu(), generate_planes()):
+        raise NotImplementedError('sample_from_planes: the B200 gather is specialised for the plane axes of generate_planes()')
+    xyz = _require_cuda_f32(coordinates, 'coordinates', (3,))
+    _forbid_autograd(plane_features if isinstance(plane_features, torch.Tensor) else None, xyz)
+    pp = pack_planes(plane_features)
+    n, m, _ = xyz.shape
+    if pp.n_img != n:
+        raise RuntimeError(f'batch mismatch: planes N={pp.n_img}, coordinates N={n}')
+    with torch.cuda.device(xyz.device):
+        out = torch.empty((n, 3, m, 32), device=xyz.device, dtype=torch.float32)
+        _lib.check(_lib.lib().tpr_sample_planes(_ptr(pp.data), n, pp.height, pp.width, _ptr(xyz), m, float(box_warp), _ptr(out),
+                                                _stream()), 'tpr_sample_planes')
+    return out
+
+
+def sample_from_3dgrid(grid, coordinates):
+    """grid [1 or N,C,D,H,W], coordinates [N,P,3] in [-1,1] -> [N,P,C], trilinear with zero padding (VR/renderer.py:67-80;
+    the reference never calls it)."""
+    grid = _require_cuda_f32(grid, 'grid')
+    xyz = _require_cuda_f32(coordinates, 'coordinates', (3,))
+    _forbid_autograd(grid, xyz)
+    if grid.dim() != 5:
+        raise RuntimeError(f'grid must be [1 or N,C,D,H,W], got {tuple(grid.shape)}')
+    n, p, _ = xyz.shape
+    g, c, d, h, w = grid.shape
+    with torch.cuda.device(xyz.device):
+        out = torch.empty((n, p, c), device=xyz.device, dtype=torch.float32)
+        _lib.check(_lib.lib().tpr_sample_3dgrid(_ptr(grid), g, c, d, h, w, _ptr(xyz), n, p, _ptr(out), _stream()),
+                   'tpr_sample_3dgrid')
+    return out
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -119,6 +169,34 @@ def pack_decoder(decoder, *, allow_grad=False) -> torch.Tensor:
     return out
 
 
+def _density_noise(options):
+    dn = float(options.get('density_noise', 0) or 0)                      # options.get('density_noise', 0) > 0, VR/renderer.py:146
+    return dn if dn > 0 else 0.0
+
+
+def _draw_noise(noise, n, m, dc, df, dn, dev):
+    """The forward's random draws, made with the reference's own torch calls in the reference's order so that the CUDA
+    generator advances exactly as the reference advances it: rand_like [N,M,Dc,1] (VR/renderer.py:190), then -- only
+    with density_noise > 0 -- randn_like [N,M*Dc,1] (:146, coarse run_model), rand [N*M,Df] (:237), randn_like
+    [N,M*Df,1] (:146, fine run_model).  ``noise`` = (jitter, u[, coarse noise, fine noise]) overrides them (parity
+    tests feed the oracle and the kernels the same numbers)."""
+    if noise is None:
+        jitter = torch.rand((n, m, dc, 1), device=dev, dtype=torch.float32)
+        nz_c = torch.randn((n, m * dc, 1), device=dev, dtype=torch.float32) if dn > 0 else None
+        u = torch.rand(n * m, df, device=dev) if df > 0 else None
+        nz_f = torch.randn((n, m * df, 1), device=dev, dtype=torch.float32) if dn > 0 and df > 0 else None
+        return jitter, u, nz_c, nz_f
+    jitter = _require_cuda_f32(noise[0], 'noise[0]').reshape(n, m, dc, 1)
+    u = _require_cuda_f32(noise[1], 'noise[1]').reshape(n * m, df) if df > 0 else None
+    nz_c = nz_f = None
+    if dn > 0:
+        if len(noise) < 4:
+            raise RuntimeError('density_noise > 0: noise must be (jitter, u, coarse density noise, fine density noise)')
+        nz_c = _require_cuda_f32(noise[2], 'noise[2]').reshape(n, m * dc, 1)
+        nz_f = _require_cuda_f32(noise[3], 'noise[3]').reshape(n, m * df, 1) if df > 0 else None
+    return jitter, u, nz_c, nz_f
+
+
 def _layout_flag(options):
     mode = options.get('output_layout', 'channels_last')
     if mode == 'channels_last':
@@ -203,8 +281,7 @@ class ImportanceRenderer(torch.nn.Module):
         _forbid_autograd(None if train or not isinstance(planes, torch.Tensor) else planes, ray_origins, ray_directions)
         if opts.get('clamp_mode', None) != 'softplus':
             raise AssertionError('MipRayMarcher only supports `clamp_mode`=`softplus`!')      # VR/ray_marcher.py:35
-        if opts.get('density_noise', 0) > 0:
-            raise NotImplementedError('density_noise > 0 (VR/renderer.py:146) is not supported by the fused renderer')
+        dn = _density_noise(opts)
         pp = self._packed(planes)
         n, m, _ = ray_origins.shape
         # N cameras over N plane sets (the reference's batch), or F*P cameras over P plane sets, camera n sampling
@@ -222,6 +299,10 @@ class ImportanceRenderer(torch.nn.Module):
 
         rs_t = re_t = None
         if opts['ray_start'] == opts['ray_end'] == 'auto':                                # VR/renderer.py:91-97
+            if opts.get('disparity_space_sampling', False):
+                # the reference's disparity branch (VR/renderer.py:174-181) takes python floats; with the per-ray tensors of
+                # the 'auto' branch it dies on a shape mismatch.  Fail as loudly instead of sampling NaN depths.
+                raise RuntimeError("ray_start = ray_end = 'auto' cannot be combined with disparity_space_sampling")
             rs_t, re_t = math_utils.get_ray_limits_box(ray_origins, ray_directions, box_side_length=opts['box_warp'])
             valid = re_t > rs_t
             if torch.any(valid).item():
@@ -234,18 +315,14 @@ class ImportanceRenderer(torch.nn.Module):
             ray_start, ray_end = float(opts['ray_start']), float(opts['ray_end'])
 
         with torch.cuda.device(dev):
-            if noise is None:
-                # same calls, shapes and order as the reference, so the CUDA generator advances identically
-                jitter = torch.rand((n, m, dc, 1), device=dev, dtype=torch.float32)
-                u = torch.rand(n * m, df, device=dev) if df > 0 else None
-            else:
-                jitter = _require_cuda_f32(noise[0], 'noise[0]').reshape(n, m, dc, 1)
-                u = _require_cuda_f32(noise[1], 'noise[1]').reshape(n * m, df) if df > 0 else None
+            jitter, u, nz_c, nz_f = _draw_noise(noise, n, m, dc, df, dn, dev)
             o = _lib.TprOptions(ray_start=ray_start, ray_end=ray_end, box_warp=float(opts['box_warp']),
                                 depth_resolution=dc, depth_resolution_importance=df,
                                 disparity_space_sampling=int(bool(opts.get('disparity_space_sampling', False))),
                                 white_back=int(bool(opts.get('white_back', False))), flags=_mlp_flag(opts),
-                                tile_width=0, plane_sets=pp.n_img, output_layout=layout, depth_clamp_group=clamp_group)
+                                tile_width=0, plane_sets=pp.n_img, output_layout=layout, depth_clamp_group=clamp_group,
+                                density_noise=dn, density_noise_coarse=nz_c.data_ptr() if nz_c is not None else None,
+                                density_noise_fine=nz_f.data_ptr() if nz_f is not None else None)
             if out is None and layout == _lib.LAYOUT_CHANNELS_FIRST:
                 # Memory is [N,32,M] -- the feature image of training/triplane.py:81 -- and the tensor returned is its
                 # [N,M,32] view, so the caller's `permute(0, 2, 1).reshape(N, 32, H, W).contiguous()` is a no-op
@@ -290,6 +367,10 @@ class ImportanceRenderer(torch.nn.Module):
                                               _stream()),
                            'tpr_render_train')
                 saved = (s_col, s_sig, s_feat) if kept.value else None
+                if dn > 0 and saved is None:
+                    raise NotImplementedError('density_noise > 0 with autograd needs the forward to keep its samples '
+                                              '(keep_samples = True and 48+48-class sample counts): the backward would '
+                                              're-evaluate sigma without the noise')
             elif peer_sinks is not None:
                 _lib.check(L.tpr_render_peers(_ptr(pp.data), n, pp.height, pp.width, _ptr(dec), _ptr(ray_origins),
                                               _ptr(ray_directions), m, _ptr(jitter), _ptr(u), _ptr(rs_t), _ptr(re_t),
@@ -309,10 +390,12 @@ class ImportanceRenderer(torch.nn.Module):
                 coarse_d = torch.empty((n * m, dc), device=dev, dtype=torch.float32)
                 _lib.check(L.tpr_sample_stratified(_ptr(jitter), n * m, _ptr(rs_t), _ptr(re_t), ctypes.byref(o), _ptr(coarse_d),
                                                    _stream()), 'tpr_sample_stratified')
+                o.density_noise, o.density_noise_coarse, o.density_noise_fine = 0.0, None, None   # (constants of the graph)
                 aux = dict(packed=pp, dec=dec, coarse=coarse_d, fine=fine_d, range=rng, options=o, saved=saved)
         self.last_depth_range = rng
         self.last_scratch = scratch                    # TPR_PHASE_TIMING=1: int64 phase counters at byte 64
         self.last_fine = (fine_d, fine_i)
+        self._noise_keepalive = (nz_c, nz_f)            # the kernel reads them asynchronously
         return rgb, depth, wsum, aux
 
     # ------------------------------------------------------------------ forward with host buffers
@@ -333,8 +416,7 @@ class ImportanceRenderer(torch.nn.Module):
             raise RuntimeError(f'planes must be [N,3,32,H,W], got {tuple(planes.shape)}')
         if opts.get('clamp_mode', None) != 'softplus':
             raise AssertionError('MipRayMarcher only supports `clamp_mode`=`softplus`!')      # VR/ray_marcher.py:35
-        if opts.get('density_noise', 0) > 0:
-            raise NotImplementedError('density_noise > 0 (VR/renderer.py:146) is not supported by the fused renderer')
+        dn = _density_noise(opts)
         if isinstance(opts['ray_start'], str) or isinstance(opts['ray_end'], str):
             raise NotImplementedError("forward_host supports scalar ray limits only (use forward() for 'auto')")
         n, _, _, h, w = planes.shape
@@ -348,16 +430,13 @@ class ImportanceRenderer(torch.nn.Module):
         df = int(opts['depth_resolution_importance'])
         L = _lib.lib()
         with torch.cuda.device(dev):
-            if noise is None:
-                jitter = torch.rand((n, m, dc, 1), device=dev, dtype=torch.float32)
-                u = torch.rand(n * m, df, device=dev) if df > 0 else None
-            else:
-                jitter = _require_cuda_f32(noise[0], 'noise[0]').reshape(n, m, dc, 1)
-                u = _require_cuda_f32(noise[1], 'noise[1]').reshape(n * m, df) if df > 0 else None
+            jitter, u, nz_c, nz_f = _draw_noise(noise, n, m, dc, df, dn, dev)
             o = _lib.TprOptions(ray_start=float(opts['ray_start']), ray_end=float(opts['ray_end']),
                                 box_warp=float(opts['box_warp']), depth_resolution=dc, depth_resolution_importance=df,
                                 disparity_space_sampling=int(bool(opts.get('disparity_space_sampling', False))),
-                                white_back=int(bool(opts.get('white_back', False))), flags=_mlp_flag(opts), tile_width=0)
+                                white_back=int(bool(opts.get('white_back', False))), flags=_mlp_flag(opts), tile_width=0,
+                                density_noise=dn, density_noise_coarse=nz_c.data_ptr() if nz_c is not None else None,
+                                density_noise_fine=nz_f.data_ptr() if nz_f is not None else None)
             if out is None:
                 out = tuple(torch.empty((n, m, c), dtype=torch.float32).pin_memory() for c in (32, 1, 1))
             for t, c in zip(out, (32, 1, 1)):
@@ -372,7 +451,7 @@ class ImportanceRenderer(torch.nn.Module):
             _lib.check(L.tpr_render_host(_ptr(planes), n, h, w, _ptr(dec), _ptr(ray_origins), _ptr(ray_directions), m,
                                          _ptr(jitter), _ptr(u), ctypes.byref(o), _ptr(out[0]), None if defer_depth else _ptr(out[1]),
                                          _ptr(out[2]), _ptr(rng), _ptr(ws), ws.numel(), _stream()), 'tpr_render_host')
-            self._host_keepalive = (dec, jitter, u, planes, ray_origins, ray_directions)    # until the next call
+            self._host_keepalive = (dec, jitter, u, nz_c, nz_f, planes, ray_origins, ray_directions)    # until the next call
         self.last_depth_range = rng
         self._host_pending = (n, h, w, m, out) if defer_depth else None
         return out
@@ -393,13 +472,13 @@ class ImportanceRenderer(torch.nn.Module):
         return out
 
     # ------------------------------------------------------------------ run_model (VR/renderer.py:142-148)
-    def run_model(self, planes, decoder, sample_coordinates, sample_directions, options, *, want_rgb=True):
+    def run_model(self, planes, decoder, sample_coordinates, sample_directions, options, *, want_rgb=True, sigma_noise=None):
         """``sample_directions`` is accepted and ignored, exactly like OSGDecoder ignores it
-        (training/triplane.py:124-136)."""
+        (training/triplane.py:124-136).  ``options['density_noise'] > 0`` adds ``randn_like(sigma) * density_noise``
+        (VR/renderer.py:146); ``sigma_noise`` [N,P,1] overrides the draw (tests)."""
         xyz = _require_cuda_f32(sample_coordinates, 'sample_coordinates', (3,))
         _forbid_autograd(planes if isinstance(planes, torch.Tensor) else None, xyz)
-        if options.get('density_noise', 0) > 0:
-            raise NotImplementedError('density_noise > 0 (VR/renderer.py:146) is not supported by the fused renderer')
+        dn = _density_noise(options)
         pp = self._packed(planes)
         n, p, _ = xyz.shape
         if pp.n_img != n:
@@ -412,7 +491,33 @@ class ImportanceRenderer(torch.nn.Module):
             _lib.check(_lib.lib().tpr_run_model(_ptr(pp.data), n, pp.height, pp.width, _ptr(dec), _ptr(xyz), p,
                                                 float(options['box_warp']), _ptr(rgb), _ptr(sigma),
                                                 _mlp_flag(options), _stream()), 'tpr_run_model')
+            if dn > 0:
+                nz = (torch.randn((n, p, 1), device=dev, dtype=torch.float32) if sigma_noise is None
+                      else _require_cuda_f32(sigma_noise, 'sigma_noise').reshape(n, p, 1))
+                _lib.check(_lib.lib().tpr_add_density_noise(_ptr(sigma), _ptr(nz), n * p, dn, _stream()), 'tpr_add_density_noise')
         return {'rgb': rgb, 'sigma': sigma}
+
+    # ------------------------------------------------------------------ sort_samples / unify_samples (VR/renderer.py:150-167)
+    def sort_samples(self, all_depths, all_colors, all_densities):
+        """[N,M,S,1], [N,M,S,C], [N,M,S,1] -> the same three tensors with every ray's samples ordered by depth.  forward()
+        never calls this (the sort happens per ray inside the fused kernel); the reference has no caller for it either."""
+        d = _require_cuda_f32(all_depths, 'all_depths')
+        c = _require_cuda_f32(all_colors, 'all_colors')
+        s = _require_cuda_f32(all_densities, 'all_densities')
+        _forbid_autograd(d, c, s)
+        n, m, ns, ch = c.shape
+        if tuple(d.shape) != (n, m, ns, 1) or tuple(s.shape) != (n, m, ns, 1):
+            raise RuntimeError(f'depths / densities must be [{n},{m},{ns},1], got {tuple(d.shape)} / {tuple(s.shape)}')
+        with torch.cuda.device(d.device):
+            ds, cs, ss = torch.empty_like(d), torch.empty_like(c), torch.empty_like(s)
+            _lib.check(_lib.lib().tpr_sort_samples(_ptr(d), _ptr(c), _ptr(s), n * m, ns, ch, _ptr(ds), _ptr(cs), _ptr(ss),
+                                                   _stream()), 'tpr_sort_samples')
+        return ds, cs, ss
+
+    def unify_samples(self, depths1, colors1, densities1, depths2, colors2, densities2):
+        """Concatenate the coarse and the importance samples of every ray and order them by depth (VR/renderer.py:157-167)."""
+        return self.sort_samples(torch.cat([depths1, depths2], dim=-2), torch.cat([colors1, colors2], dim=-2),
+                                 torch.cat([densities1, densities2], dim=-2))
 
     # ------------------------------------------------------------------ the remaining public helpers
     def sample_stratified(self, ray_origins, ray_start, ray_end, depth_resolution, disparity_space_sampling=False, *,

@@ -17,7 +17,8 @@
  *     synchronises the device, and is re-entrant across host threads and streams;
  *   - return value: 0 = success, < 0 = argument error (TPR_E_*), > 0 = a cudaError_t from the
  *     launch; tpr_last_error() returns a thread-local message for the last non-zero return.
- *   - forward only: there is no backward pass.
+ *   - forward AND backward: tpr_render / tpr_render_train are the forward, tpr_render_backward the gradient with respect
+ *     to the planes and the decoder (the reference gets it from autograd).
  */
 #ifndef TRIPLANE_B200_H_
 #define TRIPLANE_B200_H_
@@ -29,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TPR_ABI_VERSION 6
+#define TPR_ABI_VERSION 7
 
 /* fixed by the reference model: OSGDecoder(32 -> 64 -> 1+32), three planes
  * (training/triplane.py:42,113-122; VR/renderer.py:29-37) */
@@ -78,7 +79,14 @@ typedef struct TprOptions {
   int32_t depth_clamp_group;     /* 0: the depth clamp (VR/ray_marcher.py:50) uses the range of ALL sample depths of the call,
                                     like one reference forward.  k > 0: every k consecutive images clamp against their own
                                     range (k = the batch of one reference forward when several forwards are batched) */
-  int32_t reserved[2];
+  int32_t reserved;
+  /* options.get('density_noise', 0) (VR/renderer.py:146): sigma += randn_like(sigma) * density_noise after each of the two
+   * point queries.  The draws are the caller's, like jitter and u: density_noise_coarse [N,M*Dc] then density_noise_fine
+   * [N,M*Df] (device pointers, standard normal; the host shim draws them with the reference's torch.randn_like calls in the
+   * reference's order: jitter, coarse noise, u, fine noise).  Both ignored (may be NULL) when density_noise == 0. */
+  double density_noise;
+  const float* density_noise_coarse;
+  const float* density_noise_fine;
 } TprOptions;
 
 /* output_layout */
@@ -198,8 +206,10 @@ int tpr_render_peers(const float* planes_packed, int64_t n_img, int32_t height, 
  * image i-1 overlap.  `workspace` is a DEVICE buffer of tpr_render_host_workspace_bytes() bytes.
  * Asynchronous like every other entry: the outputs are complete when `stream` has drained.
  * depth_range_io: DEVICE [2], receives the global depth range (may be NULL unless depth_host is NULL, see
- * tpr_render_host_depth).  opt->cameras_per_plane_set must be 0 or 1
- * (every image brings its own planes across PCIe). */
+ * tpr_render_host_depth).  opt->plane_sets must be 0 (or n_img) and opt->depth_clamp_group 0:
+ * every image brings its own planes across PCIe and the call clamps against one range, like one reference forward.
+ * Calls on one device are serialised inside the library while they ENQUEUE (they share the two copy streams); the enqueued
+ * work of different callers' streams still overlaps. */
 size_t tpr_render_host_workspace_bytes(int64_t n_img, int32_t height, int32_t width, int64_t n_rays);
 int tpr_render_host(const float* planes_host, int64_t n_img, int32_t height, int32_t width,
                     const float* decoder_packed,
@@ -245,6 +255,27 @@ int tpr_sample_stratified(const float* jitter, int64_t n_rays, const float* ray_
 /* ---- a14: math_utils.get_ray_limits_box (VR/math_utils.py:46-98) ------------------------ */
 int tpr_ray_limits_box(const float* origins, const float* dirs, int64_t n_rays,
                        float box_side_length, float* t_min, float* t_max, void* stream);
+
+/* ---- a4 stand-alone: sample_from_planes (VR/renderer.py:55-65) ------------------------------------------------ */
+/* xyz [N,P,3] -> features [N,3,P,32]: the three bilinear plane lookups of every point, NOT summed (what the reference hands
+ * to OSGDecoder.forward; tpr_decode takes exactly this tensor).  grid_sample(bilinear, zeros, align_corners=False). */
+int tpr_sample_planes(const float* planes_packed, int64_t n_img, int32_t height, int32_t width, const float* xyz,
+                      int64_t n_pts, double box_warp, float* features, void* stream);
+
+/* ---- a8: the density_noise term of run_model (VR/renderer.py:146): sigma[i] += noise[i] * density_noise ---------------- */
+int tpr_add_density_noise(float* sigma, const float* noise, int64_t n, double density_noise, void* stream);
+
+/* ---- a12 / a15 stand-alone: unify_samples / sort_samples (VR/renderer.py:150-167) ---------------------------------- */
+/* Sort every ray's samples by depth and carry colours and densities along: depths [R,S], colours [R,S,C], densities [R,S]
+ * -> *_sorted of the same shapes (ties keep their input order).  S <= TPR_MAX_SAMPLES. */
+int tpr_sort_samples(const float* depths, const float* colours, const float* densities, int64_t n_rays, int32_t n_samples,
+                     int32_t n_channels, float* depths_sorted, float* colours_sorted, float* densities_sorted, void* stream);
+
+/* ---- a15: sample_from_3dgrid (VR/renderer.py:67-80; no caller in the reference) ------------------------------------ */
+/* grid [G,C,D,H,W] with G == 1 (shared by the whole batch) or G == N; coords [N,P,3] as (x, y, z) in [-1,1], x walking W,
+ * y walking H, z walking D -> features [N,P,C]: trilinear, zero padding, align_corners=False. */
+int tpr_sample_3dgrid(const float* grid, int64_t n_grids, int32_t channels, int32_t depth, int32_t height, int32_t width,
+                      const float* coords, int64_t n_batch, int64_t n_pts, float* features, void* stream);
 
 /* ---- backward of a13 (the reference gets it from autograd, used by
  *      training/training_loop.py:335,377) ------------------------------------------------------------------------- */
@@ -293,25 +324,6 @@ int tpr_unpack_decoder_grad(const float* g_decoder_packed, float w1_gain, float 
 int tpr_march_backward(const float* depths_coarse, const float* depths_fine, int32_t dc, int32_t df, const float* sigma,
                        const float* colours, const float* g_rgb, const float* g_depth, const float* g_weight_sum,
                        const float* depth_range, int32_t white_back, int64_t n_rays_total, float* g_sigma, float* omega,
-                       void* stream);
-
-/* ---- measurement aid: the gather roofline ------------------------- */
-/* Fetches random 128-byte lines of buf[n_lines*32 floats] with the render kernels' access shape (8 lanes x
- * 16 bytes per line, 12 lines in flight per thread) from `ctas` CTAs of 512 threads, `iters` rounds each.
- * sink: 65536 floats.  Returns the number of lines fetched (> 0) or a negative error.  The caller times
- * it with CUDA events; lines * 128 B / time is the L2 (small buffer) or DRAM (large buffer) gather bandwidth
- * bench.py reports beside the HBM copy peak. */
-int64_t tpr_gather_microbench(const float* buf, int64_t n_lines, int32_t ctas, int32_t iters, float* sink,
-                              void* stream);
-/* same with the CTA size (multiple of 32, <= 1024) and the lines in flight per thread (4, 6, 12 or 24) chosen
- * by the caller; sink: 65536 floats */
-int64_t tpr_gather_microbench_ex(const float* buf, int64_t n_lines, int32_t ctas, int32_t threads,
-                                 int32_t in_flight, int32_t iters, float* sink, void* stream);
-
-/* Issues `count` tcgen05.mma (M = 128, N = n, one K step; tf32 or bf16 operands; A from shared memory or TMEM)
- * from one thread of one CTA; tight != 0 issues them from precomputed descriptors (count % 4 == 0).
- * out_dev[0] = cycles spent issuing, out_dev[1] = cycles until all have completed. */
-int tpr_mma_microbench(int32_t n, int32_t bf16, int32_t a_from_tmem, int32_t count, int32_t tight, long long* out_dev,
                        void* stream);
 
 #ifdef __cplusplus

@@ -192,10 +192,80 @@ def decode(features: np.ndarray, dec: DecoderParams):
     return rgb.astype(F32), out[..., 0:1].astype(F32)
 
 
-def run_model(planes, dec: DecoderParams, xyz, box_warp: float):
-    """a8: ImportanceRenderer.run_model (VR/renderer.py:142-148) without
-    density noise (no G-NeRF config sets it)."""
-    return decode(gather_planes(planes, xyz, box_warp), dec)
+def run_model(planes, dec: DecoderParams, xyz, box_warp: float, density_noise: float = 0.0, sigma_noise=None):
+    """a8: ImportanceRenderer.run_model (VR/renderer.py:142-148).  ``sigma_noise`` [N,P,1] stands for the
+    torch.randn_like draw of :146 (only read when density_noise > 0)."""
+    rgb, sigma = decode(gather_planes(planes, xyz, box_warp), dec)
+    if density_noise > 0:
+        sigma = (sigma + np.asarray(sigma_noise, F32).reshape(sigma.shape) * F32(density_noise)).astype(F32)
+    return rgb, sigma
+
+
+# --------------------------------------------------------------------------
+# a14. get_ray_limits_box                                 VR/math_utils.py:46-98
+# --------------------------------------------------------------------------
+def ray_limits_box(origins: np.ndarray, dirs: np.ndarray, box_side_length: float):
+    """origins / dirs [...,3] -> (t_min [...,1], t_max [...,1]): slab test against the cube of side
+    ``box_side_length`` centred on the origin, x then y then z; rays that miss get (-1, -2)."""
+    o = np.asarray(origins, F32).reshape(-1, 3)
+    d = np.asarray(dirs, F32).reshape(-1, 3)
+    half = F32(box_side_length / 2)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        inv = (F32(1) / d).astype(F32)
+        neg = inv < 0
+        near = np.where(neg, half, -half).astype(F32)          # the bound hit first along each axis
+        far = np.where(neg, -half, half).astype(F32)
+        t0 = ((near - o) * inv).astype(F32)
+        t1 = ((far - o) * inv).astype(F32)
+        valid = np.ones(o.shape[0], bool)
+        tmin, tmax = t0[:, 0], t1[:, 0]
+        for ax in (1, 2):
+            valid &= ~((tmin > t1[:, ax]) | (t0[:, ax] > tmax))
+            tmin, tmax = np.maximum(tmin, t0[:, ax]), np.minimum(tmax, t1[:, ax])
+    tmin = np.where(valid, tmin, F32(-1)).astype(F32)
+    tmax = np.where(valid, tmax, F32(-2)).astype(F32)
+    shape = tuple(np.asarray(origins).shape[:-1]) + (1,)
+    return tmin.reshape(shape), tmax.reshape(shape)
+
+
+def auto_ray_limits(origins: np.ndarray, dirs: np.ndarray, box_warp: float):
+    """The 'auto' branch of forward (VR/renderer.py:91-96): box limits per ray; rays that miss the box get
+    ray_start = min and ray_end = MAX OF THE VALID ray_starts (sic, :95-96).  -> ([N,M,1], [N,M,1])."""
+    rs, re = ray_limits_box(origins, dirs, box_warp)
+    valid = re > rs
+    if valid.any():
+        lo, hi = rs[valid].min(), rs[valid].max()
+        rs = np.where(valid, rs, lo).astype(F32)
+        re = np.where(valid, re, hi).astype(F32)
+    return rs, re
+
+
+# --------------------------------------------------------------------------
+# a15. sample_from_3dgrid (dead code in the reference)    VR/renderer.py:67-80
+# --------------------------------------------------------------------------
+def sample_from_3dgrid(grid: np.ndarray, coords: np.ndarray) -> np.ndarray:
+    """grid [1 or N,C,D,H,W], coords [N,P,3] (x -> W, y -> H, z -> D) -> [N,P,C]: trilinear, zeros padding,
+    align_corners=False (5-D grid_sample)."""
+    grid, coords = np.asarray(grid, F32), np.asarray(coords, F32)
+    n, p, _ = coords.shape
+    g, c, dd, hh, ww = grid.shape
+    out = np.zeros((n, p, c), np.float64)
+    pos = [((coords[..., k] + 1) * size - 1) / 2 for k, size in enumerate((ww, hh, dd))]
+    base = [np.floor(q) for q in pos]
+    for corner in range(8):
+        off = [(corner >> k) & 1 for k in range(3)]
+        idx = [b.astype(np.int64) + o for b, o in zip(base, off)]
+        wt = np.ones((n, p), np.float64)
+        for q, b, o in zip(pos, base, off):
+            wt *= (q - b) if o else (1 - (q - b))
+        ok = np.ones((n, p), bool)
+        for i, size in zip(idx, (ww, hh, dd)):
+            ok &= (i >= 0) & (i < size)
+        xi, yi, zi = (np.clip(i, 0, size - 1) for i, size in zip(idx, (ww, hh, dd)))
+        for b in range(n):
+            v = grid[0 if g == 1 else b][:, zi[b], yi[b], xi[b]].T          # [P,C]
+            out[b] += np.where(ok[b][:, None], v * wt[b][:, None], 0.0)
+    return out.astype(F32)
 
 
 # --------------------------------------------------------------------------
@@ -355,11 +425,12 @@ def unify_samples(d1, c1, s1, d2, c2, s2):
 # a13. ImportanceRenderer.forward                          VR/renderer.py:88-140
 # --------------------------------------------------------------------------
 def render(planes, dec: DecoderParams, origins, dirs, options: dict,
-           jitter: np.ndarray, u: np.ndarray, return_stages: bool = False):
+           jitter: np.ndarray, u: np.ndarray, return_stages: bool = False, density_noise_draws=None):
     """Full forward with the two random draws supplied by the caller:
     ``jitter`` [N,M,Dc,1] stands for torch.rand_like at VR/renderer.py:190 and
-    ``u`` [N*M,Df] for torch.rand at :237.  Scalar ray limits only (the 'auto'
-    branch, :91-97, is not used by any G-NeRF config).
+    ``u`` [N*M,Df] for torch.rand at :237.  ray_start == ray_end == 'auto' takes the
+    per-ray box limits (:91-97).  options['density_noise'] > 0 (:146) reads
+    ``density_noise_draws`` = (coarse [N,M*Dc,1], fine [N,M*Df,1]), the torch.randn_like draws.
 
     Returns (rgb [N,M,32], depth [N,M,1], weight_sum [N,M,1]) like :140.
     """
@@ -367,12 +438,19 @@ def render(planes, dec: DecoderParams, origins, dirs, options: dict,
     n, m, _ = origins.shape
     bw = options['box_warp']
     white = bool(options.get('white_back', False))
+    dn = float(options.get('density_noise', 0) or 0)
+    nz_c, nz_f = density_noise_draws if dn > 0 else (None, None)
     assert options.get('clamp_mode', 'softplus') == 'softplus'       # ray_marcher.py:32-35
-    d_c = stratified_depths(jitter, options['ray_start'], options['ray_end'],
-                            options.get('disparity_space_sampling', False))
+    if isinstance(options['ray_start'], str):
+        assert options['ray_start'] == options['ray_end'] == 'auto'
+        rs, re = auto_ray_limits(origins, dirs, bw)
+        d_c = stratified_depths_per_ray(jitter, rs, re)
+    else:
+        d_c = stratified_depths(jitter, options['ray_start'], options['ray_end'],
+                                options.get('disparity_space_sampling', False))
     dc = d_c.shape[2]
     xyz = (origins[:, :, None, :] + d_c * dirs[:, :, None, :]).reshape(n, -1, 3)
-    rgb_c, sig_c = run_model(planes, dec, xyz, bw)
+    rgb_c, sig_c = run_model(planes, dec, xyz, bw, dn, nz_c)
     rgb_c, sig_c = rgb_c.reshape(n, m, dc, -1), sig_c.reshape(n, m, dc, 1)
     stages = {'depths_coarse': d_c, 'rgb_coarse': rgb_c, 'sigma_coarse': sig_c}
     df = int(options.get('depth_resolution_importance', 0))
@@ -380,7 +458,7 @@ def render(planes, dec: DecoderParams, origins, dirs, options: dict,
         _, _, w_c = march(rgb_c, sig_c, d_c, white)
         d_f, inds = sample_importance(d_c, w_c, u)
         xyz = (origins[:, :, None, :] + d_f * dirs[:, :, None, :]).reshape(n, -1, 3)
-        rgb_f, sig_f = run_model(planes, dec, xyz, bw)
+        rgb_f, sig_f = run_model(planes, dec, xyz, bw, dn, nz_f)
         rgb_f, sig_f = rgb_f.reshape(n, m, df, -1), sig_f.reshape(n, m, df, 1)
         d_all, c_all, s_all = unify_samples(d_c, rgb_c, sig_c, d_f, rgb_f, sig_f)
         rgb, depth, w = march(c_all, s_all, d_all, white)

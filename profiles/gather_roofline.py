@@ -7,7 +7,7 @@ pkg = importlib.import_module('g-nerf_b200')
 
 
 def measure(mbytes, ctas=296, threads=512, in_flight=12, iters=400, reps=4):
-    L = pkg._lib.lib()
+    L = pkg._lib.bench_lib()
     n_lines = mbytes * (1 << 20) // 128
     buf = torch.randn(n_lines * 32, device='cuda')
     sink = torch.empty(65536, device='cuda')

@@ -3,7 +3,7 @@ import ctypes, importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 pkg = importlib.import_module('g-nerf_b200')
-L = pkg._lib.lib()
+L = pkg._lib.bench_lib()
 out = torch.zeros(2, dtype=torch.int64, device='cuda')
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 print('issue  kind  A-from  N    count  issue cyc/MMA  total cyc/MMA')

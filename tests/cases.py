@@ -1,5 +1,5 @@
-"""Golden cases shared by the CPU (oracle vs reference fixtures) and GPU (kernels vs oracle) tests.
-Must stay in sync with tests/golden/make_golden.py:CASES (the fixtures were generated from it)."""
+"""Golden cases shared by the CPU (oracle vs reference fixtures) and GPU (kernels vs oracle) tests and by
+tests/golden/make_golden.py, which generated the fixtures from them."""
 import os
 
 import numpy as np
@@ -21,7 +21,54 @@ CASES = {
     'inference_96': (17, 1, 12, 48, 96, 96, 0.5, {}),
     'mid_64':       (18, 1, 10, 40, 64, 64, 0.5, {}),
     'uneven_96_40': (19, 1, 8, 32, 96, 40, 0.5, {}),
+    # the 'auto' ray limits (VR/renderer.py:91-97 + math_utils.get_ray_limits_box): a box small enough that the outer rays miss it
+    'auto_limits':  (24, 2, 12, 48, 32, 32, 0.5, {'ray_start': 'auto', 'ray_end': 'auto', 'box_warp': 0.5}),
+    # density_noise (VR/renderer.py:146): sigma += randn_like(sigma) * density_noise after each point query
+    'density_noise': (25, 1, 10, 40, 24, 24, 0.5, {'density_noise': 0.5}),
 }
+
+
+def density_noise_draws(name):
+    """The standard-normal draws that stand for torch.randn_like at VR/renderer.py:146 in a density_noise case:
+    (coarse [N,M*Dc,1], fine [N,M*Df,1], run_model points [N,257,1])."""
+    seed, n, res, _, dc, df, _, _ = CASES[name]
+    rng = np.random.RandomState(seed + 3000)
+    m = res * res
+    return (rng.standard_normal((n, m * dc, 1)).astype(np.float32), rng.standard_normal((n, m * df, 1)).astype(np.float32),
+            rng.standard_normal((n, 257, 1)).astype(np.float32))
+
+
+# the cases the scalar-limits-only restatements (oracle/torch_oracle.py, oracle/triplane_oracle.c) cover
+SCALAR_CASES = [n for n, c in CASES.items() if not isinstance(c[7].get('ray_start', 0.0), str) and not c[7].get('density_noise', 0)]
+
+
+def case_noise(name, scene):
+    """The random draws of a case as the tuple ImportanceRenderer.forward(noise=...) takes (numpy arrays)."""
+    if CASES[name][7].get('density_noise', 0) > 0:
+        nz_c, nz_f, _ = density_noise_draws(name)
+        return scene['jitter'], scene['u'], nz_c, nz_f
+    return scene['jitter'], scene['u']
+
+
+def oracle_render(name, scene, opts, origins=None, dirs=None, return_stages=True):
+    draws = density_noise_draws(name)[:2] if opts.get('density_noise', 0) > 0 else None
+    return O.render(scene['planes'], scene['dec'], scene['origins'] if origins is None else origins,
+                    scene['dirs'] if dirs is None else dirs, opts, scene['jitter'], scene['u'], return_stages=return_stages,
+                    density_noise_draws=draws)
+
+
+def coarse_depths(scene, opts):
+    """The case's coarse depths [N,M,Dc,1] (VR/renderer.py:169-192), whichever branch its options select."""
+    if isinstance(opts['ray_start'], str):
+        return O.stratified_depths_per_ray(scene['jitter'], *O.auto_ray_limits(scene['origins'], scene['dirs'], opts['box_warp']))
+    return O.stratified_depths(scene['jitter'], opts['ray_start'], opts['ray_end'], opts.get('disparity_space_sampling', False))
+
+
+def depth_peak(opts, gold):
+    """Peak value for a depth PSNR: ray_end - ray_start, or the spread of the fixture's depths with 'auto' limits."""
+    if isinstance(opts['ray_start'], str):
+        return float(gold['depth'].max() - gold['depth'].min())
+    return opts['ray_end'] - opts['ray_start']
 
 
 def load_case(name):

@@ -31,15 +31,18 @@ from training.triplane import OSGDecoder                                  # noqa
 
 
 @contextlib.contextmanager
-def injected_noise(jitter, u):
-    """Make the next torch.rand_like / torch.rand return the seeded draws."""
-    real_rand_like, real_rand = torch.rand_like, torch.rand
+def injected_noise(jitter, u, normal_draws=()):
+    """Make the next torch.rand_like / torch.rand return the seeded draws; successive torch.randn_like calls (the
+    density_noise term, VR/renderer.py:146) return ``normal_draws`` in order."""
+    real_rand_like, real_rand, real_randn_like = torch.rand_like, torch.rand, torch.randn_like
+    pending = list(normal_draws)
     torch.rand_like = lambda t, *a, **k: torch.from_numpy(jitter).reshape(t.shape).clone()
     torch.rand = lambda *a, **k: torch.from_numpy(u).clone()
+    torch.randn_like = lambda t, *a, **k: torch.from_numpy(pending.pop(0)).reshape(t.shape).clone()
     try:
         yield
     finally:
-        torch.rand_like, torch.rand = real_rand_like, real_rand
+        torch.rand_like, torch.rand, torch.randn_like = real_rand_like, real_rand, real_randn_like
 
 
 def ref_decoder(dec: O.DecoderParams) -> OSGDecoder:
@@ -52,20 +55,7 @@ def ref_decoder(dec: O.DecoderParams) -> OSGDecoder:
     return m.requires_grad_(False)
 
 
-CASES = {
-    # name: (seed, n_img, res, plane_res, dc, df, bias_scale, extra options)
-    'ffhq_small':  (11, 2, 16, 64, 48, 48, 0.5, {}),
-    'white_back':  (12, 1, 12, 32, 24, 24, 0.5, {'white_back': True}),
-    'ragged':      (13, 1, 9, 48, 20, 13, 0.5, {}),
-    'disparity':   (14, 1, 8, 32, 32, 32, 0.0, {'disparity_space_sampling': True}),
-    'coarse_only': (15, 1, 8, 32, 32, 0, 0.5, {}),
-    'wide_box':    (16, 1, 10, 40, 16, 16, 0.5, {'box_warp': 0.6}),   # many out-of-plane taps
-    # R = 4 ray groups of the warp-specialised kernel (more than 64 samples per pass): the gen_videos.py:127-128 depths,
-    # and two shapes that exercise the pair rank count with 2 / 3 purely-coarse rows
-    'inference_96': (17, 1, 12, 48, 96, 96, 0.5, {}),
-    'mid_64':       (18, 1, 10, 40, 64, 64, 0.5, {}),
-    'uneven_96_40': (19, 1, 8, 32, 96, 40, 0.5, {}),
-}
+from tests.cases import CASES, density_noise_draws                      # noqa: E402
 
 
 def run_case(name):
@@ -98,18 +88,32 @@ def run_case(name):
         cap['inds'] = out.numpy().copy()
         return out
     torch.searchsorted = ss
+    noisy = opts.get('density_noise', 0) > 0
+    nz_c, nz_f, nz_p = density_noise_draws(name) if noisy else (None, None, None)
     try:
-        with injected_noise(sc['jitter'], sc['u']):
+        with injected_noise(sc['jitter'], sc['u'], [nz_c, nz_f] if noisy else []):
             rgb, depth, wsum = R(t(sc['planes']), dec, ro, rd, opts)
     finally:
         torch.searchsorted = real_ss
     # --- run_model on scattered points (some outside the box)
     rng = np.random.RandomState(seed + 1000)
     pts = (rng.random_sample((n, 257, 3)).astype(np.float32) - 0.5) * 1.3 * opts['box_warp']
-    rm = ImportanceRenderer().run_model(t(sc['planes']), dec, t(pts), None, opts)
+    with injected_noise(sc['jitter'], sc['u'], [nz_p] if noisy else []):
+        rm = ImportanceRenderer().run_model(t(sc['planes']), dec, t(pts), None, opts)
     out = dict(origins=ro.numpy(), dirs=rd.numpy(), rgb=rgb.numpy(), depth=depth.numpy(),
                wsum=wsum.numpy(), pts=pts, pts_rgb=rm['rgb'].numpy(), pts_sigma=rm['sigma'].numpy())
     out.update(cap)
+    if opts['ray_start'] == 'auto':
+        # a14: the box limits themselves (VR/math_utils.py:46-98), plus a second set of rays aimed at and past a unit box
+        from training.volumetric_rendering import math_utils as MU
+        tmin, tmax = MU.get_ray_limits_box(ro, rd, box_side_length=opts['box_warp'])
+        brng = np.random.RandomState(seed + 2000)
+        bo = (brng.standard_normal((3, 97, 3)) * 1.2).astype(np.float32)
+        bd = brng.standard_normal((3, 97, 3)).astype(np.float32)
+        bd /= np.linalg.norm(bd, axis=-1, keepdims=True)
+        bmin, bmax = MU.get_ray_limits_box(t(bo), t(bd), box_side_length=1.0)
+        out.update(box_tmin=tmin.numpy(), box_tmax=tmax.numpy(), box2_origins=bo, box2_dirs=bd, box2_tmin=bmin.numpy(),
+                   box2_tmax=bmax.numpy())
     # --- stand-alone marcher on random inputs
     s = 17
     mc, ms = rng.random_sample((1, 33, s, 32)).astype(np.float32), rng.standard_normal((1, 33, s, 1)).astype(np.float32) * 3
@@ -124,8 +128,9 @@ def main():
     for name in (sys.argv[1:] or CASES):      # optional: only the named cases
         sc, opts, out = run_case(name)
         # cross-check the numpy oracle against the reference before committing
+        draws = density_noise_draws(name)[:2] if opts.get('density_noise', 0) > 0 else None
         (rgb, depth, wsum), st = O.render(sc['planes'], sc['dec'], sc['origins'], sc['dirs'], opts,
-                                          sc['jitter'], sc['u'], return_stages=True)
+                                          sc['jitter'], sc['u'], return_stages=True, density_noise_draws=draws)
         err = {k: float(np.abs(a - out[k]).max()) for k, a in
                dict(rgb=rgb, depth=depth, wsum=wsum, origins=sc['origins'], dirs=sc['dirs']).items()}
         if 'inds' in out:

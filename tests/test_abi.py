@@ -27,12 +27,12 @@ def test_library_exports_every_declared_symbol(pkg):
     for s in header_symbols():
         assert hasattr(lib, s), f'{s} declared in the header but not exported'
     assert set(header_symbols()) == set(pkg._lib.EXPORTED_SYMBOLS), 'binding and header disagree'
-    assert lib.tpr_abi_version() == 6
+    assert lib.tpr_abi_version() == 7
 
 
 def test_options_struct_layout_matches_header(pkg):
-    # 3 doubles + 9 int32 + 2 reserved int32 = 68 -> padded to 72 (8-byte alignment)
-    assert ctypes.sizeof(pkg._lib.TprOptions) == 72
+    # 3 doubles + 10 int32 (= 64) + density_noise double + its two draw pointers
+    assert ctypes.sizeof(pkg._lib.TprOptions) == 88
 
 
 def test_peer_sinks_struct_layout_matches_header(pkg):
@@ -89,3 +89,32 @@ def test_host_shim_rejects_cpu_tensors_and_bad_decoders(pkg):
         pkg.pack_decoder(torch.nn.Linear(32, 33))
     assert sorted(dec.state_dict()) == ['net.0.bias', 'net.0.weight', 'net.2.bias', 'net.2.weight']
     assert R.plane_axes.shape == (3, 3, 3) and len(list(R.parameters())) == 0
+
+
+def test_reference_module_names_are_importable(pkg):
+    """every public name of the reference's renderer module exists here too."""
+    from importlib import import_module
+    r = import_module('g-nerf_b200.volumetric_rendering.renderer')
+    for name in ('generate_planes', 'project_onto_planes', 'sample_from_planes', 'sample_from_3dgrid', 'ImportanceRenderer'):
+        assert callable(getattr(r, name)), name
+    for name in ('forward', 'run_model', 'sort_samples', 'unify_samples', 'sample_stratified', 'sample_importance', 'sample_pdf'):
+        assert callable(getattr(r.ImportanceRenderer, name)), name
+    import torch
+    axes = r.generate_planes()
+    xyz = torch.tensor([[[0.1, 0.2, 0.3]]])
+    got = r.project_onto_planes(axes, xyz)                       # plane 0 <- (x,y), 1 <- (x,z), 2 <- (z,x)
+    torch.testing.assert_close(got, torch.tensor([[[0.1, 0.2]], [[0.1, 0.3]], [[0.3, 0.1]]]))
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        r.sample_from_planes(axes, torch.zeros(1, 3, 32, 4, 4), xyz, box_warp=1)
+
+
+def test_measurement_library_is_separate_from_the_product(pkg):
+    """The microbenchmarks and the raw tcgen05 layer test live in libtriplane_b200_bench.so (include/triplane_b200_bench.h);
+    the product library exports none of them."""
+    text = open(os.path.join(ROOT, 'include', 'triplane_b200_bench.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    declared = sorted(set(re.findall(r'\b(tpr_[a-z_0-9]+)\s*\(', text)))
+    assert set(declared) == set(pkg._lib.BENCH_EXPORTED_SYMBOLS)
+    bench, prod = pkg._lib.bench_lib(), pkg._lib.lib()
+    for s in declared:
+        assert hasattr(bench, s) and not hasattr(prod, s), s

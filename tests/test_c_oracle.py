@@ -3,7 +3,7 @@ numpy oracle."""
 import numpy as np
 import pytest
 
-from tests.cases import CASES, load_case
+from tests.cases import SCALAR_CASES as CASES, load_case
 from oracle import triplane_oracle as O
 from oracle import c_oracle
 

@@ -133,9 +133,12 @@ def test_sample_stratified_bit_exact(pkg, name):
     scene, opts, gold = load_case(name)
     R = pkg.ImportanceRenderer()
     dc = opts['depth_resolution']
-    got = R.sample_stratified(T(scene['origins']), opts['ray_start'], opts['ray_end'], dc,
-                              opts.get('disparity_space_sampling', False), jitter=T(scene['jitter']))
-    want = O.stratified_depths(scene['jitter'], opts['ray_start'], opts['ray_end'], opts.get('disparity_space_sampling', False))
+    rs, re = opts['ray_start'], opts['ray_end']
+    if isinstance(rs, str):                                                  # 'auto': per-ray tensor limits (VR/renderer.py:91-97)
+        rs, re = (T(a) for a in O.auto_ray_limits(scene['origins'], scene['dirs'], opts['box_warp']))
+    got = R.sample_stratified(T(scene['origins']), rs, re, dc, opts.get('disparity_space_sampling', False), jitter=T(scene['jitter']))
+    from tests.cases import coarse_depths
+    want = coarse_depths(scene, opts)
     assert got.shape == want.shape
     np.testing.assert_array_equal(got.cpu().numpy(), want)
 

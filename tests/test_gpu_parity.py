@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.cases import CASES, load_case
+from tests.cases import CASES, case_noise, coarse_depths, density_noise_draws, depth_peak, load_case, oracle_render
 from oracle import triplane_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -58,12 +58,15 @@ def test_pack_planes_is_a_pure_transpose(pkg, name):
 @pytest.mark.parametrize('name', list(CASES))
 def test_run_model(pkg, name):
     scene, opts, gold = load_case(name)
-    out = pkg.ImportanceRenderer().run_model(T(scene['planes']), make_decoder(pkg, scene['dec']), T(gold['pts']), None, opts)
-    rgb_o, sig_o = O.run_model(scene['planes'], scene['dec'], gold['pts'], opts['box_warp'])
+    dn = opts.get('density_noise', 0)
+    nz = density_noise_draws(name)[2] if dn > 0 else None                  # stands for randn_like at VR/renderer.py:146
+    kw = dict(sigma_noise=T(nz)) if dn > 0 else {}
+    out = pkg.ImportanceRenderer().run_model(T(scene['planes']), make_decoder(pkg, scene['dec']), T(gold['pts']), None, opts, **kw)
+    rgb_o, sig_o = O.run_model(scene['planes'], scene['dec'], gold['pts'], opts['box_warp'], dn, nz)
     for got, want in ((out['rgb'], rgb_o), (out['sigma'], sig_o), (out['rgb'], gold['pts_rgb']), (out['sigma'], gold['pts_sigma'])):
         assert np.abs(got.cpu().numpy() - want).max() < 2e-5
     sig_only = pkg.ImportanceRenderer().run_model(T(scene['planes']), make_decoder(pkg, scene['dec']), T(gold['pts']),
-                                                  None, opts, want_rgb=False)
+                                                  None, opts, want_rgb=False, **kw)
     assert sig_only['rgb'] is None
     torch.testing.assert_close(sig_only['sigma'], out['sigma'], rtol=0, atol=0)
 
@@ -90,10 +93,10 @@ def test_render_bf16_decoder_psnr(pkg, name):
     scene, opts, gold = load_case(name)
     o = dict(opts, decoder_precision='bf16')
     rgb, depth, wsum = pkg.ImportanceRenderer()(T(scene['planes']), make_decoder(pkg, scene['dec']), T(scene['origins']),
-                                                T(scene['dirs']), o, noise=(T(scene['jitter']), T(scene['u'])))
+                                                T(scene['dirs']), o, noise=tuple(T(a) for a in case_noise(name, scene)))
     assert torch.isfinite(rgb).all() and torch.isfinite(depth).all()
     p_rgb = psnr(rgb.cpu().numpy(), gold['rgb'], 2.0)
-    p_d = psnr(depth.cpu().numpy(), gold['depth'], opts['ray_end'] - opts['ray_start'])
+    p_d = psnr(depth.cpu().numpy(), gold['depth'], depth_peak(opts, gold))
     p_w = psnr(wsum.cpu().numpy(), gold['wsum'], 1.0)
     print(f'{name}: bf16 PSNR rgb {p_rgb:.1f} dB, depth {p_d:.1f} dB, wsum {p_w:.1f} dB')
     assert p_rgb >= 50 and p_d >= 50 and p_w >= 50
@@ -108,9 +111,8 @@ def test_render_against_oracle_and_reference_fixture(pkg, name, mode):
     R = pkg.ImportanceRenderer()
     R.debug_outputs = True
     rgb, depth, wsum = R(T(scene['planes']), make_decoder(pkg, scene['dec']), T(scene['origins']), T(scene['dirs']),
-                         opts, noise=(T(scene['jitter']), T(scene['u'])))
-    (rgb_o, depth_o, wsum_o), st = O.render(scene['planes'], scene['dec'], scene['origins'], scene['dirs'], opts,
-                                            scene['jitter'], scene['u'], return_stages=True)
+                         opts, noise=tuple(T(a) for a in case_noise(name, scene)))
+    (rgb_o, depth_o, wsum_o), st = oracle_render(name, scene, opts)
     assert rgb.shape == rgb_o.shape and depth.shape == depth_o.shape and wsum.shape == wsum_o.shape
     for got, a, b in ((rgb, rgb_o, gold['rgb']), (depth, depth_o, gold['depth']), (wsum, wsum_o, gold['wsum'])):
         g = got.cpu().numpy()
@@ -145,7 +147,7 @@ def test_sample_pdf_bin_indices_bit_exact(pkg, name):
 def test_sample_importance_bit_exact(pkg, name):
     scene, opts, gold = load_case(name)
     n, m = scene['origins'].shape[:2]
-    d_c = O.stratified_depths(scene['jitter'], opts['ray_start'], opts['ray_end'], opts.get('disparity_space_sampling', False))
+    d_c = coarse_depths(scene, opts)
     w_c = gold['weights_coarse']
     k = scene['u'].shape[1]
     out, inds = pkg.ImportanceRenderer().sample_importance(T(d_c), T(w_c), k, u=T(scene['u']), return_inds=True)
@@ -165,34 +167,38 @@ def test_ray_marcher(pkg, name):
     assert np.abs(w.cpu().numpy() - gold['march_w']).max() < 1e-5
 
 
-def test_ray_limits_box_and_auto_limits(pkg):
-    rng = np.random.RandomState(5)
-    o = (rng.standard_normal((1, 300, 3)) * 1.5).astype(np.float32)
-    d = rng.standard_normal((1, 300, 3)).astype(np.float32)
-    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+def test_ray_limits_box_against_reference_fixture(pkg):
+    """a14: get_ray_limits_box (VR/math_utils.py:46-98) against what the unmodified reference returned for the same rays
+    (tests/golden/auto_limits.npz): the case's camera rays around a box the outer rays miss, and random rays around a unit
+    box.  Same float32 operations in the same order, so bit for bit, including the (-1, -2) markers of the misses.  The
+    'auto' forward built on it (VR/renderer.py:91-97) is the 'auto_limits' case of the render tests above."""
     from importlib import import_module
     mu = import_module('g-nerf_b200.volumetric_rendering.math_utils')
-    tmin, tmax = mu.get_ray_limits_box(T(o), T(d), 1.0)
-    tmin, tmax = tmin.cpu().numpy()[0, :, 0], tmax.cpu().numpy()[0, :, 0]
-    # independent slab test in float64
-    inv = 1.0 / d[0].astype(np.float64)
-    t0, t1 = (-0.5 - o[0]) * inv, (0.5 - o[0]) * inv
-    near, far = np.minimum(t0, t1).max(-1), np.maximum(t0, t1).min(-1)
-    hit = near <= far
-    missed = (tmin == -1) & (tmax == -2)                   # the reference's marker for "no intersection"
-    assert (missed == ~hit).mean() > 0.99                  # float32 vs float64 may disagree on grazing rays
-    sel = hit & ~missed
-    np.testing.assert_allclose(tmin[sel], near[sel], rtol=1e-4, atol=1e-4)
-    np.testing.assert_allclose(tmax[sel], far[sel], rtol=1e-4, atol=1e-4)
-    # 'auto' limits drive the per-ray branch of sample_stratified (VR/renderer.py:91-97,183-186)
-    scene, opts, _ = load_case('ragged')
-    o2 = dict(opts, ray_start='auto', ray_end='auto', box_warp=1)
+    _, opts, gold = load_case('auto_limits')
+    for o, d, side, want_min, want_max in ((gold['origins'], gold['dirs'], opts['box_warp'], gold['box_tmin'], gold['box_tmax']),
+                                           (gold['box2_origins'], gold['box2_dirs'], 1.0, gold['box2_tmin'], gold['box2_tmax'])):
+        tmin, tmax = mu.get_ray_limits_box(T(o), T(d), side)
+        assert tmin.shape == want_min.shape and tmax.shape == want_max.shape
+        np.testing.assert_array_equal(tmin.cpu().numpy(), want_min)
+        np.testing.assert_array_equal(tmax.cpu().numpy(), want_max)
+    assert 0 < int((gold['box_tmin'] == -1).sum()) < gold['box_tmin'].size
+
+
+def test_auto_limits_reject_disparity_sampling(pkg):
+    """The reference's disparity branch takes python floats (VR/renderer.py:174-181); with 'auto' limits it dies on shapes.
+    Here: a loud error instead of NaN depths, from the host shim and from the C ABI."""
+    scene, opts, _ = load_case('auto_limits')
     R = pkg.ImportanceRenderer()
-    rgb, depth, wsum = R(T(scene['planes']), make_decoder(pkg, scene['dec']), T(scene['origins']), T(scene['dirs']), o2,
-                         noise=(T(scene['jitter']), T(scene['u'])))
-    assert torch.isfinite(rgb).all() and torch.isfinite(depth).all()
-    lo, hi = R.last_depth_range.tolist()
-    assert 2.0 < lo < hi < 3.6 and depth.min() >= lo and depth.max() <= hi
+    args = (T(scene['planes']), make_decoder(pkg, scene['dec']), T(scene['origins']), T(scene['dirs']))
+    with pytest.raises(RuntimeError, match='disparity_space_sampling'):
+        R(*args, dict(opts, disparity_space_sampling=True), noise=(T(scene['jitter']), T(scene['u'])))
+    import ctypes
+    o = pkg._lib.TprOptions(ray_start=0.0, ray_end=0.0, box_warp=1.0, depth_resolution=8, depth_resolution_importance=8,
+                            disparity_space_sampling=1)
+    buf = torch.zeros(4096, device=dev())
+    p = ctypes.c_void_p(buf.data_ptr())
+    rc = pkg._lib.lib().tpr_render(p, 1, 8, 8, p, p, p, 4, p, p, p, p, ctypes.byref(o), p, p, p, None, None, None, 1, p, 1024, None)
+    assert rc == -3 and b'disparity' in pkg._lib.lib().tpr_last_error()
 
 
 def test_empty_space_rays_clamp_to_global_max_depth(pkg):

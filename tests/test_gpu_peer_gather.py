@@ -113,7 +113,9 @@ def _two_rank_worker(rank, world, port, q):
         opts = dict(O.FFHQ_OPTIONS, depth_resolution=dc, depth_resolution_importance=df)
         R = pkg.ImportanceRenderer()
         peer = pkg.parallel.PeerGather(n, m)
-        for step in range(3):                          # both buffer sets, and the first one again
+        assert peer.sets == 3
+        held = []                                      # (step, gathered outputs still living in the peer buffers, expected)
+        for step in range(5):                          # every buffer set, and the first two again
             scene = O.synthetic_scene(300 + 10 * step + rank, n, res, 48, dc, df, 0.5)
             dec = make_decoder(pkg, O.synthetic_scene(300, n, res, 48, dc, df, 0.5)['dec'], device=d)
             t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(d)       # noqa: E731
@@ -126,6 +128,15 @@ def _two_rank_worker(rank, world, port, q):
             for g, w in zip(got, want):
                 assert g.shape == w.shape and torch.equal(g, w), f'rank {rank} step {step}: peer gather differs'
             assert got[0].shape == (world * n, m, 32)
+            # the lifetime contract of PeerGather (three sets): the outputs of call s may still be read after call s+1 --
+            # consume step s-1 NOW, after this step's render + gather, while the other rank may already be a step ahead
+            if rank == 1:
+                torch.cuda._sleep(20_000_000)          # the slower rank: ~10 ms behind its peer
+            for hs, hgot, hwant in held:
+                if hs == step - 1:
+                    for g, w in zip(hgot, hwant):
+                        assert torch.equal(g, w), f'rank {rank}: outputs of step {hs} were overwritten before step {step + 1}'
+            held = [(step, got, want)]
         peer.close()
         q.put((rank, 'ok'))
     except Exception as e:              # noqa: BLE001

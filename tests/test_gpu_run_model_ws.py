@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import triplane_oracle as O
-from tests.cases import CASES, load_case
+from tests.cases import SCALAR_CASES as CASES, load_case
 from tests.test_gpu_parity import T, make_decoder, psnr, dev
 
 pytestmark = pytest.mark.gpu

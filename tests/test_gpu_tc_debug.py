@@ -18,8 +18,7 @@ def _run(pkg, mode, P=1000, seed=0):
     x = torch.randn(P, 32, device=dev)
     hidden = torch.full((P, 64), float('nan'), device=dev)
     out = torch.full((P, 48), float('nan'), device=dev)
-    L = pkg._lib.lib()
-    L.tpr_debug_tc_decode.restype = ctypes.c_int
+    L = pkg._lib.bench_lib()            # the raw tcgen05 layer test lives in the measurement library
     p = lambda t: ctypes.c_void_p(t.data_ptr())
     rc = L.tpr_debug_tc_decode(p(x), ctypes.c_int64(P), p(packed), ctypes.c_int32(mode), p(hidden), p(out),
                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))

@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from tests.cases import CASES, load_case
+from tests.cases import CASES, density_noise_draws, load_case
 from oracle import triplane_oracle as O
 
 TOL = 1e-5      # oracle vs reference (both fp32 CPU; differences are summation order / libm)
@@ -19,8 +19,9 @@ def test_ray_sampler_matches_reference(name):
 @pytest.mark.parametrize('name', list(CASES))
 def test_render_matches_reference(name):
     scene, opts, gold = load_case(name)
+    draws = density_noise_draws(name)[:2] if opts.get('density_noise', 0) > 0 else None
     (rgb, depth, wsum), st = O.render(scene['planes'], scene['dec'], gold['origins'], gold['dirs'], opts,
-                                      scene['jitter'], scene['u'], return_stages=True)
+                                      scene['jitter'], scene['u'], return_stages=True, density_noise_draws=draws)
     assert np.abs(rgb - gold['rgb']).max() < TOL
     assert np.abs(depth - gold['depth']).max() < TOL
     assert np.abs(wsum - gold['wsum']).max() < TOL
@@ -47,7 +48,9 @@ def test_sample_pdf_indices_bit_exact_given_identical_inputs(name):
 @pytest.mark.parametrize('name', list(CASES))
 def test_run_model_matches_reference(name):
     scene, opts, gold = load_case(name)
-    rgb, sigma = O.run_model(scene['planes'], scene['dec'], gold['pts'], opts['box_warp'])
+    dn = opts.get('density_noise', 0)
+    rgb, sigma = O.run_model(scene['planes'], scene['dec'], gold['pts'], opts['box_warp'], dn,
+                             density_noise_draws(name)[2] if dn > 0 else None)
     assert np.abs(rgb - gold['pts_rgb']).max() < TOL
     assert np.abs(sigma - gold['pts_sigma']).max() < 2e-5
 
@@ -60,6 +63,22 @@ def test_marcher_matches_reference(name):
     assert np.abs(rgb - gold['march_rgb']).max() < TOL
     assert np.abs(depth - gold['march_depth']).max() < TOL
     assert np.abs(w - gold['march_w']).max() < TOL
+
+
+def test_ray_limits_box_and_auto_limits_match_reference():
+    """a14: get_ray_limits_box (VR/math_utils.py:46-98) on the case's camera rays (a box the outer rays miss) and on random
+    rays around a unit box, bit for bit; the 'auto' replacement of the misses (VR/renderer.py:93-96) through render above."""
+    scene, opts, gold = load_case('auto_limits')
+    tmin, tmax = O.ray_limits_box(gold['origins'], gold['dirs'], opts['box_warp'])
+    np.testing.assert_array_equal(tmin, gold['box_tmin'])
+    np.testing.assert_array_equal(tmax, gold['box_tmax'])
+    misses = int((gold['box_tmin'] == -1).sum())
+    assert 0 < misses < tmin.size                      # the fixture exercises both kinds of ray
+    tmin, tmax = O.ray_limits_box(gold['box2_origins'], gold['box2_dirs'], 1.0)
+    np.testing.assert_array_equal(tmin, gold['box2_tmin'])
+    np.testing.assert_array_equal(tmax, gold['box2_tmax'])
+    rs, re = O.auto_ray_limits(gold['origins'], gold['dirs'], opts['box_warp'])
+    assert (re[gold['box_tmin'] == -1] == gold['box_tmin'][gold['box_tmin'] != -1].max()).all()
 
 
 def test_cdf_contract_is_order_independent():

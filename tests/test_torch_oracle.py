@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.cases import CASES, load_case
+from tests.cases import SCALAR_CASES as CASES, load_case
 from oracle import torch_oracle as TO
 
 TOL = 1e-5
