@@ -12,7 +12,8 @@ from .build import build  # noqa: F401
 from . import parallel  # noqa: F401
 from . import frames  # noqa: F401
 from .frames import render_frames, synthesize_frames, enable_plane_cache, disable_plane_cache  # noqa: F401
+from .launch import enable_reference_plugins  # noqa: F401
 
 __all__ = ['ImportanceRenderer', 'RaySampler', 'MipRayMarcher2', 'OSGDecoder', 'FullyConnectedLayer',
            'PackedPlanes', 'pack_planes', 'pack_decoder', 'generate_planes', 'install', 'uninstall', 'build',
-           'render_frames', 'synthesize_frames', 'enable_plane_cache', 'disable_plane_cache']
+           'render_frames', 'synthesize_frames', 'enable_plane_cache', 'disable_plane_cache', 'enable_reference_plugins']

@@ -143,14 +143,14 @@ def disable_plane_cache(G):
 
 
 def synthesize_frames(G, ws, cam2world, intrinsics, neural_rendering_resolution=None, *, frames_per_call=None,
-                      superresolution=True, **synthesis_kwargs):
+                      superresolution=True, update_emas=False, **synthesis_kwargs):
     """The frame loop of gen_videos.py:153-171 for a reference TriPlaneGenerator ``G`` with the renderer batched:
     backbone once (training/triplane.py:69), all frames through render_frames, then -- still the reference's own code,
     frame by frame -- the super-resolution head (training/triplane.py:86-87).  Returns lists of per-frame dicts with the
     keys ``synthesis`` returns."""
     res = G.neural_rendering_resolution if neural_rendering_resolution is None else neural_rendering_resolution
     G.neural_rendering_resolution = res
-    planes = G.backbone.synthesis(ws, **synthesis_kwargs)
+    planes = G.backbone.synthesis(ws, update_emas=update_emas, **synthesis_kwargs)      # the call of training/triplane.py:69
     planes = planes.view(len(planes), 3, 32, planes.shape[-2], planes.shape[-1])
     r = render_frames(G.renderer, planes, G.decoder, cam2world, intrinsics, res, G.rendering_kwargs,
                       ray_sampler=G.ray_sampler, frames_per_call=frames_per_call)

@@ -6,7 +6,8 @@
 What it does before handing over to the script with ``runpy`` ("ship install() plus a launcher"):
   1. puts the reference checkout on ``sys.path`` and calls ``install()`` (class-level patch of the reference's
      ImportanceRenderer / RaySampler / MipRayMarcher2, g-nerf_b200/install.py);
-  2. wraps ``legacy.load_network_pkl`` so that every TriPlaneGenerator it returns gets the backbone / repacked-plane
+  2. makes the reference's own CUDA plugins loadable under a current PyTorch (``enable_reference_plugins``);
+  3. wraps ``legacy.load_network_pkl`` so that every TriPlaneGenerator it returns gets the backbone / repacked-plane
      cache (frames.enable_plane_cache: gen_videos.py re-runs the backbone for each of its 120 frames with the same ws,
      gen_videos.py:150,171) and the renderer options chosen on the command line in its ``rendering_kwargs``.
 The reference's files are not modified and nothing is copied from them.
@@ -19,6 +20,29 @@ import sys
 
 from . import frames
 from .install import install
+
+
+def enable_reference_plugins():
+    """Let the reference's OWN CUDA plugins (bias_act / upfirdn2d, used by its backbone and super-resolution head, which stay on
+    the reference path) load under a current PyTorch.  The reference's loader calls ``torch.utils.cpp_extension.load(name=...)``
+    and then ``importlib.import_module(name)`` (torch_utils/custom_ops.py:141-144): that relied on ``load`` leaving the built
+    module in ``sys.modules``, which PyTorch 2.x no longer does (it returns the module without registering it), so every
+    plugin fails with ModuleNotFoundError right after compiling.  This wraps ``load`` to register what it returns -- the
+    behaviour the reference was written against.  The reference's files are not touched.  Idempotent."""
+    import torch.utils.cpp_extension as ext
+    if getattr(ext.load, '_tpr_registers_module', False):
+        return
+    original = ext.load
+
+    def load(name, *args, **kwargs):
+        module = original(name, *args, **kwargs)
+        if kwargs.get('is_python_module', True) and hasattr(module, '__name__'):
+            sys.modules.setdefault(name, module)
+        return module
+
+    load._tpr_registers_module = True
+    load.__wrapped__ = original
+    ext.load = load
 
 
 def _configure_generators(obj, extra_options, plane_cache):
@@ -68,6 +92,7 @@ def main(argv=None):
     if ref not in sys.path:
         sys.path.insert(0, ref)
     install()
+    enable_reference_plugins()
     extra = {'decoder_precision': args.decoder_precision}
     if args.channels_first:
         extra['output_layout'] = 'channels_first'

@@ -110,21 +110,48 @@ class PeerGather:
         n_floats = self._set_floats * self.sets
         L = _lib.lib()
         ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(_lib.PEER_HANDLE_BYTES)
+        self._own, self._peer_base, self.flat = None, {}, None
+        # Every step that can fail on ONE rank (allocation, IPC mapping) is followed by an exchange of the outcome, so that
+        # all ranks raise together instead of one raising while the others wait in the next collective.
         with torch.cuda.device(self.device):
-            _lib.check(L.tpr_peer_alloc(n_floats * 4, ctypes.byref(ptr), handle), 'tpr_peer_alloc')
-            self._own = ptr.value
-            self.flat = torch.as_tensor(_DeviceBlock(self._own, n_floats), device=self.device)
-            self.flat.zero_()
+            err = None
+            try:
+                _lib.check(L.tpr_peer_alloc(n_floats * 4, ctypes.byref(ptr), handle), 'tpr_peer_alloc')
+                self._own = ptr.value
+                self.flat = torch.as_tensor(_DeviceBlock(self._own, n_floats), device=self.device)
+                self.flat.zero_()
+            except Exception as e:          # noqa: BLE001
+                err = f'rank {self.rank}: {e}'
             handles = [None] * self.world
-            dist.all_gather_object(handles, handle.raw, group=group)
-            self._peer_base = {}
-            for r, h in enumerate(handles):
-                if r == self.rank:
-                    continue
-                p = ctypes.c_void_p()
-                _lib.check(L.tpr_peer_open(h, ctypes.byref(p)), f'tpr_peer_open(rank {r})')
-                self._peer_base[r] = p.value
+            dist.all_gather_object(handles, err if err is not None else handle.raw, group=group)
+            failed = [h for h in handles if isinstance(h, str)]
+            if not failed:
+                try:
+                    for r, h in enumerate(handles):
+                        if r == self.rank:
+                            continue
+                        p = ctypes.c_void_p()
+                        _lib.check(L.tpr_peer_open(h, ctypes.byref(p)), f'tpr_peer_open(rank {r})')
+                        self._peer_base[r] = p.value
+                except Exception as e:      # noqa: BLE001
+                    err = f'rank {self.rank}: {e}'
+                status = [None] * self.world
+                dist.all_gather_object(status, err, group=group)
+                failed = [s for s in status if s is not None]
+            if failed:
+                self._release()
+                raise RuntimeError('PeerGather: ' + '; '.join(failed))
         dist.barrier(group=group)            # nobody renders into a peer before every rank has zeroed and mapped
+
+    def _release(self):
+        L = self._lib.lib()
+        with torch.cuda.device(self.device):
+            for p in self._peer_base.values():
+                L.tpr_peer_close(self._ctypes.c_void_p(p))
+            self.flat = None
+            if self._own is not None:
+                L.tpr_peer_free(self._ctypes.c_void_p(self._own))
+        self._own, self._peer_base = None, {}
 
     def next_set(self) -> int:
         k = self._step % self.sets
@@ -292,3 +319,63 @@ def render_ray_sharded(renderer, planes, decoder, ray_origins, ray_directions, r
             wsum[s.image, sl] = buf[r, k, :s.n_rays, 33:34]
     depth = torch.clamp(torch.nan_to_num(depth, nan=float('inf')), lo, hi)
     return rgb, depth, wsum
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# run_model (density grids, TriPlaneGenerator.sample / sample_mixed) sharded over point slabs
+# ----------------------------------------------------------------------------------------------------------------
+def point_slabs(n_pts: int, world: int) -> List[range]:
+    """Contiguous slabs of the flattened point index, one per rank, as even as possible (the first n_pts % world ranks
+    get one more).  For the density grid of gen_videos.py:33-55 the flattened index runs z-slowest, so a slab is a z-slab
+    of the cube."""
+    if n_pts <= 0 or world <= 0:
+        raise ValueError('point_slabs: n_pts and world must be positive')
+    base, extra = divmod(n_pts, world)
+    out, begin = [], 0
+    for r in range(world):
+        cnt = base + (1 if r < extra else 0)
+        out.append(range(begin, begin + cnt))
+        begin += cnt
+    return out
+
+
+def run_model_sharded(renderer, planes, decoder, sample_coordinates, sample_directions, options, *, group=None,
+                      want_rgb: bool = False, local_query: Optional[Callable] = None, gather: bool = True):
+    """``ImportanceRenderer.run_model`` (VR/renderer.py:142-148) for one identity's planes held by EVERY rank (25 MB: each
+    rank ran the backbone on the same ws with noise_mode='const', or received a broadcast) and the full coordinate tensor
+    [N,P,3]: rank r queries the r-th contiguous slab of the P points and sigma (4 bytes per point; plus rgb, 128 bytes,
+    only when asked for) is all-gathered in place, so every rank returns the complete {'rgb', 'sigma'} of the reference.
+    ``gather=False`` returns this rank's slab only (a caller that writes its own z-slab of an .mrc volume).
+    No collective touches the planes or the coordinates; density_noise is drawn per slab (each rank from its own generator)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n, p, _ = sample_coordinates.shape
+    slabs = point_slabs(p, world)
+    mine = slabs[rank]
+    query = local_query or (lambda xyz: renderer.run_model(planes, decoder, xyz, None, options, want_rgb=want_rgb))
+    dev = sample_coordinates.device
+    even = p % world == 0
+    if not gather or world == 1:
+        out = query(sample_coordinates[:, mine.start:mine.stop].contiguous()) if len(mine) else \
+            {'rgb': torch.empty((n, 0, 32), device=dev) if want_rgb else None, 'sigma': torch.empty((n, 0, 1), device=dev)}
+        return out
+    cap = len(slabs[0])                                   # the largest slab
+    # gather buffers [world, N, cap, C]: with one image and equal slabs that IS the [N,P,C] result, no unpacking copy
+    chans = [('sigma', 1)] + ([('rgb', 32)] if want_rgb else [])
+    bufs = {k: torch.empty((world, n, cap, c), device=dev, dtype=torch.float32) for k, c in chans}
+    if len(mine):
+        res = query(sample_coordinates[:, mine.start:mine.stop].contiguous())
+        for k, _ in chans:
+            bufs[k][rank, :, :len(mine)] = res[k]
+    for k, _ in chans:
+        dist.all_gather_into_tensor(bufs[k].view(-1), bufs[k][rank].reshape(-1), group=group)        # in place
+    out = {'rgb': None}
+    for k, c in chans:
+        if n == 1 and even:
+            out[k] = bufs[k].view(1, p, c)
+        else:
+            full = torch.empty((n, p, c), device=dev, dtype=torch.float32)
+            for r, sl in enumerate(slabs):
+                full[:, sl.start:sl.stop] = bufs[k][r, :, :len(sl)]
+            out[k] = full
+    return out

@@ -174,14 +174,20 @@ def _density_noise(options):
     return dn if dn > 0 else 0.0
 
 
-def _draw_noise(noise, n, m, dc, df, dn, dev):
+def _draw_noise(noise, n, m, dc, df, dn, dev, per_ray_limits=False):
     """The forward's random draws, made with the reference's own torch calls in the reference's order so that the CUDA
     generator advances exactly as the reference advances it: rand_like [N,M,Dc,1] (VR/renderer.py:190), then -- only
     with density_noise > 0 -- randn_like [N,M*Dc,1] (:146, coarse run_model), rand [N*M,Df] (:237), randn_like
     [N,M*Df,1] (:146, fine run_model).  ``noise`` = (jitter, u[, coarse noise, fine noise]) overrides them (parity
     tests feed the oracle and the kernels the same numbers)."""
     if noise is None:
-        jitter = torch.rand((n, m, dc, 1), device=dev, dtype=torch.float32)
+        if per_ray_limits:
+            # the 'auto' branch builds its depths as math_utils.linspace(...) [D,N,M,1] .permute(1,2,0,3) and calls rand_like
+            # on that VIEW (VR/renderer.py:184-186): rand_like keeps the strides and fills in memory order, i.e. the draw is
+            # rand([D,N,M,1]) seen through the same permutation
+            jitter = torch.rand((dc, n, m, 1), device=dev, dtype=torch.float32).permute(1, 2, 0, 3).contiguous()
+        else:
+            jitter = torch.rand((n, m, dc, 1), device=dev, dtype=torch.float32)
         nz_c = torch.randn((n, m * dc, 1), device=dev, dtype=torch.float32) if dn > 0 else None
         u = torch.rand(n * m, df, device=dev) if df > 0 else None
         nz_f = torch.randn((n, m * df, 1), device=dev, dtype=torch.float32) if dn > 0 and df > 0 else None
@@ -315,7 +321,7 @@ class ImportanceRenderer(torch.nn.Module):
             ray_start, ray_end = float(opts['ray_start']), float(opts['ray_end'])
 
         with torch.cuda.device(dev):
-            jitter, u, nz_c, nz_f = _draw_noise(noise, n, m, dc, df, dn, dev)
+            jitter, u, nz_c, nz_f = _draw_noise(noise, n, m, dc, df, dn, dev, per_ray_limits=rs_t is not None)
             o = _lib.TprOptions(ray_start=ray_start, ray_end=ray_end, box_warp=float(opts['box_warp']),
                                 depth_resolution=dc, depth_resolution_importance=df,
                                 disparity_space_sampling=int(bool(opts.get('disparity_space_sampling', False))),
@@ -536,7 +542,9 @@ class ImportanceRenderer(torch.nn.Module):
             raise RuntimeError('disparity_space_sampling takes scalar ray limits (VR/renderer.py:174-181)')
         with torch.cuda.device(dev):
             if jitter is None:
-                jitter = torch.rand((n, m, d, 1), device=dev, dtype=torch.float32)
+                # the reference's rand_like, which for the per-ray branch fills a permuted [D,N,M,1] view (see _draw_noise)
+                jitter = (torch.rand((d, n, m, 1), device=dev, dtype=torch.float32).permute(1, 2, 0, 3) if per_ray
+                          else torch.rand((n, m, d, 1), device=dev, dtype=torch.float32))
             jitter = _require_cuda_f32(jitter, 'jitter').reshape(n, m, d, 1)
             rs = _require_cuda_f32(ray_start, 'ray_start').reshape(-1) if per_ray else None
             re = _require_cuda_f32(ray_end, 'ray_end').reshape(-1) if per_ray else None

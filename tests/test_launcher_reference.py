@@ -1,4 +1,4 @@
-"""CPU, and only where the reference checkout is present (this container; not the GPU box): the launcher's pieces --
+"""CPU, wherever the unmodified reference is present (/root/reference here, oracle/_ref on the GPU box): the launcher's pieces --
 install(), the load_network_pkl wrapper and the backbone / plane cache -- against the REAL, unmodified reference
 TriPlaneGenerator.  CPU tensors keep going to the reference renderer (install.py dispatches on device), so this checks the
 host logic either side of the hot path, not the kernels."""
@@ -8,9 +8,10 @@ import sys
 import pytest
 import torch
 
-REF = '/root/reference/g_nerf'
-pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'training', 'volumetric_rendering')),
-                                reason='reference checkout not present')
+from oracle import ref_loader
+
+REF = ref_loader.reference_dir()
+pytestmark = pytest.mark.skipif(REF is None, reason='reference not present (neither /root/reference nor oracle/_ref)')
 
 
 @pytest.fixture(scope='module')

@@ -86,3 +86,53 @@ def test_two_rank_gloo_matches_single_process(mode):
         for got, w in zip(ret[r], want):
             assert got.shape == w.shape
             np.testing.assert_allclose(got, w, atol=1e-6, rtol=0)
+
+
+def test_point_slabs_cover_every_point_once(pkg):
+    P = pkg.parallel
+    for n_pts, world in [(256 ** 3, 8), (1000, 3), (5, 8), (7, 1), (10_000_000, 8)]:
+        slabs = P.point_slabs(n_pts, world)
+        assert len(slabs) == world and slabs[0].start == 0 and slabs[-1].stop == n_pts
+        assert all(a.stop == b.start for a, b in zip(slabs, slabs[1:]))
+        assert max(map(len, slabs)) - min(map(len, slabs)) <= 1
+    with pytest.raises(ValueError):
+        P.point_slabs(0, 2)
+
+
+def _slab_worker(rank, world, port, n_img, n_pts, want_rgb, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import gnerf_b200 as pkg
+        scene = O.synthetic_scene(41, n_img, 4, 16, 8, 8, 0.5)
+        pts = (np.random.RandomState(5).random_sample((n_img, n_pts, 3)).astype(np.float32) - 0.5) * 1.2
+
+        def query(xyz):                                   # the oracle stands in for the per-rank CUDA point query
+            rgb, sigma = O.run_model(scene['planes'], scene['dec'], xyz.numpy(), 1.0)
+            return {'rgb': torch.from_numpy(rgb) if want_rgb else None, 'sigma': torch.from_numpy(sigma)}
+        out = pkg.parallel.run_model_sharded(None, None, None, torch.from_numpy(pts), None, {'box_warp': 1}, want_rgb=want_rgb,
+                                             local_query=query)
+        mine = pkg.parallel.run_model_sharded(None, None, None, torch.from_numpy(pts), None, {'box_warp': 1}, want_rgb=want_rgb,
+                                              local_query=query, gather=False)
+        ret[rank] = (out['sigma'].numpy().copy(), out['rgb'].numpy().copy() if want_rgb else None, mine['sigma'].numpy().copy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n_img,n_pts,want_rgb', [(1, 64, False), (1, 65, True), (2, 33, False)])
+def test_two_rank_gloo_run_model_sharded(pkg, n_img, n_pts, want_rgb):
+    """Config 5's sharding: contiguous point slabs per rank, sigma (and rgb) all-gathered; even and
+    ragged slab sizes, one and two images."""
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_slab_worker, args=(world, _free_port(), n_img, n_pts, want_rgb, ret), nprocs=world, join=True)
+    scene = O.synthetic_scene(41, n_img, 4, 16, 8, 8, 0.5)
+    pts = (np.random.RandomState(5).random_sample((n_img, n_pts, 3)).astype(np.float32) - 0.5) * 1.2
+    rgb, sigma = O.run_model(scene['planes'], scene['dec'], pts, 1.0)
+    slabs = pkg.parallel.point_slabs(n_pts, world)
+    for r in range(world):
+        got_sigma, got_rgb, mine = ret[r]
+        np.testing.assert_allclose(got_sigma, sigma, atol=2e-6, rtol=0)       # (numpy matmul blocks differently per slab size)
+        if want_rgb:
+            np.testing.assert_allclose(got_rgb, rgb, atol=2e-6, rtol=0)
+        np.testing.assert_allclose(mine, sigma[:, slabs[r].start:slabs[r].stop], atol=2e-6, rtol=0)
