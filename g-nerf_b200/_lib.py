@@ -82,6 +82,7 @@ _BENCH_SIGNATURES = {
     'tpr_gather_microbench': (c_int64, [_P, c_int64, c_int32, c_int32, _P, _P]),
     'tpr_mma_microbench': (ctypes.c_int, [c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     'tpr_gather_microbench_ex': (c_int64, [_P, c_int64, c_int32, c_int32, c_int32, c_int32, _P, _P]),
+    'tpr_gather_microbench_v2': (c_int64, [_P, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     'tpr_debug_tc_decode': (ctypes.c_int, [_P, c_int64, _P, c_int32, _P, _P, _P]),
 }
 BENCH_EXPORTED_SYMBOLS = tuple(_BENCH_SIGNATURES)
@@ -93,12 +94,13 @@ def lib() -> ctypes.CDLL:
     """Load (once) and return the shared library; raise loudly if it is not there."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get('TPR_LIB') or LIB_PATH          # TPR_LIB: an A/B build made by build.py --alt (development aid)
+        if not os.path.exists(path):
             raise RuntimeError(
-                f'{LIB_PATH} is missing: the sm_100a CUDA library has not been built. Run '
+                f'{path} is missing: the sm_100a CUDA library has not been built. Run '
                 f'`python -c "import __graft_entry__ as g; g.build()"` (needs nvcc). There is no CPU or '
                 f'PyTorch fallback for the tri-plane renderer.')
-        handle = ctypes.CDLL(LIB_PATH)
+        handle = ctypes.CDLL(path)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)           # AttributeError if a declared symbol is not exported
             fn.restype, fn.argtypes = res, args

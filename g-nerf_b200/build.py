@@ -75,6 +75,36 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def build_alt(defines, name='alt', verbose=False) -> str:
+    """Development aid for same-box A/B measurements: the product library compiled with extra -D switches into
+    lib/libtriplane_b200_<name>.so (load it with TPR_LIB=<path>; see _lib.py).  Not built by build()."""
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    out_dir = os.path.join(LIB_DIR, 'obj_' + name)
+    os.makedirs(out_dir, exist_ok=True)
+    objs, jobs = [], []
+    for src in SOURCES:
+        obj = os.path.join(out_dir, src[:-3] + '.o')
+        objs.append(obj)
+        cmd = [nvcc] + NVCC_FLAGS + list(defines) + ['-I', os.path.join(ROOT, 'include'), '-I', CSRC] + \
+              (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        jobs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, proc in jobs:
+        out, _ = proc.communicate()
+        if proc.returncode != 0:
+            raise RuntimeError(f'nvcc failed on {src}:\n{out}')
+        if verbose:
+            print(out)
+    lib = os.path.join(LIB_DIR, f'libtriplane_b200_{name}.so')
+    res = subprocess.run([nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a'] + objs + ['-o', lib], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError('link failed:\n' + res.stdout + res.stderr)
+    return lib
+
+
 if __name__ == '__main__':
     import sys
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    if '--alt' in sys.argv:
+        i = sys.argv.index('--alt')
+        print(build_alt(sys.argv[i + 2:], name=sys.argv[i + 1], verbose='-v' in sys.argv))
+    else:
+        print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

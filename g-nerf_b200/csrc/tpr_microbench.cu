@@ -64,6 +64,89 @@ extern "C" int64_t tpr_gather_microbench_ex(const float* buf, int64_t n_lines, i
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Variants of the gather shape (what should the render kernel's gather warps look like?): 128-bit loads with eight lanes
+// per line or 256-bit loads (LDG.E.ENL2.256, sm_100) with four lanes per line; a burst of kInFlight loads consumed together,
+// or software-pipelined (the next burst is issued before the previous one is consumed: between kInFlight and 2*kInFlight
+// loads in flight per thread at any time).
+// ---------------------------------------------------------------------------------------------------------
+namespace tpr {
+struct __align__(32) F8 { float v[8]; };
+__device__ __forceinline__ F8 ldg256(const float* p) {
+  F8 r;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "l"(p));
+  return r;
+}
+template <int kVec, int kInFlight, bool kPipe>
+__global__ void __launch_bounds__(1024) gather_bench2_kernel(const float* __restrict__ buf, uint32_t n_lines, int iters,
+                                                            float* __restrict__ sink) {
+  constexpr int kLanes = 32 / kVec;                         // lanes per 128-byte line
+  const int sub = threadIdx.x % kLanes;
+  const uint32_t grp = (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
+  const uint32_t n_grp = (gridDim.x * blockDim.x) / kLanes;
+  float acc = 0.f;
+  uint32_t ctr = grp;
+  float cur[kInFlight][kVec], nxt[kInFlight][kVec];
+  auto issue = [&](float (&dst)[kInFlight][kVec]) {
+#pragma unroll
+    for (int k = 0; k < kInFlight; ++k) {
+      const uint32_t line = (uint32_t)(((uint64_t)mix32(ctr) * n_lines) >> 32);
+      ctr += n_grp;
+      const float* p = buf + (size_t)line * 32 + sub * kVec;
+      if (kVec == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+        dst[k][0] = v.x; dst[k][1] = v.y; dst[k][2] = v.z; dst[k][3] = v.w;
+      } else {
+        const F8 v = ldg256(p);
+#pragma unroll
+        for (int c = 0; c < kVec; ++c) dst[k][c] = v.v[c];
+      }
+    }
+  };
+  auto consume = [&](float (&src)[kInFlight][kVec]) {
+#pragma unroll
+    for (int k = 0; k < kInFlight; ++k)
+#pragma unroll
+      for (int c = 0; c < kVec; ++c) acc += src[k][c];
+  };
+  if (!kPipe) {
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) { issue(cur); consume(cur); }
+  } else {
+    issue(cur);
+#pragma unroll 1
+    for (int it = 0; it + 2 <= iters; it += 2) { issue(nxt); consume(cur); issue(cur); consume(nxt); }
+    consume(cur);
+  }
+  sink[(blockIdx.x * blockDim.x + threadIdx.x) & 0xffff] = acc;
+}
+}  // namespace tpr
+
+extern "C" int64_t tpr_gather_microbench_v2(const float* buf, int64_t n_lines, int32_t ctas, int32_t threads, int32_t vec_floats,
+                                            int32_t in_flight, int32_t pipelined, int32_t iters, float* sink, void* stream) {
+  if (!buf || !sink || n_lines <= 0 || n_lines > 0x7fffffff || ctas <= 0 || iters <= 0 || (iters & 1) || threads < 32 ||
+      threads > 1024 || (threads & 31))
+    return TPR_E_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint32_t nl = (uint32_t)n_lines;
+#define TPR_GB2(V, F, P) tpr::gather_bench2_kernel<V, F, P><<<ctas, threads, 0, st>>>(buf, nl, iters, sink)
+  const int key = vec_floats * 1000 + in_flight * 10 + (pipelined ? 1 : 0);
+  switch (key) {
+    case 4020: TPR_GB2(4, 2, false); break;  case 4021: TPR_GB2(4, 2, true); break;
+    case 4040: TPR_GB2(4, 4, false); break;  case 4041: TPR_GB2(4, 4, true); break;
+    case 4060: TPR_GB2(4, 6, false); break;  case 4080: TPR_GB2(4, 8, false); break;
+    case 8010: TPR_GB2(8, 1, false); break;  case 8011: TPR_GB2(8, 1, true); break;
+    case 8020: TPR_GB2(8, 2, false); break;  case 8021: TPR_GB2(8, 2, true); break;
+    case 8040: TPR_GB2(8, 4, false); break;  case 8041: TPR_GB2(8, 4, true); break;
+    default: return TPR_E_SHAPE;
+  }
+#undef TPR_GB2
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return -(int64_t)e - 1000;
+  return (int64_t)ctas * (threads / (32 / vec_floats)) * in_flight * iters;          // lines fetched
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // tcgen05.mma cost for the small shapes of the decoder: `count` back-to-back MMAs of M = 128, N = n, one K step
 // each (tf32: K = 8, bf16: K = 16), A from shared memory (SS) or TMEM (TS), issued by one thread.  Reports
 // cycles from the first issue to the commit's arrival, and the issue-only cycles.

@@ -1,9 +1,9 @@
 // Warp-specialised fused ImportanceRenderer.forward (VR/renderer.py:88-140) for sm_100a.
 //
-// Same arithmetic as render_tc_kernel (tpr_render_tc.cu) -- plane gather, OSGDecoder on tcgen05 (3xTF32 or
-// bf16), in-register ray march / CDF / sort -- but the three kinds of work run CONCURRENTLY on one SM instead
-// of taking turns, because each of them alone leaves the SM mostly idle (ncu on the turn-taking kernel: 36 %
-// issue utilisation; the gather is bound by L2 latency, the per-ray phases by dependent-instruction latency):
+// Plane gather, OSGDecoder on tcgen05 (2xFP16 = the fp32-grade mode, or bf16), in-register ray march / CDF / sort; the
+// three kinds of work run CONCURRENTLY on one SM instead of taking turns, because each of them alone leaves the SM mostly
+// idle (ncu on a turn-taking predecessor: 36 % issue utilisation; the gather is bound by L2 latency, the per-ray phases by
+// dependent-instruction latency):
 //
 //   warps  0-15  GATHER    per tile of 128 samples: bilinear taps -> 12 x 128-byte texel reads per sample -> A1
 //                          operand tile in shared memory (SWIZZLE_128B), three tiles deep
@@ -16,10 +16,10 @@
 //   GATHER/DECODE job order:  C(0) C(1) F(0) C(2) F(1) ...    (C = coarse pass, F = fine pass of a group)
 //   RAYS step g:              resample(g)  setup(g+2)  sort+composite(g-1)
 // so the importance resampling of group g hides behind the coarse gather of group g+1 and its sort/composite
-// behind the next jobs.  Layer-2 colour outputs stay in TMEM until the group's composite: a pool of 32-column
-// slots (12 in 3xTF32 mode, 13 in bf16 mode) with flow control (a slot is reused only after the composite of
-// the group that owned it); sigma is the epilogue's fp32 dot product with the sigma row of layer 2 and goes to shared
-// memory per tile.
+// behind the next jobs.  Layer 1 accumulates into a 64-column TMEM stage and its activations overwrite it in place; layer-2
+// colour outputs stay in TMEM until the group's composite: a pool of fourteen 32-column slots with flow control (a slot is
+// reused only after the composite of the group that owned it); sigma is the epilogue's fp32 dot product with the sigma row
+// of layer 2 and goes to shared memory per tile.
 // mbarriers carry every hand-off; nothing per-sample ever touches HBM.
 //
 // Citations relative to /root/reference/g_nerf/ (VR/ = training/volumetric_rendering/).
@@ -40,13 +40,13 @@ namespace ws {
 struct Barriers {
   uint64_t a1_full[kBufs];      // 16 gather-warp arrivals: tile gathered and published to the async proxy
   uint64_t a1_free[kBufs];      // tcgen05.commit: layer 1 has consumed the tile
-  uint64_t d1_full;             // tcgen05.commit: layer 1 of the current tile is in TMEM
+  uint64_t d1_full;             // tcgen05.commit: layer 1 of the current tile is in the TMEM stage
   uint64_t a2_full;             // 8 decode-warp arrivals: activations are back in TMEM
-  uint64_t m2_done;             // tcgen05.commit: layer 2 of the current tile is in its slot / sigma block
   uint64_t coarse_ready[kCtx];  // 8 ray-warp arrivals: coarse depths of the group are in shared memory
   uint64_t fine_ready[kCtx];    // 8 ray-warp arrivals: importance depths are in shared memory
   uint64_t csig_ready[kCtx];    // 4 decode-warp arrivals: every coarse sigma of the group is in shared memory
-  uint64_t fsig_ready[kCtx];    // 4 decode-warp arrivals: every fine sigma, and every colour slot of the group is final
+  uint64_t fsig_ready[kCtx];    // 4 decode-warp arrivals (every sigma of the group's last pass is in shared memory) + 1
+                                // tcgen05.commit (the last layer 2, and with it every colour slot of the group, is final)
 };
 
 // per-group shared-memory context
@@ -80,10 +80,12 @@ __device__ __forceinline__ Geom group_geom(const RenderArgs& a, unsigned grp, in
 //         warps sustains more random-line bandwidth than twelve loads in flight per thread.
 // ---------------------------------------------------------------------------------------------------------
 template <int MODE, bool TRAIN = false>
-__device__ __forceinline__ void gather_tile(const RenderArgs& a, float* a1_hi, float* a1_lo, const float* __restrict__ img,
+__device__ __forceinline__ void gather_tile(const RenderArgs& a, float* a1_hi, const float* __restrict__ img,
                                             const Ctx& cx, Tap2* tw, int nr, int Dx, int off, int S, int t, int dpt_shift,
                                             int warp, int lane, long long ray0 = 0, int rstride = 0) {
+#ifndef TPR_GATHER_256
   const int grp = lane >> 3, sub = lane & 7;
+#endif
   const int dpt = 1 << dpt_shift;
   {
     const int s = lane / 3, p = lane - s * 3;
@@ -107,6 +109,22 @@ __device__ __forceinline__ void gather_tile(const RenderArgs& a, float* a1_hi, f
     }
   }
   __syncwarp();
+#ifdef TPR_GATHER_256          // (measured slower in the kernel: 2.45 vs 2.30 ms at config 2, profiles/r02_ab1_*.json; kept for A/B builds)
+  // Step 2, 256-bit loads: four lanes per sample, the warp's eight rows in one round (see blend_sample8)
+  {
+    const int s = lane >> 2, sub4 = lane & 3;
+    const ulonglong2* base = reinterpret_cast<const ulonglong2*>(img) + 2 * sub4;
+    asm volatile("" : "+l"(base));           // opaque to the compiler so that an address is one IMAD.WIDE
+    const int row = warp * 8 + s;
+    const int r = row >> dpt_shift, di = t * dpt + (row & (dpt - 1));
+    if (r < nr && di < Dx) {
+      // training: the summed features of the sample are kept for the backward (128 contiguous bytes per sample)
+      float4* keep = (TRAIN && a.sample_features != nullptr)
+          ? reinterpret_cast<float4*>(a.sample_features + ((ray0 + (long long)r * rstride) * S + off + di) * 32) + 2 * sub4 : nullptr;
+      blend_sample8<MODE>(a1_hi, base, tw + s * 3, row, sub4, keep);
+    }
+  }
+#else
   // this lane's four channels of every texel; opaque to the compiler so that an address is one IMAD.WIDE
   const ulonglong2* base = reinterpret_cast<const ulonglong2*>(img) + sub;
   asm volatile("" : "+l"(base));
@@ -120,9 +138,10 @@ __device__ __forceinline__ void gather_tile(const RenderArgs& a, float* a1_hi, f
       // training: the summed features of the sample are kept for the backward (128 contiguous bytes per sample)
       float4* keep = (TRAIN && a.sample_features != nullptr)
           ? reinterpret_cast<float4*>(a.sample_features + ((ray0 + (long long)r * rstride) * S + off + di) * 32) + sub : nullptr;
-      blend_sample<MODE>(a1_hi, a1_lo, base, te, row, sub, keep);
+      blend_sample<MODE>(a1_hi, base, te, row, sub, keep);
     }
   }
+#endif
   __syncwarp();           // the tap table is rewritten by the next tile
 }
 
@@ -168,14 +187,22 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
   // derives from role-dependent control flow (buffer index, slot, descriptors) then lives in uniform registers and a
   // tcgen05.mma costs one or two instructions instead of an elect/broadcast loop
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  // Waits poll (mbarrier.try_wait with a suspend hint).  Measured alternatives, same box (profiles/r02_ab2_*.json, r02_ab3_*.json):
+  // sleeping between polls (mbar_wait_sleep) for the waits that have slack is neutral (fp32 2.339 vs 2.344 ms, bf16 2.044 vs
+  // 2.050) although polls are 21 % of all executed warp instructions; handing d1_full to the eight decode warps through a
+  // named barrier polled by the issuer alone is 3 % SLOWER.  TPR_WS_VARIANT & 2 selects the sleeping waits (A/B).
+  const bool sleep_waits = (a.variant & 2) != 0;
+#define WAIT_SLACK(bar, par) do { if (sleep_waits) mbar_wait_sleep(bar, par); else mbar_wait_parked(bar, par); } while (0)
 
+  const int nf_host = a.Df;          // (coarse-only renders: see csig_ready below)
   if (tid == 0) {
     range_sm[0] = 0xffffffffu; range_sm[1] = 0u;
     for (int b = 0; b < kBufs; ++b) { mbar_init(&bars.a1_full[b], kGatherWarps); mbar_init(&bars.a1_free[b], 1); }
-    mbar_init(&bars.d1_full, 1); mbar_init(&bars.a2_full, kDecodeWarps); mbar_init(&bars.m2_done, 1);
+    mbar_init(&bars.d1_full, 1); mbar_init(&bars.a2_full, kDecodeWarps);
     for (int c = 0; c < kCtx; ++c) {
       mbar_init(&bars.coarse_ready[c], kRayWarps); mbar_init(&bars.fine_ready[c], kRayWarps);
-      mbar_init(&bars.csig_ready[c], 4); mbar_init(&bars.fsig_ready[c], 4);
+      // coarse-only renders (nf == 0) composite straight after the coarse pass: csig then also carries the MMA completion
+      mbar_init(&bars.csig_ready[c], nf_host == 0 ? 5 : 4); mbar_init(&bars.fsig_ready[c], 5);
     }
     freed_warps = 0u;
     for (int i = 0; i < 24; ++i) prof[i] = 0;
@@ -212,16 +239,15 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
         const Ctx cx = ctx_of(gi);
         const uint32_t cpar = (uint32_t)(gi >> 2) & 1u;
         PROF_T0();
-        mbar_wait_parked(pass == 0 ? &bars.coarse_ready[gi & 3] : &bars.fine_ready[gi & 3], cpar);
+        WAIT_SLACK(pass == 0 ? &bars.coarse_ready[gi & 3] : &bars.fine_ready[gi & 3], cpar);
         PROF_ADD(pass, tid == 0);
         const float* img = a.planes + (size_t)((unsigned)gg.n % (unsigned)a.plane_sets) * img_stride;
         const int T = pass == 0 ? nc : nf, Dx = pass == 0 ? Dc : Df, off = pass == 0 ? 0 : Dc;
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
-          mbar_wait_parked(&bars.a1_free[b], ph ^ 1u);      // passes immediately the first time round
+          WAIT_SLACK(&bars.a1_free[b], ph ^ 1u);            // passes immediately the first time round
           PROF_ADD(2, tid == 0);
-          gather_tile<MODE, TRAIN>(a, tl.a1[b][0], tl.a1[b][MODE == 0 ? 1 : 0], img, cx, tw, gg.nr, Dx, off, S, t, dpt_shift, warp, lane,
-                                   gg.ray0, gg.rstride);
+          gather_tile<MODE, TRAIN>(a, tl.a1[b][0], img, cx, tw, gg.nr, Dx, off, S, t, dpt_shift, warp, lane, gg.ray0, gg.rstride);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars.a1_full[b]);
@@ -234,11 +260,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
     // ====================================== DECODE ======================================
     const int dw = warp - kFirstDecodeWarp, q = dw & 3, h = dw >> 2;
     const bool issuer = dw == 0;
-    int b = 0; uint32_t ph = 0;                      // A1 buffer ring
-    uint32_t pt = 0;                                 // per-tile phase of d1_full / a2_full / m2_done
+    uint32_t pt = 0;                                 // per-tile phase of d1_full / a2_full (and the psig buffer)
     const uint32_t dbase = smem_desc_lo(smem_u32(&tl));
     uint32_t free_mask = (1u << Cols<MODE>::ns) - 1u;  // issuer only (warp-uniform): free colour slots
     int freed_groups = 0;                              // groups whose slots have been taken back
+    int b = 0; uint32_t ph = 0;                      // A1 buffer ring
     for (int step = 0; step <= G; ++step) {
 #pragma unroll 1
       for (int jb = 0; jb < 2; ++jb) {
@@ -253,13 +279,14 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
         for (int t = 0; t < T; ++t) {
           PROF_T0();
           const bool pl = dw == 0 && lane == 0;
+          const uint32_t st = tmem;                        // the layer-1 stage: columns [0, 64)
           if (issuer) {
             mbar_wait_parked(&bars.a1_full[b], ph);
             PROF_ADD(4, pl);
             tcgen05_fence_after();
             const int bu = __shfl_sync(0xffffffffu, b, 0);     // uniform register for the descriptor arithmetic
             if (elect_one_sync()) {
-              issue_layer1<MODE>(dbase, bu, tmem);
+              issue_layer1<MODE>(dbase, bu, st);
               mma_commit(&bars.a1_free[b]);
               mma_commit(&bars.d1_full);
             }
@@ -281,10 +308,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
             if (lane == 0) slot_tab[gi & (kCtx - 1)][(pass == 0 ? 0 : nc) + t] = slot;
           }
           PROF_ADD(5, pl);
-          mbar_wait_parked(&bars.d1_full, pt);               // also: layer 2 of the previous tile has consumed A2
+          mbar_wait_parked(&bars.d1_full, pt);               // also: layer 2 of the previous tile has consumed the activations
           PROF_ADD(6, pl);
           tcgen05_fence_after();
-          const float sgp = epilogue1<MODE>(tl, tmem, lane_base, h);
+          const float sgp = epilogue1<MODE>(tl, st, lane_base, h);
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars.a2_full);
@@ -294,25 +321,27 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
             PROF_ADD(8, pl);
             tcgen05_fence_after();
             if (elect_one_sync()) {
-              issue_layer2<MODE>(dbase, tmem, tmem + Cols<MODE>::slots + slot * kSlotCols);
-              mma_commit(&bars.m2_done);
+              issue_layer2<MODE>(dbase, st, tmem + Cols<MODE>::slots + slot * kSlotCols);
+              // Last tile of the group's last pass: the composite needs every colour slot of the group, i.e. this layer 2
+              // (and with it all earlier MMAs) complete.  The commit arrives on the group's barrier itself, so no decode
+              // warp -- least of all this one, which issues the next job's MMAs -- ever waits for the tensor pipe to drain.
+              if (t == T - 1 && (pass == 1 || nf == 0)) mma_commit(pass == 0 ? &bars.csig_ready[gi & 3] : &bars.fsig_ready[gi & 3]);
             }
             __syncwarp();
           }
           PROF_ADD(9, pl);
-          // sigma of this tile -> shared memory: the two warps of a lane quarter add their halves
-          if (h == 1) tl.psig[q * 32 + lane] = sgp;
+          // sigma of this tile -> shared memory: the two warps of a lane quarter add their halves.  psig is double buffered
+          // by tile parity: the h == 1 warp of tile t+2 can only get here after the epilogue barrier (a2_full) of tile t+1,
+          // which the h == 0 warp arrives at after it has read tile t's partial sums -- one named barrier per tile is enough.
+          float* ps = tl.psig + (pt ? kRows : 0);
+          if (h == 1) ps[q * 32 + lane] = sgp;
           named_bar_sync(3 + q, 64);
           if (h == 0) {
             const int row = q * 32 + lane, r = row >> dpt_shift, di = t * dpt + (row & (dpt - 1));
-            if (r < gg.nr && di < Dx) cx.sig[r * S + off + di] = sgp + tl.psig[row] + tl.bias2[kNc];
+            if (r < gg.nr && di < Dx) cx.sig[r * S + off + di] = sgp + ps[row] + tl.bias2[kNc];
           }
-          named_bar_sync(3 + q, 64);                  // psig is rewritten by the next tile
           PROF_ADD(10, pl);
           if (h == 0 && t == T - 1) {
-            // coarse pass: the resampling only needs sigma.  Last pass of the group: the composite also needs every
-            // colour slot of the group, i.e. this tile's layer 2 (and with it all earlier MMAs) complete.
-            if (pass == 1 || nf == 0) { mbar_wait_parked(&bars.m2_done, pt); }
             __syncwarp();
             if (lane == 0) mbar_arrive(pass == 0 ? &bars.csig_ready[gi & 3] : &bars.fsig_ready[gi & 3]);
           }
@@ -380,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
       const Geom gg = group_geom(a, blockIdx.x + (unsigned)gi * gridDim.x, R);
       const Ctx cx = ctx_of(gi);
       PROF_T0();
-      mbar_wait_parked(&bars.csig_ready[gi & 3], (uint32_t)(gi >> 2) & 1u);
+      WAIT_SLACK(&bars.csig_ready[gi & 3], (uint32_t)(gi >> 2) & 1u);
       PROF_ADD(13, pl);
       if (a.noise_c != nullptr) {     // density_noise (VR/renderer.py:146), coarse pass
         add_density_noise(a, a.noise_c, cx.sig, S, 0, Dc, gg.nr * Dc, gg.ray0, gg.rstride, rtid, kRayThreads);
@@ -401,7 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
       const Geom gg = group_geom(a, blockIdx.x + (unsigned)gi * gridDim.x, R);
       const Ctx cx = ctx_of(gi);
       PROF_T0();
-      mbar_wait_parked(nf > 0 ? &bars.fsig_ready[gi & 3] : &bars.csig_ready[gi & 3], (uint32_t)(gi >> 2) & 1u);
+      WAIT_SLACK(nf > 0 ? &bars.fsig_ready[gi & 3] : &bars.csig_ready[gi & 3], (uint32_t)(gi >> 2) & 1u);
       PROF_ADD(15, pl);
       if (a.noise_c != nullptr) {     // density_noise (VR/renderer.py:146): the pass whose sigma has just arrived
         if (nf > 0) add_density_noise(a, a.noise_f, cx.sig, S, Dc, Df, gg.nr * Df, gg.ray0, gg.rstride, rtid, kRayThreads);
@@ -507,7 +536,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
       if (i == 0 && r < gg.nr) {
         const float wsr = rayw[r];
         long long cstride;
-        float* dst1 = rgb_ptr(a, gg.ray0 + (long long)r * gg.rstride, gg.n, cstride) + 16 * hc * cstride;
+        float* dst1 = rgb_ptr(a, gg.ray0 + (long long)r * gg.rstride, gg.n, cstride);
+        dst1 += 16 * hc * cstride;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           float v = acc[c];
@@ -574,17 +604,22 @@ static Kernel pick_kernel(int S, bool prof, bool train) {
   if (train && !prof && S > 64 && S <= 96) return render_ws_kernel<MODE, 4, 3, false, true>;
   if (prof && S > 64 && S <= 96) return render_ws_kernel<MODE, 4, 3, true>;      // TPR_PHASE_TIMING=1 (profiles/phase_timing.py)
   if (prof && S > 128 && S <= 192) return render_ws_kernel<MODE, 8, 6, true>;                 // (192 samples: TPR_PT_DEPTH=96)
+#ifdef TPR_DEV_BUILD          // A/B builds (build.py --alt): only the 48+48 and 96+96 instantiations, a fifth of the compile time
+  return S <= 96 ? render_ws_kernel<MODE, 4, 3, false> : render_ws_kernel<MODE, 8, 6, false>;
+#else
   return S <= 64 ? render_ws_kernel<MODE, 2, 2, false> : S <= 96 ? render_ws_kernel<MODE, 4, 3, false>
        : S <= 128 ? render_ws_kernel<MODE, 4, 4, false> : S <= 192 ? render_ws_kernel<MODE, 8, 6, false>
        : render_ws_kernel<MODE, 8, 8, false>;
+#endif
 }
 
 }  // namespace ws
 
 // Rays per group (8 or 4) the warp-specialised kernel would use, or 0 if (Dc, Df) does not fit its slot ring:
 // the pipelined job order keeps the coarse slots of two groups and the fine slots of one alive at once.
-int ws_rays_per_group(int Dc, int Df, int bf16) {
-  const int ns = bf16 ? ws::Cols<1>::ns : ws::Cols<0>::ns;
+// mode: 1 = bf16, 2 = 2xFP16 (the template parameter MODE)
+int ws_rays_per_group(int Dc, int Df, int mode) {
+  const int ns = mode == 1 ? ws::Cols<1>::ns : ws::Cols<2>::ns;
   for (int R = 8; R >= 4; R >>= 1) {
     const int dpt = ws::kRows / R;
     const int nc = (Dc + dpt - 1) / dpt, nf = Df > 0 ? (Df + dpt - 1) / dpt : 0;
@@ -594,12 +629,12 @@ int ws_rays_per_group(int Dc, int Df, int bf16) {
 }
 
 // Sample counts for which a TRAIN instantiation exists (the reference's training depths, 48+48: train.py:312-313).
-bool ws_keeps_samples(int Dc, int Df) { const int S = Dc + Df; return S > 64 && S <= 96 && ws_rays_per_group(Dc, Df, 0) == 8; }
+bool ws_keeps_samples(int Dc, int Df) { const int S = Dc + Df; return S > 64 && S <= 96 && ws_rays_per_group(Dc, Df, 2) == 8; }
 
 // Launch; returns cudaError_t (0 = ok), or -1 if the configuration does not fit (the caller falls back).
-int launch_render_ws(RenderArgs a, int bf16, int sms, int smem_optin, long long n_img, long long n_rays, cudaStream_t st) {
+int launch_render_ws(RenderArgs a, int mode, int sms, int smem_optin, long long n_img, long long n_rays, cudaStream_t st) {
   const int S = a.Dc + a.Df;
-  a.R = ws_rays_per_group(a.Dc, a.Df, bf16);
+  a.R = ws_rays_per_group(a.Dc, a.Df, mode);
   if (a.R == 0) return -1;
   if (a.col_w > 0 && (a.col_w % a.R != 0 || (long long)a.col_w * a.col_w != n_rays)) a.col_w = 0;
   a.tiles_per_img = (n_rays + a.R - 1) / a.R;
@@ -607,8 +642,8 @@ int launch_render_ws(RenderArgs a, int bf16, int sms, int smem_optin, long long 
   if (a.n_tiles >= (1ll << 31) || n_rays >= (1ll << 31)) return -1;      // group_geom works in 32 bits
   const bool train = a.sample_colours != nullptr && a.sample_sigma != nullptr;
   if (train && !ws_keeps_samples(a.Dc, a.Df)) return -1;
-  ws::Kernel k = bf16 ? ws::pick_kernel<1>(S, a.dbg != nullptr, train) : ws::pick_kernel<0>(S, a.dbg != nullptr, train);
-  const size_t smem = bf16 ? ws::smem_bytes<1>(a.R, S, a.Df) : ws::smem_bytes<0>(a.R, S, a.Df);
+  ws::Kernel k = mode == 1 ? ws::pick_kernel<1>(S, a.dbg != nullptr, train) : ws::pick_kernel<2>(S, a.dbg != nullptr, train);
+  const size_t smem = mode == 1 ? ws::smem_bytes<1>(a.R, S, a.Df) : ws::smem_bytes<2>(a.R, S, a.Df);
   cudaFuncAttributes fa;
   cudaError_t e = cudaFuncGetAttributes(&fa, k);
   if (e != cudaSuccess) return (int)e;

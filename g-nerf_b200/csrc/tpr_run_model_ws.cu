@@ -28,8 +28,10 @@ using namespace tc;
 using namespace ws;
 
 constexpr int kColourWarps = 8;
-constexpr int kStages = 2, kStageCols = 128;       // TMEM: stage s = columns [128 s, 128 s + 128)
-constexpr int kSlots = 8, kSlotBase = 256;         // colour slots: columns [256 + 32 k, 256 + 32 k + 32)
+constexpr int kStages = 2;                         // TMEM: stage s = columns [128 s, 128 s + 128) (D1, and bf16's activations behind it)
+constexpr uint32_t kRmStageCols = 128;
+constexpr int kSlots = 8;                          // colour slots: columns [256 + 32 k, 256 + 32 k + 32)
+constexpr uint32_t kRmSlotBase = kStages * kRmStageCols;
 
 struct RmArgs {
   const float* planes; int H, W;
@@ -50,7 +52,7 @@ struct RmBarriers {
 
 // one tile of 128 points -> A1 buffer.  Warp w owns rows [8w, 8w+8); same two steps as the forward's gather_tile.
 template <int MODE>
-__device__ __forceinline__ void gather_tile_points(const RmArgs& a, float* a1_hi, float* a1_lo, const float* __restrict__ img,
+__device__ __forceinline__ void gather_tile_points(const RmArgs& a, float* a1_hi, const float* __restrict__ img,
                                                    const float* __restrict__ pts, int nvalid, Tap2* tw, int warp, int lane) {
   const int grp = lane >> 3, sub = lane & 7;
   {
@@ -77,7 +79,7 @@ __device__ __forceinline__ void gather_tile_points(const RmArgs& a, float* a1_hi
   for (int rd = 0; rd < 2; ++rd) {
     const int s = rd * 4 + grp;
     const int row = warp * 8 + s;
-    if (row < nvalid) blend_sample<MODE>(a1_hi, a1_lo, base, tw + s * 3, row, sub);
+    if (row < nvalid) blend_sample<MODE>(a1_hi, base, tw + s * 3, row, sub);
   }
   __syncwarp();           // the tap table is rewritten by the next tile
 }
@@ -131,7 +133,7 @@ run_model_ws_kernel(const RmArgs a) {
       long long n, p0; int nvalid;
       tile_of(i, n, p0, nvalid);
       mbar_wait_parked(&bars.a1_free[b], ph ^ 1u);          // passes immediately the first time round
-      gather_tile_points<MODE>(a, tl.a1[b][0], tl.a1[b][MODE == 0 ? 1 : 0], a.planes + (size_t)n * img_stride,
+      gather_tile_points<MODE>(a, tl.a1[b][0], a.planes + (size_t)n * img_stride,
                                a.xyz + (size_t)(n * a.n_pts + p0) * 3, nvalid, tw, warp, lane);
       fence_proxy_async_smem();
       __syncwarp();
@@ -152,7 +154,7 @@ run_model_ws_kernel(const RmArgs a) {
       if (j >= 2) mbar_wait_parked(&bars.a2_full[j & 1], (uint32_t)((j - 2) >> 1) & 1u);
       tcgen05_fence_after();
       const int bu = __shfl_sync(0xffffffffu, b, 0);
-      const uint32_t st = tmem + (uint32_t)(j & 1) * kStageCols;
+      const uint32_t st = tmem + (uint32_t)(j & 1) * kRmStageCols;
       if (elect_one_sync()) {
         issue_layer1<MODE>(dbase, bu, st);
         mma_commit(&bars.a1_free[b]);
@@ -171,7 +173,7 @@ run_model_ws_kernel(const RmArgs a) {
       if (issuer && i + 1 < G) issue_l1(i + 1);         // the tensor core works on tile i+1 during this epilogue
       mbar_wait_parked(&bars.d1_full[s], sph);
       tcgen05_fence_after();
-      const float sgp = epilogue1<MODE, RGB>(tl, tmem + (uint32_t)s * kStageCols, lane_base, h);
+      const float sgp = epilogue1<MODE, RGB>(tl, tmem + (uint32_t)s * kRmStageCols, lane_base, h);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.a2_full[s]);
@@ -181,7 +183,7 @@ run_model_ws_kernel(const RmArgs a) {
         mbar_wait_parked(&bars.slot_free[k], ((uint32_t)(i / kSlots) & 1u) ^ 1u);     // passes the first time round
         tcgen05_fence_after();
         if (elect_one_sync()) {
-          issue_layer2<MODE>(dbase, tmem + (uint32_t)s * kStageCols, tmem + kSlotBase + (uint32_t)k * kSlotCols);
+          issue_layer2<MODE>(dbase, tmem + (uint32_t)s * kRmStageCols, tmem + kRmSlotBase + (uint32_t)k * kSlotCols);
           mma_commit(&bars.slot_full[k]);
         }
         __syncwarp();
@@ -206,7 +208,7 @@ run_model_ws_kernel(const RmArgs a) {
       mbar_wait_parked(&bars.slot_full[k], (uint32_t)(i / kSlots) & 1u);
       tcgen05_fence_after();
       uint32_t v[16];
-      tmem_ld16(tmem + kSlotBase + (uint32_t)k * kSlotCols + lane_base + 16 * hc, v);
+      tmem_ld16(tmem + kRmSlotBase + (uint32_t)k * kSlotCols + lane_base + 16 * hc, v);
       tmem_wait_ld();
       tcgen05_fence_before();
       __syncwarp();
@@ -237,7 +239,7 @@ static size_t smem_bytes() { return 1024 + sizeof(Tiles<MODE>) + sizeof(Tap2) * 
 
 // Launch; returns cudaError_t (0 = ok) or -1 if the shape does not fit (the caller uses the FFMA kernel).
 int launch_run_model_ws(const float* planes, long long n_img, int H, int W, const float* dec, const float* xyz, long long n_pts,
-                        float box_scale, float* rgb, float* sigma, int bf16, int sms, int smem_optin, cudaStream_t st) {
+                        float box_scale, float* rgb, float* sigma, int mode, int sms, int smem_optin, cudaStream_t st) {
   using namespace wsrm;
   RmArgs a;
   a.planes = planes; a.H = H; a.W = W; a.dec = dec; a.xyz = xyz; a.n_pts = n_pts;
@@ -247,9 +249,9 @@ int launch_run_model_ws(const float* planes, long long n_img, int H, int W, cons
   if (a.n_tiles >= (1ll << 31) * (long long)sms) return -1;          // the per-CTA tile count is an int
   typedef void (*Kernel)(const RmArgs);
   const bool want_rgb = rgb != nullptr;
-  Kernel k = bf16 ? (want_rgb ? run_model_ws_kernel<1, true> : run_model_ws_kernel<1, false>)
-                  : (want_rgb ? run_model_ws_kernel<0, true> : run_model_ws_kernel<0, false>);
-  const size_t smem = bf16 ? smem_bytes<1>() : smem_bytes<0>();
+  Kernel k = mode == 1 ? (want_rgb ? run_model_ws_kernel<1, true> : run_model_ws_kernel<1, false>)
+                       : (want_rgb ? run_model_ws_kernel<2, true> : run_model_ws_kernel<2, false>);
+  const size_t smem = mode == 1 ? smem_bytes<1>() : smem_bytes<2>();
   cudaFuncAttributes fa;
   cudaError_t e = cudaFuncGetAttributes(&fa, k);
   if (e != cudaSuccess) return (int)e;

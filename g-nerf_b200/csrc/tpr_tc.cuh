@@ -44,6 +44,15 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity,
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
   } while (ok == 0);
 }
+// Wait with sleep back-off, for waits with slack (a role waiting for another role's pipeline stage): one immediate attempt,
+// then the warp leaves the scheduler for ~ns at a time.  ncu on render_ws_kernel (profiles/r02a_render_ws_fp32_ncu_lines.txt):
+// try_wait does not really park -- a waiting warp re-issued the poll every ~55 cycles and 21 % of ALL executed warp
+// instructions were mbarrier polls, taking issue slots (and shared-memory pipe cycles: SYNCS goes through it) from the warps
+// of the other roles on the same scheduler, the softplus epilogue of the decode chain first of all.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns = 128u) {
+  if (mbar_try_wait(bar, parity)) return;
+  do { __nanosleep(ns); } while (!mbar_try_wait(bar, parity));
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -19,12 +19,12 @@
 namespace tpr {
 
 // warp-specialised tensor-core render path (tpr_render_ws.cu)
-int ws_rays_per_group(int Dc, int Df, int bf16);
+int ws_rays_per_group(int Dc, int Df, int mode);
 bool ws_keeps_samples(int Dc, int Df);
-int launch_render_ws(RenderArgs a, int bf16, int sms, int smem_optin, long long n_img, long long n_rays, cudaStream_t st);
+int launch_render_ws(RenderArgs a, int mode, int sms, int smem_optin, long long n_img, long long n_rays, cudaStream_t st);
 // tpr_run_model_ws.cu
 int launch_run_model_ws(const float* planes, long long n_img, int H, int W, const float* dec, const float* xyz, long long n_pts,
-                        float box_scale, float* rgb, float* sigma, int bf16, int sms, int smem_optin, cudaStream_t st);
+                        float box_scale, float* rgb, float* sigma, int mode, int sms, int smem_optin, cudaStream_t st);
 
 // tpr_backward.cu
 int launch_bwd_points(const float* origins, const float* dirs, const float* dc, const float* df, int Dc, int Df,
@@ -299,7 +299,8 @@ __device__ __forceinline__ void ray_composite(const RenderArgs& a, const TileSme
   float c = acc0 + acc1;
   if (a.white_back) c = c + 1.0f - wsum;              // VR/ray_marcher.py:52-53
   long long cstride;
-  rgb_ptr(a, g, n, cstride)[lane * cstride] = c * 2.0f - 1.0f;      // :55
+  float* px = rgb_ptr(a, g, n, cstride);
+  px[lane * cstride] = c * 2.0f - 1.0f;                              // :55
   if (lane == 0) {
     a.depth[g] = dnum / wsum;                         // NaN -> inf and the clamp happen in finish_kernel
     a.wsum[g] = wsum;
@@ -562,6 +563,10 @@ static int env_int(const char* name, int dflt) {
   return v && *v ? atoi(v) : dflt;
 }
 
+// Operand scheme of the tcgen05 decoder for a TPR_MLP_* flag (the kernels' MODE): 1 = bf16 operands (the PSNR mode),
+// 2 = 2xFP16 (x = hi + lo in fp16, three products: the fp32-grade mode; it replaced 3xTF32, see tpr_ws.cuh).
+static int tc_mode(int flags) { return flags == TPR_MLP_BF16 ? 1 : 2; }
+
 int grid_for(long long work_items, int per_block, int sms, int waves) {
   long long blocks = (work_items + per_block - 1) / per_block;
   long long cap = (long long)sms * waves;
@@ -684,7 +689,7 @@ static int launch_run_model(bool from_features, const float* planes, int64_t n_i
   // fp32 FFMA kernel below, whose 32-point chunks spread over the SMs at any size.
   if (!from_features && flags != TPR_MLP_FFMA && (long long)n_img * n_pts >= env_int("TPR_RM_WS_MIN_POINTS", 1 << 16) &&
       !env_int("TPR_FORCE_FFMA", 0)) {
-    int rc = launch_run_model_ws(planes, n_img, H, W, dec, in, n_pts, box_scale, rgb, sigma, flags == TPR_MLP_BF16, di.sms,
+    int rc = launch_run_model_ws(planes, n_img, H, W, dec, in, n_pts, box_scale, rgb, sigma, tc_mode(flags), di.sms,
                                  di.smem_optin, (cudaStream_t)stream);
     if (rc > 0) return cuda_fail((cudaError_t)rc, "run_model_ws_kernel");
     if (rc == 0) return 0;
@@ -838,10 +843,10 @@ static int render_impl(const float* planes_packed, int64_t n_img, int32_t height
   // Dispatch: the warp-specialised tcgen05 kernel whenever the sample counts fit its TMEM colour-slot pool (every depth
   // pair any G-NeRF configuration uses), else -- or with TPR_MLP_FFMA -- the fp32 FFMA kernel, which takes any S <= 256.
   bool done = false;
-  if (opt->flags != TPR_MLP_FFMA && !env_int("TPR_FORCE_FFMA", 0) && ws_rays_per_group(Dc, Df, opt->flags == TPR_MLP_BF16) > 0) {
+  if (opt->flags != TPR_MLP_FFMA && !env_int("TPR_FORCE_FFMA", 0) && ws_rays_per_group(Dc, Df, tc_mode(opt->flags)) > 0) {
     const bool keep = sample_colours && sample_sigma && ws_keeps_samples(Dc, Df) && !a.dbg;
     if (keep) { a.sample_colours = sample_colours; a.sample_sigma = sample_sigma; a.sample_features = sample_features; }   // (only this kernel can keep them)
-    int rc = launch_render_ws(a, opt->flags == TPR_MLP_BF16, di.sms, di.smem_optin, n_img, n_rays, st);
+    int rc = launch_render_ws(a, tc_mode(opt->flags), di.sms, di.smem_optin, n_img, n_rays, st);
     if (rc > 0) return cuda_fail((cudaError_t)rc, "render_ws_kernel");
     done = rc == 0;                       // < 0: does not fit shared memory, fall through
     a.sample_colours = nullptr; a.sample_sigma = nullptr; a.sample_features = nullptr;

@@ -27,6 +27,12 @@ int64_t tpr_gather_microbench(const float* buf, int64_t n_lines, int32_t ctas, i
 int64_t tpr_gather_microbench_ex(const float* buf, int64_t n_lines, int32_t ctas, int32_t threads,
                                  int32_t in_flight, int32_t iters, float* sink, void* stream);
 
+/* Variants of the gather shape: vec_floats = 4 (LDG.128, eight lanes per line) or 8 (LDG.256, four lanes per line); in_flight loads
+ * per burst; pipelined != 0: the next burst is issued before the previous one is consumed.  iters must be even.
+ * Supported (vec, in_flight, pipelined): (4, 2|4, 0|1), (4, 6|8, 0), (8, 1|2|4, 0|1).  Returns the lines fetched. */
+int64_t tpr_gather_microbench_v2(const float* buf, int64_t n_lines, int32_t ctas, int32_t threads, int32_t vec_floats,
+                                 int32_t in_flight, int32_t pipelined, int32_t iters, float* sink, void* stream);
+
 /* Issues `count` tcgen05.mma (M = 128, N = n, one K step; tf32 or bf16 operands; A from shared memory or TMEM)
  * from one thread of one CTA; tight != 0 issues them from precomputed descriptors (count % 4 == 0).
  * out_dev[0] = cycles spent issuing, out_dev[1] = cycles until all have completed. */

@@ -7,7 +7,7 @@ import torch, numpy as np
 pkg = importlib.import_module('g-nerf_b200')
 import bench
 dev = torch.device('cuda:0')
-planes_h, c2w, K = bench.make_inputs(torch, dev, 100)
+planes_h, c2w, K = bench.make_inputs(torch, 100)
 dec = bench.make_decoder(torch, pkg, dev, 0)
 R, S = pkg.ImportanceRenderer(), pkg.RaySampler()
 planes = planes_h.to(dev); o, d = S(c2w.to(dev), K.to(dev), 128)

@@ -101,8 +101,11 @@ def test_plane_cache_and_batched_frames_equal_the_per_frame_loop(pkg, setup):
         real_rf = pkg.frames.render_frames
 
         def spy(*a, **k):
-            got['r'] = real_rf(*a, **k)
-            return got['r']
+            r = real_rf(*a, **k)
+            # snapshot: the SR head's toRGB skip adds into rgb_image IN PLACE (networks_stylegan2.py, `img.add_`), and rgb_image
+            # is a view of the feature image's first three channels (training/triplane.py:86), here as in the reference
+            got['r'] = {k2: v.clone() for k2, v in r.items()}
+            return r
         pkg.frames.render_frames = spy
         try:
             torch.manual_seed(12)
