@@ -369,6 +369,13 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
     int* hist = reinterpret_cast<int*>(stg_ray + R * 8 + 8);      // [R][Dc + 4] (R = 4: warp_merge_scatter)
     // R = 4 (more than 64 samples per pass): a ray's samples are merged instead of rank-counted (tpr_render.cuh)
     const bool merge = R == 4 && nf > 0 && (Df & 3) == 0 && a.variant != 3;
+    // R = 4, SPLIT steps: a group has four rays but there are eight ray warps, and the ray warps' serial timeline (resample
+    // 10 k + merge 8.6 k + march 5.4 k + composite 8.7 k cycles per group at 96+96) was the critical path of the whole kernel
+    // (phase counters, profiles/r02_phase96_*.txt: gather and decode waited for it).  So warps 0-3 resample group g (and rank
+    // its draws) WHILE warps 4-7 sort and march group g-1, each on its own scratch rows; all eight then composite g-1.
+    const bool split = merge && a.noise_c == nullptr && (a.variant & 16) == 0;
+    float* so_a = split ? reinterpret_cast<float*>(hist + R * (Dc + 4)) : wa;      // omega rows of the concurrent sort
+    float* so_b = split ? so_a + R * S : wb;                                         // its 2*S scratch floats per ray
     auto prefetch = [&](int gi) {
       const Geom gg = group_geom(a, blockIdx.x + (unsigned)gi * gridDim.x, R);
       if (rtid < gg.nr * 6) {
@@ -420,13 +427,46 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
         warp_resample_ray(a, cx.dep + r * S, cx.sig + r * S, wa + r * S, wb + r * S, wc + r * S, cx.dep + r * S + Dc,
                           gg.ray0 + (long long)r * gg.rstride, lane, cx.u + r * Df);
       // R = 4: warps 4-7 have no ray to resample; they rank the group's uniform draws for the merge of the next step
-      if (merge && rw >= 4 && rw - 4 < gg.nr) warp_rank_draws(cx.u + (rw - 4) * Df, cx.rk + (rw - 4) * Df, Df, lane);
+      if (!split && merge && rw >= 4 && rw - 4 < gg.nr) warp_rank_draws(cx.u + (rw - 4) * Df, cx.rk + (rw - 4) * Df, Df, lane);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.fine_ready[gi & 3]);
+      // split steps: the resampling warp ranks its own ray's draws, after the importance depths have been handed to the gather
+      // (the sorting warps doing it instead -- TPR_WS_VARIANT & 32 -- is +0.6 % in the 2xFP16 mode, -3.5 % in the bf16 mode)
+      if (split && (a.variant & 32) == 0 && rw < gg.nr) warp_rank_draws(cx.u + rw * Df, cx.rk + rw * Df, Df, lane);
       PROF_ADD(14, pl);
     };
 
-    auto sort_composite = [&](int gi) {
+    // split steps: sort + final march of ray rw - 4 of group gi by warp rw >= 4 alone (merge, else the single-warp rank count)
+    auto sort_split = [&](int gi) {
+      const Geom gg = group_geom(a, blockIdx.x + (unsigned)gi * gridDim.x, R);
+      const Ctx cx = ctx_of(gi);
+      PROF_T0();
+      mbar_wait_parked(&bars.fsig_ready[gi & 3], (uint32_t)(gi >> 2) & 1u);
+      PROF_ADD(15, pl);
+      if (range_slot(a, gg.n) != cur_slot) { range_fold(a, cur_slot, smn, smx, mn, mx, lane); cur_slot = range_slot(a, gg.n); }
+      const int r = rw - 4;
+      if (r < gg.nr) {
+        float wsum, dnum;
+        bool pre = false;
+        if (cx.rk[r * Df] >= 0)
+          pre = warp_merge_scatter(cx.dep + r * S, cx.sig + r * S, cx.rk + r * Df, so_a + r * S, so_b + r * 2 * S, hist + r * (Dc + 4),
+                                   S, Dc, lane);
+        warp_sort_and_weights<E, true, ER>(cx.dep + r * S, cx.sig + r * S, so_a + r * S, nullptr, S, lane, wsum, dnum, smn, smx,
+                                           so_b + r * 2 * S, pre);
+        if (lane == 0) {
+          const long long g = gg.ray0 + (long long)r * gg.rstride;
+          rayw[r] = wsum;
+          const float dq = dnum / wsum;               // NaN -> inf and the clamp happen in finish_kernel
+          a.depth[g] = dq;
+          a.wsum[g] = wsum;
+          for (int p = 0; p < a.peers.n; ++p) { a.peers.depth[p][g] = dq; a.peers.wsum[p][g] = wsum; }   // NVLink stores
+        }
+      }
+      PROF_ADD(18, pl);
+    };
+
+    // `sorted` = true: the group has been sorted already (split steps); the composite reads omega from `om`
+    auto sort_composite = [&](int gi, bool sorted, const float* om_rows) {
       const Geom gg = group_geom(a, blockIdx.x + (unsigned)gi * gridDim.x, R);
       const Ctx cx = ctx_of(gi);
       PROF_T0();
@@ -441,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
       // ---- sort + final march: omega per sample (scattered to original order), depth, weight sum
       // R = 4: two warps per ray share the rank count (pair_rank_scatter); warp rw < 4 then runs the march alone
       const bool pairs = R == 4 && nf > 0 && (Dc & 31) == 0 && (Df & 7) == 0;
-      for (int r = (pairs || merge) ? (rw & 3) : rw; r < gg.nr; r += kRayWarps) {
+      for (int r = (pairs || merge) ? (rw & 3) : rw; !sorted && r < gg.nr; r += kRayWarps) {
         float wsum, dnum;
         bool pre = false;
         const bool mg = merge && cx.rk[r * Df] >= 0;   // (both warps of the ray read the same verdict on the draws)
@@ -488,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
         const int slot = slot_tab[gi & (kCtx - 1)][sl];
         const int di = tl_i * dpt + i;
         const bool valid = r < gg.nr && di < (fine ? Df : Dc);
-        const float om = valid ? wa[r * S + (fine ? Dc : 0) + di] : 0.0f;
+        const float om = valid ? om_rows[r * S + (fine ? Dc : 0) + di] : 0.0f;
         uint32_t v[16];
         tmem_ld16(tmem + Cols<MODE>::slots + slot * kSlotCols + lane_base + 16 * hc, v);
         tmem_wait_ld();
@@ -568,12 +608,29 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
     if (G > 1) { prefetch(1); setup(1); }
     if (G > 2) prefetch(2);
     for (int g = 0; g < G; ++g) {
-      if (nf > 0) resample(g);
+      if (split) {
+        if (rw < 4) resample(g);
+        else {
+          if (lane == 0) mbar_arrive(&bars.fine_ready[g & 3]);       // (nothing to contribute: the four resampling warps complete it)
+          if (g >= 1) sort_split(g - 1);
+          if ((a.variant & 32) != 0) {                                // (A/B) rank the draws of group g for its merge in the next step
+            const Geom gg = group_geom(a, blockIdx.x + (unsigned)g * gridDim.x, R);
+            const Ctx cx = ctx_of(g);
+            if (rw - 4 < gg.nr) warp_rank_draws(cx.u + (rw - 4) * Df, cx.rk + (rw - 4) * Df, Df, lane);
+          }
+        }
+        RAY_SYNC();
+      } else if (nf > 0) {
+        resample(g);
+      }
       if (g + 2 < G) { setup(g + 2); if (g + 3 < G) prefetch(g + 3); }
-      if (nf > 0) { if (g >= 1) sort_composite(g - 1); }
-      else sort_composite(g);
+      if (nf > 0) { if (g >= 1) sort_composite(g - 1, split, so_a); }
+      else sort_composite(g, false, wa);
     }
-    if (nf > 0) sort_composite(G - 1);
+    if (nf > 0) {
+      if (split) { if (rw >= 4) sort_split(G - 1); RAY_SYNC(); }
+      sort_composite(G - 1, split, so_a);
+    }
     range_fold(a, cur_slot, smn, smx, mn, mx, lane);
     mn = warp_min(mn); mx = warp_max(mx);
     if (lane == 0 && mn <= mx) {
@@ -595,7 +652,7 @@ template <int MODE>
 static size_t smem_bytes(int R, int S, int Df) {
   return 1024 + sizeof(Tiles<MODE>) + sizeof(Tap2) * kGatherWarps * 24 +
          sizeof(float) * ((size_t)kCtx * (2 * R * S + R * Df + R * 8 + (R == 4 ? R * Df : 0)) + (size_t)3 * R * S + R +
-                          (size_t)R * S + R * 8 + 8 + (R == 4 ? R * (S - Df + 4) : 0));
+                          (size_t)R * S + R * 8 + 8 + (R == 4 ? R * (S - Df + 4) + (size_t)3 * R * S : 0));
 }
 
 typedef void (*Kernel)(const RenderArgs);

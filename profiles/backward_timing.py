@@ -13,7 +13,7 @@ ap.add_argument('--reps', type=int, default=10); ap.add_argument('--mode', defau
 args = ap.parse_args()
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = torch.device('cuda:0')
-planes_h, c2w, K = bench.make_inputs(torch, dev, 100, n_img=args.n_img)
+planes_h, c2w, K = bench.make_inputs(torch, 100, n_img=args.n_img)
 planes = planes_h.to(dev).requires_grad_(True)
 dec = bench.make_decoder(torch, pkg, dev, 0).requires_grad_(True)
 o, d = pkg.RaySampler()(c2w.to(dev), K.to(dev), bench.RES)

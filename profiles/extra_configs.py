@@ -27,7 +27,7 @@ def timed(fn, warm=3, n=10):
 out = {}
 if not args.skip4:
     n = args.n_img
-    planes_h, c2w, K = bench.make_inputs(torch, dev, 7, n_img=n)
+    planes_h, c2w, K = bench.make_inputs(torch, 7, n_img=n)
     planes = planes_h.to(dev); del planes_h
     o, d = S(c2w.to(dev), K.to(dev), 256)
     opts = dict(bench.OPTS, depth_resolution=96, depth_resolution_importance=96, decoder_precision=args.mode)
@@ -41,7 +41,7 @@ if not args.skip4:
     del planes, pp, o, d
     torch.cuda.empty_cache()
 if not args.skip5:
-    planes_h, _, _ = bench.make_inputs(torch, dev, 9, n_img=1)
+    planes_h, _, _ = bench.make_inputs(torch, 9, n_img=1)
     pp = pkg.pack_planes(planes_h.to(dev))
     g = 256
     # gen_videos.create_samples: voxel centres of a cube of side box_warp, x fastest
@@ -59,7 +59,7 @@ if not args.skip5:
     out['config5_shuffled'] = {'points': g ** 3, 'ms': ms, 'points_per_s': g ** 3 / ms * 1e3}
 # config 3 (renderer part): the gen_videos.py orbit of one identity -- 120 frames x 64^2 rays x (96+96) samples
 ap3 = dict(bench.OPTS, depth_resolution=96, depth_resolution_importance=96, decoder_precision=args.mode)
-planes_h, _, _ = bench.make_inputs(torch, dev, 11, n_img=1)
+planes_h, _, _ = bench.make_inputs(torch, 11, n_img=1)
 planes = planes_h.to(dev)
 cams = importlib.import_module('g-nerf_b200.camera_utils')
 c2w, K = cams.orbit_cameras(120)

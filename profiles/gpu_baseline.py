@@ -12,7 +12,7 @@ pkg = importlib.import_module('g-nerf_b200')
 torch.backends.cuda.matmul.allow_tf32 = False
 torch.backends.cudnn.allow_tf32 = False
 dev = torch.device('cuda:0')
-planes_h, c2w, K = bench.make_inputs(torch, dev, 100)
+planes_h, c2w, K = bench.make_inputs(torch, 100)
 planes = planes_h.to(dev)
 dec = bench.make_decoder(torch, pkg, dev, 0)
 o, d = pkg.RaySampler()(c2w.to(dev), K.to(dev), bench.RES)
