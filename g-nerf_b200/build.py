@@ -12,10 +12,11 @@ CSRC = os.path.join(PKG, 'csrc')
 LIB_DIR = os.path.join(PKG, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libtriplane_b200.so')
 BENCH_LIB_PATH = os.path.join(LIB_DIR, 'libtriplane_b200_bench.so')
-SOURCES = ['triplane_b200.cu', 'tpr_render_ws.cu', 'tpr_run_model_ws.cu', 'tpr_backward.cu', 'tpr_standalone.cu']
+SOURCES = ['triplane_b200.cu', 'tpr_render_ws.cu', 'tpr_render_ws_f16x2_a.cu', 'tpr_render_ws_f16x2_b.cu', 'tpr_render_ws_bf16_a.cu',
+           'tpr_render_ws_bf16_b.cu', 'tpr_run_model_ws.cu', 'tpr_backward.cu', 'tpr_backward_tc.cu', 'tpr_standalone.cu']
 BENCH_SOURCES = ['tpr_microbench.cu', 'tpr_tc_debug.cu']
 HEADERS = [os.path.join(CSRC, 'tpr_device.cuh'), os.path.join(CSRC, 'tpr_render.cuh'), os.path.join(CSRC, 'tpr_tc.cuh'),
-           os.path.join(CSRC, 'tpr_ws.cuh'), os.path.join(CSRC, 'tpr_host.h'), os.path.join(ROOT, 'include', 'triplane_b200.h'),
+           os.path.join(CSRC, 'tpr_ws.cuh'), os.path.join(CSRC, 'tpr_render_ws.cuh'), os.path.join(CSRC, 'tpr_host.h'), os.path.join(ROOT, 'include', 'triplane_b200.h'),
            os.path.join(ROOT, 'include', 'triplane_b200_bench.h')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',

@@ -35,6 +35,11 @@ int launch_bwd_march(const float* dc, const float* df, int Dc, int Df, const flo
 int launch_bwd_decode(const float* planes, int H, int W, const float* dec, const float* pts, const float* colours,
                       const float* features, const float* gsig, const float* omega, const float* g_rgb, long long total, long long pts_per_img, int S,
                       float box_scale, float* g_planes, float* g_dec, int fast, int skip, int sms, cudaStream_t st);
+// tpr_backward_tc.cu: the decoder backward on tcgen05 (returns -1 if it cannot run here)
+int launch_bwd_decode_tc(const float* planes, int H, int W, const float* dec, const float* pts, const float* colours,
+                         const float* features, const float* gsig, const float* omega, const float* g_rgb, long long total,
+                         long long pts_per_img, int S, float box_scale, float* g_planes, float* g_dec, float* scale_buf,
+                         int sms, int smem_optin, cudaStream_t st);
 int launch_unpack_decoder_grad(const float* gd, float g_w1, float g_b1, float g_w2, float g_b2, float* w1, float* b1, float* w2,
                                float* b2, cudaStream_t st);
 
@@ -1199,8 +1204,8 @@ static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 size_t tpr_render_backward_scratch_bytes(int64_t n_img, int64_t n_rays, int32_t n_samples) {
   if (n_img <= 0 || n_rays <= 0 || n_samples <= 0) return 0;
   const size_t T = (size_t)n_img * (size_t)n_rays * (size_t)n_samples;
-  // points [T,3], colours [T,32], sigma [T], g_sigma [T], omega [T]
-  return align256(T * 12) + align256(T * 128) + 3 * align256(T * 4);
+  // points [T,3], colours [T,32], sigma [T], g_sigma [T], omega [T], the operand scale of the tcgen05 decoder backward
+  return align256(T * 12) + align256(T * 128) + 3 * align256(T * 4) + 256;
 }
 
 int tpr_march_backward(const float* depths_coarse, const float* depths_fine, int32_t dc, int32_t df, const float* sigma,
@@ -1248,7 +1253,8 @@ int tpr_render_backward(const float* planes_packed, int64_t n_img, int32_t heigh
   float* colours = (float*)p; p += align256(T * 128);
   float* sigma = (float*)p; p += align256(T * 4);
   float* gsig = (float*)p; p += align256(T * 4);
-  float* omega = (float*)p;
+  float* omega = (float*)p; p += align256(T * 4);
+  float* scale_buf = (float*)p;
   int rc = launch_bwd_points(origins, dirs, depths_coarse, depths_fine, Dc, Df, rays, pts, di.sms, st);
   if (rc != 0) return cuda_fail((cudaError_t)rc, "points_kernel");
   const float* col_in = sample_colours; const float* sig_in = sample_sigma;
@@ -1267,6 +1273,16 @@ int tpr_render_backward(const float* planes_packed, int64_t n_img, int32_t heigh
   if (g_planes_packed) e = cudaMemsetAsync(g_planes_packed, 0, (size_t)n_img * 3 * height * width * kC * sizeof(float), st);
   if (e == cudaSuccess && g_decoder_packed) e = cudaMemsetAsync(g_decoder_packed, 0, kDecFloats * sizeof(float), st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+  // The decoder backward: tcgen05 + TMEM, warp-specialised (tpr_backward_tc.cu).  TPR_BWD_IMPL=hmma selects the mma.sync kernel
+  // it replaced (A/B runs; also the fallback if the tcgen05 kernel's shared memory does not fit the device).
+  const char* impl = getenv("TPR_BWD_IMPL");
+  if (!(impl && strcmp(impl, "hmma") == 0)) {
+    rc = launch_bwd_decode_tc(planes_packed, height, width, decoder_packed, pts, col_in, sample_features, gsig, omega, g_rgb, (long long)T,
+                              (long long)n_rays * S, S, (float)(2.0 / opt->box_warp), g_planes_packed, g_decoder_packed, scale_buf,
+                              di.sms, di.smem_optin, st);
+    if (rc > 0) return cuda_fail((cudaError_t)rc, "decode_backward_tc_kernel");
+    if (rc == 0) return 0;
+  }
   float* g_dec_out = g_decoder_packed ? g_decoder_packed : reinterpret_cast<float*>(scratch);      // (never written when skipped)
   rc = launch_bwd_decode(planes_packed, height, width, decoder_packed, pts, col_in, sample_features, gsig, omega, g_rgb, (long long)T,
                          (long long)n_rays * S, S, (float)(2.0 / opt->box_warp), g_planes_packed, g_dec_out,
