@@ -83,6 +83,7 @@ _BENCH_SIGNATURES = {
     'tpr_mma_microbench': (ctypes.c_int, [c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     'tpr_gather_microbench_ex': (c_int64, [_P, c_int64, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     'tpr_gather_microbench_v2': (c_int64, [_P, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
+    'tpr_scatter_microbench': (c_int64, [_P, c_int64, c_int32, c_int32, c_int32, c_int32, _P]),
     'tpr_debug_tc_decode': (ctypes.c_int, [_P, c_int64, _P, c_int32, _P, _P, _P]),
 }
 BENCH_EXPORTED_SYMBOLS = tuple(_BENCH_SIGNATURES)

@@ -110,11 +110,26 @@ __global__ void __launch_bounds__(128) march_backward_kernel(const MarchArgs a) 
       q[p] = acc;                                   // sum_c d(loss)/d(rgb_raw_c) * colour_c
     }
     __syncwarp();
-    // sort by depth (VR/renderer.py:157-167): rank = number of smaller depths, ties by sample index (a stable sort)
+    // sort by depth (VR/renderer.py:157-167): rank = number of smaller depths, ties by sample index (a stable sort).  The
+    // coarse depths of a ray ascend (stratified: VR/renderer.py:199-224), so a coarse sample's rank among them is its index and
+    // an importance sample's is an upper bound found by bisection; only the Df importance depths are compared one by one.
+    bool ascending = true;
+    for (int p = lane; p + 1 < a.Dc; p += 32) ascending = ascending && (z[p] <= z[p + 1]);
+    ascending = __all_sync(kFull, ascending);
     for (int p = lane; p < S; p += 32) {
       const float zp = z[p];
       int cnt = 0;
-      for (int j = 0; j < S; ++j) { const float v = z[j]; cnt += (int)((v < zp) || (v == zp && j < p)); }
+      if (ascending) {
+        if (p < a.Dc) cnt = p;
+        else {
+          int lo_i = 0, hi_i = a.Dc;                      // first coarse index whose depth is > zp
+          while (lo_i < hi_i) { const int mid = (lo_i + hi_i) >> 1; if (z[mid] <= zp) lo_i = mid + 1; else hi_i = mid; }
+          cnt = lo_i;
+        }
+        for (int j = a.Dc; j < S; ++j) { const float v = z[j]; cnt += (int)((v < zp) || (v == zp && j < p)); }
+      } else {
+        for (int j = 0; j < S; ++j) { const float v = z[j]; cnt += (int)((v < zp) || (v == zp && j < p)); }
+      }
       zs[cnt] = zp; ss[cnt] = sg[p]; qs[cnt] = q[p]; idx[cnt] = p;
     }
     __syncwarp();

@@ -15,13 +15,21 @@
 //       accumulated in TMEM over ALL tiles of the CTA and flushed once.  The operands of WG are the SAME shared-memory
 //       tiles G1-G3 use: a tile stored as [sample rows][128 bytes of fp16] with the 128-byte swizzle is K-major for a GEMM
 //       whose K runs along the row and MN-major for one whose K runs over the rows (instruction descriptor bits 15 / 16).
+//       The inputs of a tile are three swizzle atoms 16 KB apart, [F lo | GYc lo], [F hi | GYc hi], [gsig hi, lo, one]: one B
+//       operand of N = 144 for the hi half of [GA ; H] and of N = 80 (from the second atom) for its lo half -- two MMAs per 16
+//       samples (every MMA re-reads its 4 KB A slice from shared memory, so few wide MMAs beat many narrow ones).
+//
+// What bounds it (profiles/r02_scatter_shapes.json, TPR_BWD_PROFILE=1): the scatter.  12 texels x 128 bytes of
+// red.global.add per sample run at ~6 TB/s when the gradient of one image's planes (25 MB) is L2 resident -- the tiles are
+// handed out so that all CTAs work on the same image -- which is 3.1-3.3 ms for config 2's 151 M lines.
 //
 // Gradient-side operands (GY, GA) are multiplied by a power of two chosen from the upstream gradient's magnitude (a tiny
 // range kernel) before they are split into fp16 halves, and the results are scaled back exactly: fp16 has 5 exponent bits
 // and gradients come at any scale (loss scaling).
 //
-// Roles (25 warps, one CTA per SM):  0-7 LOAD (features / colours / upstream gradient -> operand tiles, taps)
-//                                     8-15 SCATTER (red.global.add.v4.f32 of GF x tap weight, one texel = one 128-byte line)
+// Roles (25 warps, one CTA per SM):  0-7 LOAD (features / colours / upstream gradient -> operand tiles)
+//                                     8-15 SCATTER (the sample's 12 taps from its position, red.global.add.v4.f32 of GF x tap
+//                                           weight; one texel = one 128-byte line = eight lanes)
 //                                     16-23 EPILOGUE (TMEM -> softplus / products -> operand tiles; GF -> shared memory): two
 //                                           warps per TMEM lane quarter, 32 hidden units each
 //                                     24 MMA issuer
@@ -30,6 +38,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <cuda_fp16.h>
 #include "triplane_b200.h"
 #include "tpr_device.cuh"
@@ -44,22 +53,23 @@ constexpr int kLoadWarps = 8, kScatWarps = 8, kEpiWarps = 8;
 constexpr int kThreads = 32 * (kLoadWarps + kScatWarps + kEpiWarps + 1);      // 800
 constexpr int kTile = kM * 128;                      // one operand tile: 128 rows x 128 bytes
 // TMEM columns
-constexpr uint32_t cD1 = 0, cGH = 64, cGF = 128, cDF = 192, cDY = 256, cDS = 320;
+constexpr uint32_t cD1 = 0, cGH = 64, cGF = 128, cW = 192;     // cW: 144 columns = [F lo | GYc lo | F hi | GYc hi | gsig hi, gsig lo, one, 0 ...]
 
 struct __align__(1024) Smem {
   uint8_t w1k[64 * 128];            // G1 B: row n (hidden) = [W1t[.][n] hi, k = 0..31 | lo]
   uint8_t w2c[64 * 128];            // G2 B: row j (hidden) = [W2t[j][1 + c] hi, c = 0..31 | lo]
   uint8_t w1g[2][32 * 128];         // G3 B: [hi, lo] row k (channel) = W1t[k][j], j = 0..63
-  uint8_t f[2][kTile];              // [F hi | F lo]                       (double buffered inputs)
-  uint8_t y[2][kTile];              // [GYc hi | GYc lo], scaled
+  // the inputs of a tile, double buffered: three 64-column swizzle atoms 16 KB apart.  Read K-major (rows = samples) by G1 / G2
+  // and MN-major, as ONE B operand of N = 144 (lo, hi, sig) or N = 80 (hi, sig), by the weight-gradient MMAs
+  struct In {
+    uint8_t lo[kTile];              // [F lo | GYc lo]  (32 + 32 fp16 per sample; GYc scaled)
+    uint8_t hi[kTile];              // [F hi | GYc hi]
+    uint8_t sig[kTile];             // [gsig hi, gsig lo, one, 0 x 13 | unused]
+  } in[2];
   uint8_t ga_hi[kTile], h_hi[kTile];   // stacked: MN-major A of WG, M = 128 = GA (64) then H (64); GA also the K-major A of G3
   uint8_t ga_lo[kTile], h_lo[kTile];
-  uint8_t s[2][kM * 32];            // unswizzled MN-major [128 x 16] fp16: columns gsig hi, gsig lo, one
   float gf[2][kM * 32];             // d/d features of a tile, 16-byte chunks XOR-swizzled by (row & 7); double buffered
-  uint32_t tap_off[2][kM * 12];     // float offset of each tap's texel inside its image
-  float tap_w[2][kM * 12];
   float gsig[2][kM];                // scaled d/d sigma (the epilogue's rank-1 term)
-  int simg[2][kM];
   float b1[64], w2s[64];
   uint64_t in_full[2], in_free[2], g12_done, hga_ready, g3_done, gf_ready[2], gf_free[2], wg_done, all_done;
   uint32_t tmem_base;
@@ -78,6 +88,7 @@ struct Args {
   float* g_planes;                      // packed, zero-initialised; NULL: no scatter
   float* g_dec;                         // [kDecFloats], zero-initialised; NULL: no weight gradients
   const float* scale;                   // [2] device: power-of-two scale of the gradient-side operands and its inverse
+  long long* prof;                      // TPR_BWD_PROFILE: cycles CTA 0 spends per role and wait (NULL: off)
 };
 
 // ---- descriptors -------------------------------------------------------------------------------------------------
@@ -100,15 +111,16 @@ __device__ __forceinline__ void unpack_f16x2(uint32_t v, float& lo_elem, float& 
 __device__ __forceinline__ void st_f16(uint8_t* tile, int row, int k, float v) {        // swizzled 128-byte rows of 64 fp16
   reinterpret_cast<__half*>(tile)[row * 64 + ((((k >> 3) ^ (row & 7)) << 3) | (k & 7))] = __float2half_rn(v);
 }
-// four fp32 values -> 8 bytes of the row's hi half and 8 bytes of its lo half ([hi 64 B | lo 64 B] rows; sub = 0..7)
-__device__ __forceinline__ void st_hilo4(uint8_t* tile, int row, int sub, float4 v) {
+// four fp32 values (columns 4 sub .. 4 sub + 3 of a 32-column block) -> 8 bytes of the hi tile's row and 8 bytes of the lo tile's,
+// in the block that starts at 16-byte chunk `chunk0` (0: features, 4: colour-logit gradients)
+__device__ __forceinline__ void st_hilo4(uint8_t* hi_tile, uint8_t* lo_tile, int row, int chunk0, int sub, float4 v) {
   const uint2 hi = make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w));
   float h0, h1, h2, h3;
   unpack_f16x2(hi.x, h0, h1); unpack_f16x2(hi.y, h2, h3);
   const uint2 lo = make_uint2(pack_f16x2(v.x - h0, v.y - h1), pack_f16x2(v.z - h2, v.w - h3));
-  uint8_t* rowp = tile + row * 128 + ((sub & 1) << 3);
-  *reinterpret_cast<uint2*>(rowp + (((sub >> 1) ^ (row & 7)) << 4)) = hi;
-  *reinterpret_cast<uint2*>(rowp + ((((sub >> 1) + 4) ^ (row & 7)) << 4)) = lo;
+  const int off = row * 128 + ((sub & 1) << 3) + (((chunk0 + (sub >> 1)) ^ (row & 7)) << 4);
+  *reinterpret_cast<uint2*>(hi_tile + off) = hi;
+  *reinterpret_cast<uint2*>(lo_tile + off) = lo;
 }
 // 16 fp32 values (hidden units [16 c, 16 c + 16) of row `row`) -> 32 bytes of a hi tile and of a lo tile (64 fp16 per row)
 __device__ __forceinline__ void st_hilo16(uint8_t* hi_tile, uint8_t* lo_tile, int row, int c, const float (&v)[16]) {
@@ -165,7 +177,14 @@ __global__ void scale_finish_kernel(const unsigned* __restrict__ acc, const floa
   }
 }
 
+// TPR_BWD_PROFILE=1: CTA 0 adds the cycles each role's first warp spends in every wait / work phase to prof[slot]
+// (kProf instantiation only; accumulated in registers, written once at the end of the role)
+#define PROF_DECL() long long prof_t = 0, prof_acc[17]; if (kProf) { for (int k_ = 0; k_ < 17; ++k_) prof_acc[k_] = 0; }
+#define PROF_T0() do { if (kProf) prof_t = clock64(); } while (0)
+#define PROF(slot) do { if (kProf) { const long long t1_ = clock64(); prof_acc[slot] += t1_ - prof_t; prof_t = t1_; } } while (0)
+#define PROF_FLUSH(first, last, cond) do { if (kProf && blockIdx.x == 0 && lane == 0 && (cond)) { for (int k_ = first; k_ <= last; ++k_) a.prof[k_] = prof_acc[k_]; } } while (0)
 // ---- the kernel ------------------------------------------------------------------------------------------------------------
+template <bool kProf>
 __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const Args a) {
   extern __shared__ uint8_t smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -175,7 +194,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const A
 
   // ---- one-time setup: barriers, TMEM, decoder operands
   if (tid == 0) {
-    for (int b = 0; b < 2; ++b) { mbar_init(&s.in_full[b], kLoadWarps); mbar_init(&s.in_free[b], 1 + kScatWarps); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s.in_full[b], kLoadWarps); mbar_init(&s.in_free[b], 1);
+    }
     mbar_init(&s.g12_done, 1); mbar_init(&s.hga_ready, kEpiWarps); mbar_init(&s.g3_done, 1);
     mbar_init(&s.gf_ready[0], kEpiWarps); mbar_init(&s.gf_ready[1], kEpiWarps); mbar_init(&s.gf_free[0], kScatWarps);
     mbar_init(&s.gf_free[1], kScatWarps); mbar_init(&s.wg_done, 1); mbar_init(&s.all_done, 1);
@@ -211,94 +232,87 @@ __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const A
 
   if (warp < kLoadWarps) {
     // ================================================ LOAD ================================================
+    // Eight lanes per sample, 16 samples per warp: two halves of two passes each, the global loads of a half issued together
+    // (the first half's before the wait for the operand buffer).  Measured alternatives at config 2, same box: all four passes'
+    // loads up front (needs the upstream gradient read at use to stay under the CTA's 72 registers per thread) 8.32 vs 7.92 ms
+    // for the train step; prefetch.global.L2 of the next tile's rows: no change (7.86 vs 7.83); setmaxnreg.inc for these warps
+    // without a matching .dec elsewhere never returns.
     const int grp = lane >> 3, sub = lane & 7;
     float b2acc[4] = {0.f, 0.f, 0.f, 0.f};          // partial sums of the (scaled) colour-logit gradients: channels 4 sub .. 4 sub + 3
     float b2sig = 0.f;
+    PROF_DECL();
     for (int i = 0; i < G; ++i) {
       const int b = i & 1;
       const long long gs0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * kM;
-      mbar_wait_parked(&s.in_free[b], ((uint32_t)(i >> 1) & 1u) ^ 1u);           // passes the first time round
+      PROF_T0();
       // tile-uniform index arithmetic once (64-bit divisions), 32-bit per sample: a tile straddles at most two images when an
       // image has >= 128 points (the launcher checks that), and (rr0 + sr) / S is a 32-bit division
       const long long n0 = gs0 / a.pts_per_img, rem0 = gs0 - n0 * a.pts_per_img;
       const long long ray0 = gs0 / a.S;
       const unsigned rr0 = (unsigned)(gs0 - ray0 * a.S);
-      // ---- taps of the tile's 128 samples x 3 planes (VR/renderer.py:39-65), the image of every sample
-      for (int task = tid; task < kM * 3; task += kLoadWarps * 32) {
-        const int sr = task / 3, p = task - sr * 3;
-        const long long gs = gs0 + sr;
-        Taps tp;
-        int n = 0;
-        if (gs < a.total) {
-          const float px = __fmul_rn(__ldg(a.pts + 3 * gs + 0), a.box_scale), py = __fmul_rn(__ldg(a.pts + 3 * gs + 1), a.box_scale),
-                      pz = __fmul_rn(__ldg(a.pts + 3 * gs + 2), a.box_scale);
-          plane_taps(p == 2 ? pz : px, p == 0 ? py : (p == 1 ? pz : px), a.H, a.W, tp);      // (x,y) (x,z) (z,x)
-          n = (int)n0 + (rem0 + sr >= a.pts_per_img ? 1 : 0);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) { tp.off[k] = 0; tp.w[k] = 0.0f; }
-        }
-        const int po = p * a.H * a.W * kC;
-        *reinterpret_cast<uint4*>(s.tap_off[b] + sr * 12 + p * 4) = make_uint4((uint32_t)(tp.off[0] + po), (uint32_t)(tp.off[1] + po),
-                                                                               (uint32_t)(tp.off[2] + po), (uint32_t)(tp.off[3] + po));
-        *reinterpret_cast<float4*>(s.tap_w[b] + sr * 12 + p * 4) = make_float4(tp.w[0], tp.w[1], tp.w[2], tp.w[3]);
-        if (p == 0) s.simg[b][sr] = n;
-      }
-      if (a.features == nullptr) named_bar_sync(1, kLoadWarps * 32);               // the gather below reads every warp's taps
-      // ---- features and the gradient of the decoder outputs: eight lanes per sample, 16 samples per warp
+      float4 f[2], colq[2], Aq[2];
+      float omq[2], gsq[2];
 #pragma unroll 1
-      for (int it = 0; it < 4; ++it) {
-        const int sr = warp * 16 + it * 4 + grp;
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int sr = warp * 16 + (2 * half + it) * 4 + grp;
         const long long gs = gs0 + sr;
-        float4 f = make_float4(0.f, 0.f, 0.f, 0.f), gy = f;
-        float gsg = 0.f;
+        f[it] = make_float4(0.f, 0.f, 0.f, 0.f); colq[it] = f[it]; Aq[it] = f[it]; omq[it] = 0.f; gsq[it] = 0.f;
         if (gs < a.total) {
           if (a.features != nullptr) {
-            f = __ldg(reinterpret_cast<const float4*>(a.features + gs * 32) + sub);
-          } else {
-            const float4* img = reinterpret_cast<const float4*>(a.planes + (size_t)s.simg[b][sr] * img_stride) + sub;
-#pragma unroll
-            for (int k = 0; k < 12; ++k) {
-              const float4 v = __ldg(img + (s.tap_off[b][sr * 12 + k] >> 2));
-              const float w = s.tap_w[b][sr * 12 + k];
-              f.x = fmaf(w, v.x, f.x); f.y = fmaf(w, v.y, f.y); f.z = fmaf(w, v.z, f.z); f.w = fmaf(w, v.w, f.w);
-            }
+            f[it] = __ldg(reinterpret_cast<const float4*>(a.features + gs * 32) + sub);
+          } else {                                 // not kept by the forward: gather again (VR/renderer.py:39-65)
+            const float px = __fmul_rn(__ldg(a.pts + 3 * gs + 0), a.box_scale), py = __fmul_rn(__ldg(a.pts + 3 * gs + 1), a.box_scale),
+                        pz = __fmul_rn(__ldg(a.pts + 3 * gs + 2), a.box_scale);
+            const int n = (int)n0 + (rem0 + sr >= a.pts_per_img ? 1 : 0);
+            f[it] = gather_point(a.planes + (size_t)n * img_stride, a.H, a.W, px, py, pz, sub);
           }
           const long long ray = ray0 + (rr0 + (unsigned)sr) / (unsigned)a.S;
-          const float4 colq = __ldg(reinterpret_cast<const float4*>(a.colours + gs * 32) + sub);
-          const float4 Aq = __ldg(reinterpret_cast<const float4*>(a.g_rgb + ray * 32) + sub);
-          const float omq = __ldg(a.omega + gs), gsq = __ldg(a.gsig + gs);
-          // rgb*2-1 (VR/ray_marcher.py:55), sigmoid*1.002 (training/triplane.py:134); times the operand scale
-          const float om = omq * (2.0f * 1.002f) * sc;
-          gsg = gsq * sc;
-          const float cc[4] = {colq.x, colq.y, colq.z, colq.w}, aa[4] = {Aq.x, Aq.y, Aq.z, Aq.w};
-          float g4[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float sv = (cc[k] + 0.001f) * (1.0f / 1.002f);           // sigmoid(logit)
-            g4[k] = aa[k] * om * sv * (1.0f - sv);
-            b2acc[k] += g4[k];
-          }
-          gy = make_float4(g4[0], g4[1], g4[2], g4[3]);
+          colq[it] = __ldg(reinterpret_cast<const float4*>(a.colours + gs * 32) + sub);
+          Aq[it] = __ldg(reinterpret_cast<const float4*>(a.g_rgb + ray * 32) + sub);
+          omq[it] = __ldg(a.omega + gs); gsq[it] = __ldg(a.gsig + gs);
         }
-        st_hilo4(s.f[b], sr, sub, f);
-        st_hilo4(s.y[b], sr, sub, gy);
+      }
+      PROF(0);
+      if (half == 0) mbar_wait_parked(&s.in_free[b], ((uint32_t)(i >> 1) & 1u) ^ 1u);   // the weight-gradient MMAs of tile i - 2 have read the tiles
+      PROF(2);
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int sr = warp * 16 + (2 * half + it) * 4 + grp;
+        const bool valid = gs0 + sr < a.total;
+        // rgb*2-1 (VR/ray_marcher.py:55), sigmoid*1.002 (training/triplane.py:134); times the operand scale
+        const float om = omq[it] * (2.0f * 1.002f) * sc;
+        const float gsg = gsq[it] * sc;
+        const float cc[4] = {colq[it].x, colq[it].y, colq[it].z, colq[it].w}, aa[4] = {Aq[it].x, Aq[it].y, Aq[it].z, Aq[it].w};
+        float g4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float sv = (cc[k] + 0.001f) * (1.0f / 1.002f);           // sigmoid(logit)
+          g4[k] = aa[k] * om * sv * (1.0f - sv);
+          b2acc[k] += g4[k];
+        }
+        st_hilo4(s.in[b].hi, s.in[b].lo, sr, 0, sub, f[it]);
+        st_hilo4(s.in[b].hi, s.in[b].lo, sr, 4, sub, make_float4(g4[0], g4[1], g4[2], g4[3]));
         if (sub == 0) {
           b2sig += gsg;
           s.gsig[b][sr] = gsg;
-          // unswizzled MN-major [128 x 16] fp16: (sample s, column n) at (s / 8) * 256 + (n / 8) * 128 + (s % 8) * 16 + (n % 8) * 2
+          // the third atom: columns (gsig hi, gsig lo, one, 0 ...) of this sample's row, 16-byte chunks 0 and 1
           const __half hi = __float2half_rn(gsg), lo = __float2half_rn(gsg - __half2float(hi));
-          uint8_t* rowp = s.s[b] + (sr >> 3) * 256 + (sr & 7) * 16;
-          const __half one = __float2half_rn(gs < a.total ? 1.0f : 0.0f), zero = __float2half_rn(0.0f);
-          __half* c0 = reinterpret_cast<__half*>(rowp);
-          c0[0] = hi; c0[1] = lo; c0[2] = one; c0[3] = zero; c0[4] = zero; c0[5] = zero; c0[6] = zero; c0[7] = zero;
-          *reinterpret_cast<uint4*>(rowp + 128) = make_uint4(0u, 0u, 0u, 0u);
+          const uint32_t w0 = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+          const uint32_t w1 = valid ? 0x3c00u : 0u;                       // fp16 1.0
+          uint8_t* rowp = s.in[b].sig + sr * 128;
+          *reinterpret_cast<uint4*>(rowp + ((0 ^ (sr & 7)) << 4)) = make_uint4(w0, w1, 0u, 0u);
+          *reinterpret_cast<uint4*>(rowp + ((1 ^ (sr & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
         }
+      }
+      PROF(3);
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.in_full[b]);
     }
+    PROF_FLUSH(0, 3, warp == 0);
     // gb2 (the bias of layer 2): sums of the outputs' gradients
     if (want_dec) {
 #pragma unroll
@@ -312,35 +326,66 @@ __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const A
     }
   } else if (warp < kLoadWarps + kScatWarps) {
     // ================================================ SCATTER ================================================
+    // Eight lanes per sample add GF x tap weight to the twelve texels of the sample (one 128-byte line each).  The taps are
+    // recomputed here from the sample's position, loaded before the wait for GF.
     const int sw = warp - kLoadWarps, grp = lane >> 3, sub = lane & 7;
+    const int plane_stride = a.H * a.W * kC;
+    PROF_DECL();
     for (int i = 0; i < G; ++i) {
       const int b = i & 1;
+      const long long gs0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * kM;
+      const long long n0 = gs0 / a.pts_per_img, rem0 = gs0 - n0 * a.pts_per_img;
+      PROF_T0();
+      float px[4], py[4], pz[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const long long gs = gs0 + sw * 16 + it * 4 + grp;
+        px[it] = py[it] = pz[it] = 0.f;
+        if (want_planes && gs < a.total) { px[it] = __ldg(a.pts + 3 * gs + 0); py[it] = __ldg(a.pts + 3 * gs + 1); pz[it] = __ldg(a.pts + 3 * gs + 2); }
+      }
+      PROF(4);
       mbar_wait_parked(&s.gf_ready[b], (uint32_t)(i >> 1) & 1u);
+      PROF(5);
       if (want_planes) {
-#pragma unroll 1
+#pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int sr = sw * 16 + it * 4 + grp;
-          const float4 gf = *reinterpret_cast<const float4*>(s.gf[b] + row_chunk_off(sr, sub));
-          float4* img = reinterpret_cast<float4*>(a.g_planes + (size_t)s.simg[b][sr] * img_stride) + sub;
+          if (gs0 + sr < a.total) {
+            const float4 gf = *reinterpret_cast<const float4*>(s.gf[b] + row_chunk_off(sr, sub));
+            const int n = (int)n0 + (rem0 + sr >= a.pts_per_img ? 1 : 0);
+            float* img = a.g_planes + (size_t)n * img_stride + sub * 4;
+            const float x = __fmul_rn(px[it], a.box_scale), y = __fmul_rn(py[it], a.box_scale), z = __fmul_rn(pz[it], a.box_scale);
 #pragma unroll
-          for (int k = 0; k < 12; ++k) {
-            const float w = s.tap_w[b][sr * 12 + k];
-            if (w != 0.0f) atomicAdd(img + (s.tap_off[b][sr * 12 + k] >> 2), make_float4(w * gf.x, w * gf.y, w * gf.z, w * gf.w));
+            for (int p = 0; p < 3; ++p) {
+              Taps tp;
+              plane_taps(p == 2 ? z : x, p == 0 ? y : (p == 1 ? z : x), a.H, a.W, tp);      // (x,y) (x,z) (z,x)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (tp.w[k] != 0.0f)
+                  atomicAdd(reinterpret_cast<float4*>(img + (unsigned)(p * plane_stride + tp.off[k])),
+                            make_float4(tp.w[k] * gf.x, tp.w[k] * gf.y, tp.w[k] * gf.z, tp.w[k] * gf.w));
+            }
           }
         }
       }
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&s.gf_free[b]); mbar_arrive(&s.in_free[b]); }
+      if (lane == 0) mbar_arrive(&s.gf_free[b]);
+      PROF(6);
     }
+    PROF_FLUSH(4, 6, sw == 0);
   } else if (warp < kLoadWarps + kScatWarps + kEpiWarps) {
     // ================================================ EPILOGUE ================================================
     const int q = warp & 3, hh = (warp - kLoadWarps - kScatWarps) >> 2;      // TMEM lane quarter (warps 16..23 -> 0..3, 0..3); hidden half
     const int row = q * 32 + lane;                            // the sample of this thread
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    PROF_DECL();
     for (int i = 0; i < G; ++i) {
       const int b = i & 1;
+      PROF_T0();
       mbar_wait_parked(&s.g12_done, (uint32_t)i & 1u);
+      PROF(7);
       if (i > 0) mbar_wait_parked(&s.wg_done, (uint32_t)(i - 1) & 1u);           // the H / GA tiles of the previous tile have been consumed
+      PROF(8);
       tcgen05_fence_after();
       const float gsg = s.gsig[b][row];
 #pragma unroll 1
@@ -366,9 +411,12 @@ __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const A
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.hga_ready);
+      PROF(9);
       // ---- GF -> shared memory (unscaled), for the scatter warps
       mbar_wait_parked(&s.g3_done, (uint32_t)i & 1u);
+      PROF(10);
       if (i > 1) mbar_wait_parked(&s.gf_free[b], (uint32_t)((i - 2) >> 1) & 1u);     // the scatter of tile i - 2 has read this buffer
+      PROF(11);
       tcgen05_fence_after();
       {
         const int c = hh;                                     // this warp's 16 of the 32 channels
@@ -384,7 +432,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const A
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.gf_ready[b]);
+      PROF(12);
     }
+    PROF_FLUSH(7, 12, q == 0 && hh == 0);
     // ---- flush the weight gradients accumulated in TMEM: rows 0..63 = GA rows (gW1t, gb1), rows 64..127 = H rows (gW2t)
     if (want_dec && G > 0) {
       mbar_wait_parked(&s.all_done, 0u);
@@ -393,28 +443,28 @@ __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const A
       uint32_t v[16], u[16];
       if (row < 64) {
 #pragma unroll 1
-        for (int c = hh; c < hh + 1; ++c) {     // DF columns [16 c, 16 c + 16) (x F hi) + [32 + 16 c, ...) (x F lo): channels k = 16 c ..
-          tmem_ld16(tmem + cDF + lane_base + 16 * c, v);
-          tmem_ld16(tmem + cDF + lane_base + 32 + 16 * c, u);
+        for (int c = hh; c < hh + 1; ++c) {     // x F hi + x F lo: channels k = 16 c ..
+          tmem_ld16(tmem + cW + lane_base + 64 + 16 * c, v);
+          tmem_ld16(tmem + cW + lane_base + 16 * c, u);
           tmem_wait_ld();
 #pragma unroll
           for (int k = 0; k < 16; ++k)
             atomicAdd(a.g_dec + kW1tOff + (16 * c + k) * kHid + j, (__uint_as_float(v[k]) + __uint_as_float(u[k])) * inv_sc);
         }
-        tmem_ld16(tmem + cDS + lane_base, v);
+        tmem_ld16(tmem + cW + lane_base + 128, v);
         tmem_wait_ld();
         if (hh == 0) atomicAdd(a.g_dec + kB1Off + j, __uint_as_float(v[2]) * inv_sc);        // x the ones column
       } else {
 #pragma unroll 1
         for (int c = hh; c < hh + 1; ++c) {
-          tmem_ld16(tmem + cDY + lane_base + 16 * c, v);
-          tmem_ld16(tmem + cDY + lane_base + 32 + 16 * c, u);
+          tmem_ld16(tmem + cW + lane_base + 96 + 16 * c, v);
+          tmem_ld16(tmem + cW + lane_base + 32 + 16 * c, u);
           tmem_wait_ld();
 #pragma unroll
           for (int k = 0; k < 16; ++k)
             atomicAdd(a.g_dec + kW2tOff + j * kOutPad + 1 + 16 * c + k, (__uint_as_float(v[k]) + __uint_as_float(u[k])) * inv_sc);
         }
-        tmem_ld16(tmem + cDS + lane_base, v);
+        tmem_ld16(tmem + cW + lane_base + 128, v);
         tmem_wait_ld();
         if (hh == 0) atomicAdd(a.g_dec + kW2tOff + j * kOutPad, (__uint_as_float(v[0]) + __uint_as_float(v[1])) * inv_sc);   // x gsig hi + lo
       }
@@ -424,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const A
     // ================================================ MMA issuer ================================================
     const uint32_t base16 = (smem_u32(&s) >> 4);
 #define OFF16(member) (base16 + (uint32_t)(offsetof(Smem, member) >> 4))
-    const uint32_t iF16_64 = instr_desc(kFmtF16, 128, 64), iF16_32 = instr_desc(kFmtF16, 128, 32), iF16_16 = instr_desc(kFmtF16, 128, 16);
+    const uint32_t iF16_64 = instr_desc(kFmtF16, 128, 64), iF16_32 = instr_desc(kFmtF16, 128, 32);
     // G1 + G2 of tile i (both only need the tile's inputs; D1 / GH are free: the epilogue of tile i - 1 has read them before it
     // published H / GA)
     auto issue_g12 = [&](int i, bool block) -> bool {
@@ -433,31 +483,36 @@ __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const A
       else if (!__shfl_sync(0xffffffffu, (int)mbar_try_wait(&s.in_full[b], (uint32_t)(i >> 1) & 1u), 0)) return false;
       tcgen05_fence_after();
       if (elect_one_sync()) {
-        // K-major operands, k-step = 32 bytes = 2 units; the lo halves start 4 units into the row
-        const uint32_t fa = OFF16(f) + (uint32_t)b * (kTile >> 4), ya = OFF16(y) + (uint32_t)b * (kTile >> 4);
+        // K-major operands, k-step = 32 bytes = 2 units; features in chunks 0-3 of a row, colour-logit gradients in chunks 4-7; W1 / W2
+        // rows are [hi | lo]: the lo halves start 4 units into the row
+        const uint32_t lo = OFF16(in) + (uint32_t)b * (uint32_t)(sizeof(Smem::In) >> 4), hi = lo + (kTile >> 4);
         const uint32_t w1 = OFF16(w1k), w2 = OFF16(w2c);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {       // G1: D1 = [F hi | F lo] . [W1 hi | W1 lo]
-          mma_f16_ss(tmem + cD1, make_desc(fa + 2 * ks, 1, 64, 2), make_desc(w1 + 2 * ks, 1, 64, 2), iF16_64, ks > 0);
-          mma_f16_ss(tmem + cD1, make_desc(fa + 4 + 2 * ks, 1, 64, 2), make_desc(w1 + 2 * ks, 1, 64, 2), iF16_64, true);
-          mma_f16_ss(tmem + cD1, make_desc(fa + 2 * ks, 1, 64, 2), make_desc(w1 + 4 + 2 * ks, 1, 64, 2), iF16_64, true);
+          mma_f16_ss(tmem + cD1, make_desc(hi + 2 * ks, 1, 64, 2), make_desc(w1 + 2 * ks, 1, 64, 2), iF16_64, ks > 0);
+          mma_f16_ss(tmem + cD1, make_desc(lo + 2 * ks, 1, 64, 2), make_desc(w1 + 2 * ks, 1, 64, 2), iF16_64, true);
+          mma_f16_ss(tmem + cD1, make_desc(hi + 2 * ks, 1, 64, 2), make_desc(w1 + 4 + 2 * ks, 1, 64, 2), iF16_64, true);
         }
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {       // G2: GH = [GYc hi | lo] . [W2c hi | lo]
-          mma_f16_ss(tmem + cGH, make_desc(ya + 2 * ks, 1, 64, 2), make_desc(w2 + 2 * ks, 1, 64, 2), iF16_64, ks > 0);
-          mma_f16_ss(tmem + cGH, make_desc(ya + 4 + 2 * ks, 1, 64, 2), make_desc(w2 + 2 * ks, 1, 64, 2), iF16_64, true);
-          mma_f16_ss(tmem + cGH, make_desc(ya + 2 * ks, 1, 64, 2), make_desc(w2 + 4 + 2 * ks, 1, 64, 2), iF16_64, true);
+          mma_f16_ss(tmem + cGH, make_desc(hi + 4 + 2 * ks, 1, 64, 2), make_desc(w2 + 2 * ks, 1, 64, 2), iF16_64, ks > 0);
+          mma_f16_ss(tmem + cGH, make_desc(lo + 4 + 2 * ks, 1, 64, 2), make_desc(w2 + 2 * ks, 1, 64, 2), iF16_64, true);
+          mma_f16_ss(tmem + cGH, make_desc(hi + 4 + 2 * ks, 1, 64, 2), make_desc(w2 + 4 + 2 * ks, 1, 64, 2), iF16_64, true);
         }
         mma_commit(&s.g12_done);
       }
       __syncwarp();
       return true;
     };
+    PROF_DECL();
     if (G > 0) issue_g12(0, true);
     for (int i = 0; i < G; ++i) {
       const int b = i & 1;
+      PROF_T0();
       mbar_wait_parked(&s.hga_ready, (uint32_t)i & 1u);                      // H and GA tiles are in shared memory
+      PROF(13);
       if (i > 0) mbar_wait_parked(&s.gf_ready[b ^ 1], (uint32_t)((i - 1) >> 1) & 1u);      // the previous GF has left TMEM
+      PROF(14);
       tcgen05_fence_after();
       const uint32_t gah = OFF16(ga_hi), gal = OFF16(ga_lo);
       if (elect_one_sync()) {
@@ -475,24 +530,16 @@ __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const A
       if (elect_one_sync()) {
         // WG: the weight gradients, accumulated over every tile of this CTA.  A = [GA ; H] (M = 128: two 64-element atoms along
         // MN, 16 KB apart = LBO 1024 units), MN-major: K = samples = rows, 16 rows = 2048 bytes = 128 units per k-step, 8-row
-        // groups 1024 bytes apart (SBO 64).  B = the F / GYc tiles, MN-major likewise (N = 64: hi | lo columns, or N = 32: hi only),
-        // and the unswizzled [128 x 16] gsig / ones tile (core matrices 128 bytes: MN stride 8 units, K-group stride 16 units).
+        // groups 1024 bytes apart (SBO 64).  B = the tile's three input atoms, MN-major likewise: [lo | hi | sig] x A hi (N = 144)
+        // and [hi | sig] x A lo (N = 80, onto columns 64..143) -- two MMAs per k-step; every MMA re-reads its 4 KB A slice from
+        // shared memory (32 cycles), which is what the six narrower MMAs per k-step of the first version were bound by
         if (want_dec) {
-          const uint32_t fa = OFF16(f) + (uint32_t)b * (kTile >> 4), ya = OFF16(y) + (uint32_t)b * (kTile >> 4);
-          const uint32_t sa = OFF16(s) + (uint32_t)b * ((kM * 32) >> 4);
-          const uint32_t mn64 = iF16_64 | kMajorMN, mn32 = iF16_32 | kMajorMN, mn16 = iF16_16 | kMajorMN;
+          const uint32_t lo = OFF16(in) + (uint32_t)b * (uint32_t)(sizeof(Smem::In) >> 4), hi = lo + (kTile >> 4);
+          const uint32_t mn144 = instr_desc(kFmtF16, 128, 144) | kMajorMN, mn80 = instr_desc(kFmtF16, 128, 80) | kMajorMN;
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
-            const bool acc = i > 0 || ks > 0;
-            const uint64_t ah = make_desc(gah + 128 * ks, 1024, 64, 2), al = make_desc(gal + 128 * ks, 1024, 64, 2);
-            const uint64_t bf = make_desc(fa + 128 * ks, 1024, 64, 2), by = make_desc(ya + 128 * ks, 1024, 64, 2);
-            const uint64_t bs = make_desc(sa + 32 * ks, 16, 8, 0);
-            mma_f16_ss(tmem + cDF, ah, bf, mn64, acc);          // [GA;H] hi x F (hi | lo)
-            mma_f16_ss(tmem + cDF, al, bf, mn32, true);         // [GA;H] lo x F hi
-            mma_f16_ss(tmem + cDY, ah, by, mn64, acc);          // x GYc (hi | lo)
-            mma_f16_ss(tmem + cDY, al, by, mn32, true);
-            mma_f16_ss(tmem + cDS, ah, bs, mn16, acc);          // x (gsig hi, gsig lo, ones)
-            mma_f16_ss(tmem + cDS, al, bs, mn16, true);
+            mma_f16_ss(tmem + cW, make_desc(gah + 128 * ks, 1024, 64, 2), make_desc(lo + 128 * ks, 1024, 64, 2), mn144, i > 0 || ks > 0);
+            mma_f16_ss(tmem + cW + 64, make_desc(gal + 128 * ks, 1024, 64, 2), make_desc(hi + 128 * ks, 1024, 64, 2), mn80, true);
           }
         }
         mma_commit(&s.wg_done);
@@ -502,8 +549,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const A
       __syncwarp();
       // (issuing G1 + G2 of the next tile AHEAD of the weight-gradient MMAs, so that its epilogue overlaps them, measured slower:
       // 7.2 vs 6.6 ms for the backward at config 2 -- the MMAs' completion is what frees the input buffer the loaders wait for)
+      PROF(15);
       if (i + 1 < G) issue_g12(i + 1, true);
+      PROF(16);
     }
+    PROF_FLUSH(13, 16, true);
 #undef OFF16
   }
   tcgen05_fence_before();
@@ -530,16 +580,33 @@ int launch_bwd_decode_tc(const float* planes, int H, int W, const float* dec, co
   Args a;
   a.planes = planes; a.H = H; a.W = W; a.dec = dec; a.pts = pts; a.colours = colours; a.features = features; a.gsig = gsig;
   a.omega = omega; a.g_rgb = g_rgb; a.total = total; a.pts_per_img = pts_per_img; a.S = S; a.box_scale = box_scale;
-  a.g_planes = g_planes; a.g_dec = g_dec; a.scale = scale_buf;
+  a.g_planes = g_planes; a.g_dec = g_dec; a.scale = scale_buf; a.prof = nullptr;
   { const char* dbg = getenv("TPR_BWD_DEBUG"); const int d = dbg ? atoi(dbg) : 0;      // profiling A/B: 1 = no scatter, 2 = no weight gradients
     if (d & 1) a.g_planes = nullptr;
     if (d & 2) a.g_dec = nullptr; }
-  e = cudaFuncSetAttribute(decode_backward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static const bool profile = getenv("TPR_BWD_PROFILE") != nullptr;
+  e = profile ? cudaFuncSetAttribute(decode_backward_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+              : cudaFuncSetAttribute(decode_backward_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   if (pts_per_img < kM) return -1;                 // (a tile may straddle at most two images)
   const long long n_tiles = (total + kM - 1) / kM;
   const long long grid = n_tiles < sms ? n_tiles : sms;
-  decode_backward_tc_kernel<<<(unsigned)grid, kThreads, smem, st>>>(a);
+  if (profile) {                                    // debugging aid: synchronous, prints CTA 0's cycles per role and phase
+    static const char* names[17] = {"load: issue loads", "-", "load: wait in_free", "load: operands", "scatter: load points",
+                                    "scatter: wait gf_ready", "scatter: red", "epi: wait g12_done", "epi: wait wg_done", "epi: H/GA",
+                                    "epi: wait g3_done", "epi: wait gf_free", "epi: GF", "mma: wait hga_ready", "mma: wait gf_ready",
+                                    "mma: issue G3+WG", "mma: wait in_full + issue G12"};
+    long long* prof = nullptr; long long host[17];
+    cudaMalloc(&prof, sizeof(host)); cudaMemsetAsync(prof, 0, sizeof(host), st);
+    a.prof = prof;
+    decode_backward_tc_kernel<true><<<(unsigned)grid, kThreads, smem, st>>>(a);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(host, prof, sizeof(host), cudaMemcpyDeviceToHost); cudaFree(prof);
+    const long long tiles0 = (n_tiles + grid - 1) / grid;
+    for (int k = 0; k < 17; ++k) fprintf(stderr, "[bwd profile] %-32s %8.0f cycles / tile\n", names[k], (double)host[k] / (double)tiles0);
+    return (int)cudaGetLastError();
+  }
+  decode_backward_tc_kernel<false><<<(unsigned)grid, kThreads, smem, st>>>(a);
   return (int)cudaGetLastError();
 }
 

@@ -147,6 +147,38 @@ extern "C" int64_t tpr_gather_microbench_v2(const float* buf, int64_t n_lines, i
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// The scatter shape of the backward pass: eight lanes add 16 bytes each (red.global.add.v4.f32) to one random
+// 128-byte line, `per_iter` lines per thread group and round.  lines * 128 B / time is the ceiling of the plane-gradient
+// scatter (12 such lines per sample).
+// ---------------------------------------------------------------------------------------------------------
+namespace tpr {
+__global__ void scatter_bench_kernel(float* __restrict__ buf, uint32_t n_lines, int per_iter, int iters) {
+  const uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, sub = threadIdx.x & 7;
+  uint32_t state = group * 2654435761u + 12345u;
+  const float4 v = make_float4(1.0f, 0.5f, 0.25f, 0.125f);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll 4
+    for (int k = 0; k < per_iter; ++k) {
+      state = state * 1664525u + 1013904223u;
+      const uint32_t line = (uint32_t)(((uint64_t)(state ^ (state >> 15)) * n_lines) >> 32);
+      atomicAdd(reinterpret_cast<float4*>(buf + (size_t)line * 32) + sub, v);
+    }
+  }
+}
+}  // namespace tpr
+
+extern "C" int64_t tpr_scatter_microbench(float* buf, int64_t n_lines, int32_t ctas, int32_t threads, int32_t per_iter, int32_t iters,
+                                          void* stream) {
+  if (!buf || n_lines <= 0 || n_lines > 0x7fffffff || ctas <= 0 || iters <= 0 || per_iter <= 0 || threads < 32 || threads > 1024 ||
+      (threads & 31))
+    return TPR_E_SHAPE;
+  tpr::scatter_bench_kernel<<<ctas, threads, 0, (cudaStream_t)stream>>>(buf, (uint32_t)n_lines, per_iter, iters);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return -(int64_t)e - 1000;
+  return (int64_t)ctas * (threads / 8) * per_iter * iters;                             // lines added to
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // tcgen05.mma cost for the small shapes of the decoder: `count` back-to-back MMAs of M = 128, N = n, one K step
 // each (tf32: K = 8, bf16: K = 16), A from shared memory (SS) or TMEM (TS), issued by one thread.  Reports
 // cycles from the first issue to the commit's arrival, and the issue-only cycles.

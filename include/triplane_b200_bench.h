@@ -33,6 +33,11 @@ int64_t tpr_gather_microbench_ex(const float* buf, int64_t n_lines, int32_t ctas
 int64_t tpr_gather_microbench_v2(const float* buf, int64_t n_lines, int32_t ctas, int32_t threads, int32_t vec_floats,
                                  int32_t in_flight, int32_t pipelined, int32_t iters, float* sink, void* stream);
 
+/* The backward pass's scatter shape: eight lanes add 16 bytes each (red.global.add.v4.f32) to random 128-byte lines of
+ * buf[n_lines*32 floats]; per_iter lines per eight-lane group and round, `iters` rounds.  Returns the lines added to. */
+int64_t tpr_scatter_microbench(float* buf, int64_t n_lines, int32_t ctas, int32_t threads, int32_t per_iter, int32_t iters,
+                               void* stream);
+
 /* Issues `count` tcgen05.mma (M = 128, N = n, one K step; tf32 or bf16 operands; A from shared memory or TMEM)
  * from one thread of one CTA; tight != 0 issues them from precomputed descriptors (count % 4 == 0).
  * out_dev[0] = cycles spent issuing, out_dev[1] = cycles until all have completed. */
