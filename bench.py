@@ -375,6 +375,51 @@ def leg_train_step(cx, planes, origins, dirs, opts):
                     'inputs resident in HBM; forward as above, backward = tpr_render_backward'}
 
 
+class SharedHostOutputs:
+    """N > 1: ONE host buffer for the whole job's outputs (a POSIX shared-memory file mapped by every rank and registered with
+    CUDA as pinned memory); rank r's device -> host copies land in slice r, so that after the step's barrier the gathered
+    [world * N_IMG, M, 32 | 1 | 1] result sits in host memory that rank 0 -- the caller -- reads.  No extra copy: the gather is
+    where the D2H copies point."""
+
+    def __init__(self, cx, n_img, m):
+        import mmap
+        torch = cx.torch
+        self.cx, self.torch = cx, torch
+        self.path = f'/dev/shm/tpr_bench_{os.environ.get("MASTER_PORT", "0")}'
+        shapes = [(cx.world * n_img, m, c) for c in (32, 1, 1)]
+        sizes = [int(np.prod(sh)) * 4 for sh in shapes]
+        total = sum(sizes)
+        if cx.rank == 0:
+            with open(self.path, 'wb') as f:
+                f.truncate(total)
+        cx.barrier()
+        self.fd = os.open(self.path, os.O_RDWR)
+        self.mm = mmap.mmap(self.fd, total)
+        whole = torch.from_numpy(np.frombuffer(self.mm, dtype=np.float32))
+        rc = torch.cuda.cudart().cudaHostRegister(whole.data_ptr(), total, 0)
+        if int(rc) != 0:
+            raise RuntimeError(f'cudaHostRegister failed: {rc}')
+        self.whole = whole
+        self.all, off = [], 0
+        for sh, sz in zip(shapes, sizes):
+            self.all.append(whole[off // 4:(off + sz) // 4].view(sh))
+            off += sz
+        self.mine = tuple(t[cx.rank * n_img:(cx.rank + 1) * n_img] for t in self.all)      # contiguous slices
+        cx.barrier()
+        if cx.rank == 0:
+            os.unlink(self.path)                     # mapped everywhere by now: the name can go
+
+    def close(self):
+        self.torch.cuda.synchronize()
+        self.torch.cuda.cudart().cudaHostUnregister(self.whole.data_ptr())
+        self.mine = self.all = self.whole = None
+        try:
+            self.mm.close()
+        except BufferError:                          # (a numpy view still alive: the mapping goes with the process)
+            pass
+        os.close(self.fd)
+
+
 def leg_h2d_ceiling(cx, planes_pin, out_pin):
     """Bare concurrent copies of the e2e path's bytes (pinned host -> device of this rank's planes, device -> pinned host of
     its outputs), all ranks at once, nothing rendered: what the host can feed N GPUs."""
@@ -788,7 +833,8 @@ def main():
     # ---- end to end: the forward with HOST buffers (ImportanceRenderer.forward_host -> tpr_render_host): every step
     # copies that step's planes and rays from pinned host memory and reads rgb / depth / weight sums back to the host
     planes_pin, o_pin, d_pin = planes_h.pin_memory(), origins.cpu().pin_memory(), dirs.cpu().pin_memory()
-    out_pin = tuple(torch.empty((N_IMG, m, c), dtype=torch.float32).pin_memory() for c in (32, 1, 1))
+    shared_out = SharedHostOutputs(cx, N_IMG, m) if world > 1 else None
+    out_pin = shared_out.mine if world > 1 else tuple(torch.empty((N_IMG, m, c), dtype=torch.float32).pin_memory() for c in (32, 1, 1))
     h2d = planes_pin.numel() * 4 + o_pin.numel() * 4 + d_pin.numel() * 4
     d2h = sum(t.numel() * 4 for t in out_pin)
 
@@ -806,6 +852,18 @@ def main():
 
     e2e_steps = max(3, min(args.steps, 10))
     e2e_ms = cx.time_steps(e2e_step, e2e_steps, warmup=2)
+    e2e_gathered = None
+    if world > 1:
+        # the gathered result is in rank 0's address space: the file starts zero-filled, so finite non-zero data in EVERY rank's
+        # slice, seen from rank 0, is every rank's D2H copies having landed in the one buffer
+        cx.barrier()
+        filled = True
+        if rank == 0:
+            for r in range(world):
+                for t in shared_out.all:
+                    sl = t[r * N_IMG:(r + 1) * N_IMG]
+                    filled = filled and bool(torch.isfinite(sl).all()) and float(sl.abs().max()) > 0.0
+        e2e_gathered = cx.all_ok(filled)
     ms, kern_ms = cx.max_over_ranks(ms, kern_ms)
 
     # ---- the other configurations / baselines, each bounded to seconds; a failing leg reports its error, never kills the line
@@ -829,6 +887,9 @@ def main():
     if peer is not None:
         peer.close()
         peer = None
+    if shared_out is not None:
+        out_pin = None
+        shared_out.close()
     if world == 1:
         run_leg('train_step', lambda: leg_train_step(cx, planes, origins, dirs, opts) if args.mode != 'fp32_ffma'
                 else {'unavailable': 'fp32_ffma'})
@@ -880,7 +941,9 @@ def main():
             'e2e': {'value': world * samples_per_step / (e2e_ms * 1e-3), 'unit': METRIC, 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'api': 'ImportanceRenderer.forward_host (tpr_render_host: per-image H2D / repack+render / D2H pipeline)'
-                    if world == 1 else 'ImportanceRenderer.forward_host(defer_depth) + 2-float all-reduce + finish_host_depth'},
+                    if world == 1 else 'ImportanceRenderer.forward_host(defer_depth) + 2-float all-reduce + finish_host_depth; every rank\'s '
+                    'D2H copies land in its slice of ONE shared pinned host buffer (the gathered result, readable by rank 0)',
+                    'outputs_gathered_on_host': e2e_gathered},
             'gpu_launches': 5 * args.steps,                    # pack_planes, pack_decoder, range_init, render_ws, finish
             'clocks': clocks,
             'notes': {'gather': ('outputs gathered by the render kernel (NVLink peer stores) + 2-float all-reduce' if args.gather == 'peer'

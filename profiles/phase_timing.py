@@ -13,9 +13,8 @@ R, S = pkg.ImportanceRenderer(), pkg.RaySampler()
 planes = planes_h.to(dev); o, d = S(c2w.to(dev), K.to(dev), 128)
 WS = ['GATHER wait coarse_ready', 'GATHER wait fine_ready', 'GATHER wait a1_free', 'GATHER gather+publish',
       'DECODE wait a1_full (issuer)', 'DECODE issue M1 + slot', 'DECODE wait d1_full', 'DECODE epilogue1', 'DECODE wait a2_full (issuer)',
-      'DECODE issue M2', 'DECODE wait m2_done', 'DECODE sigma readback', 'RAYS setup', 'RAYS wait csig', 'RAYS resample',
+      'DECODE issue M2', 'DECODE sigma halves exchange (named barrier)', 'DECODE publish sigma (arrive)', 'RAYS setup', 'RAYS wait csig', 'RAYS resample',
       'RAYS wait fsig', 'RAYS sort+march', 'RAYS composite', 'RAYS   (merge / pair rank count at 96+96: part of the sort, not counted in sort+march)']
-TC = ['setup', 'G0+sync', 'issueM1', 'G(t+1)', 'wait bar1/2', 'E1+sync', 'issueM2', 'pass-end wait+sigma', 'resample', 'sort', 'composite']
 D = int(os.environ.get('TPR_PT_DEPTH', '48'))          # samples per pass (96 = gen_videos / config 4)
 RPG = 8 if D <= 48 else 4                                # rays per group the kernel picks
 for mode in sys.argv[1:] or ['fp32']:
@@ -24,6 +23,6 @@ for mode in sys.argv[1:] or ['fp32']:
     torch.cuda.synchronize()
     t = R.last_scratch[64:64 + 24 * 8].view(torch.int64).cpu().numpy()
     ngroups = 16384 * 8 / RPG / 148
-    names = TC if os.environ.get('TPR_RENDER_IMPL') == '1' else WS
+    names = WS
     print(mode, 'CTA0 cycles per group (', int(ngroups), 'groups )')
     for n, v in zip(names, t): print(f'  {n:32s} {int(v / ngroups):7d}')
