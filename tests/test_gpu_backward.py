@@ -109,6 +109,14 @@ def test_backward_is_linear_in_the_upstream_gradient_and_respects_requires_grad(
     _, g2 = run_backward(pkg, scene, opts, 2 * A, 2 * B, 2 * C)
     for a, b in zip(g1, g2):
         assert rel_err((2 * a).cpu().numpy(), b.cpu().numpy()) < 1e-5
+    # gradients come at any scale (loss scaling): the backward rescales its fp16 gradient-side operands by a power of two
+    # taken from the upstream gradient's magnitude (csrc/tpr_backward_tc.cu: scale_kernel), so 2^-20 x and 2^20 x the upstream
+    # gradient give exactly-scaled results, neither flushed to zero nor saturated
+    for k in (-20, 20):
+        f = float(2.0 ** k)
+        _, gk = run_backward(pkg, scene, opts, f * A, f * B, f * C)
+        for a, b in zip(g1, gk):
+            assert rel_err((f * a).cpu().numpy(), b.cpu().numpy()) < 1e-5, k
     # planes only: the decoder stays frozen and gets no .grad
     dec = make_decoder(pkg, scene['dec'])
     planes = T(scene['planes']).requires_grad_(True)

@@ -1,5 +1,7 @@
-"""GPU: BASELINE.json's full config-2 shape, EVERY ray, against the torch restatement of the reference running on the same
-GPU (oracle/torch_oracle.py, pinned on CPU against the reference fixtures by tests/test_torch_oracle.py).
+"""GPU: BASELINE.json's full config-2 shape, EVERY ray: the whole 8-image batch against the UNMODIFIED reference on the same
+GPU from the same generator state (oracle/_ref), and an image pair with injected draws against the torch restatement
+(oracle/torch_oracle.py, pinned on CPU against the reference fixtures by tests/test_torch_oracle.py), which also exposes the
+intermediate stages (importance depths, searchsorted indices).
 
 Gates (BASELINE.json north_star): fp32 mode max-abs <= 1e-4 on rgb / depth / weight sum; bf16-MLP mode PSNR >= 50 dB;
 sample_pdf bin indices bit-exact given identical weights / bins / u."""
@@ -7,6 +9,7 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import ref_loader
 from oracle import triplane_oracle as O
 from oracle import torch_oracle as TO
 from tests.test_gpu_parity import T, make_decoder, TOL, dev
@@ -53,6 +56,34 @@ def test_config2_every_ray_fp32_and_bf16(pkg, full_scene):
             'depth': _psnr(got16[1].cpu().numpy(), want[1].cpu().numpy(), opts['ray_end'] - opts['ray_start'])}
     print('bf16-MLP PSNR vs torch-on-GPU (dB):', psnr)
     assert min(psnr.values()) >= 50.0, psnr
+
+
+@pytest.mark.skipif(ref_loader.reference_dir() is None, reason='oracle/_ref (python oracle/build_ref.py) not present')
+def test_config2_full_batch_against_the_unmodified_reference(pkg):
+    """BASELINE configs[1] as the bench runs it -- 8 images x 128^2 rays x (48+48), 3x32x256^2 planes -- through the
+    reference's own ImportanceRenderer.forward (VR/renderer.py:88-140) and ours, both drawing their noise from the same CUDA
+    generator state.  1e-4 on every ray of every image; bf16-MLP mode >= 50 dB; the generator ends in the same state."""
+    from tests.test_gpu_reference import _both, _decoders, _psnr as psnr_t
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    ref = ref_loader.import_reference()
+    g = torch.Generator().manual_seed(5)
+    planes = torch.randn((8, 3, 32, 256, 256), generator=g).to(dev())
+    scene = O.synthetic_scene(22, 8, 128, 8, 2, 2, 0.5)                      # (only its cameras / rays are used)
+    o, d = T(scene['origins']), T(scene['dirs'])
+    theirs, ours = _decoders(pkg, ref)
+    opts = dict(O.FFHQ_OPTIONS)
+    want, got, s_ref, s_ours = _both(pkg, ref, planes, theirs, ours, o, d, opts)
+    errs = {k: float((a - b).abs().max()) for k, a, b in zip(('rgb', 'depth', 'wsum'), got, want)}
+    print('config 2, 8 images x 16384 rays, fp32 max-abs vs the unmodified reference on the same GPU:', errs)
+    assert max(errs.values()) < TOL, errs
+    assert torch.equal(s_ref, s_ours)
+    torch.manual_seed(1)
+    with torch.no_grad():
+        got16 = pkg.ImportanceRenderer()(planes, ours, o, d, dict(opts, decoder_precision='bf16'))
+    db = {'rgb': psnr_t(got16[0], want[0], 2.0), 'depth': psnr_t(got16[1], want[1], opts['ray_end'] - opts['ray_start'])}
+    print('bf16-MLP PSNR vs the reference (dB):', db)
+    assert min(db.values()) >= 50.0, db
 
 
 def test_config2_sample_importance_indices_bit_exact(pkg, full_scene):
