@@ -132,7 +132,16 @@ __device__ __forceinline__ void gather_tile(const RenderArgs& a, float* a1_hi, c
   asm volatile("" : "+l"(base));
 #pragma unroll 1
   for (int rd = 0; rd < 2; ++rd) {
+    // One warp instruction stores four rows of the operand tile.  The 128-byte swizzle XORs a row's 16-byte chunk index with
+    // (row & 7), so rows that differ only in bits 0-1 put their 64 bytes into the SAME 16 banks: rows {0,1,2,3} per round was a
+    // 4-way conflict on every operand store (ncu: 49.8 M conflicts of 232 M shared wavefronts).  Rows {0,1,4,5} / {2,3,6,7}
+    // split a round over both bank halves: two wavefronts for 256 bytes, the minimum.  (Same-box A/B, profiles/r02_ab_rows_*:
+    // neutral -- fp32 2.222 vs 2.216 ms, bf16 2.100 vs 2.105 ms: the L1 data pipe is not where the gather waits.)
+#if !defined(TPR_ROWS_INTERLEAVED) || TPR_ROWS_INTERLEAVED
+    const int s = (grp & 1) | ((grp >> 1) << 2) | (rd << 1);
+#else
     const int s = rd * 4 + grp;
+#endif
     const int row = warp * 8 + s;
     const int r = row >> dpt_shift, di = t * dpt + (row & (dpt - 1));
     if (r < nr && di < Dx) {
