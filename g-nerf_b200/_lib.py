@@ -11,7 +11,7 @@ from ctypes import c_char_p, c_double, c_float, c_int32, c_int64, c_size_t, c_vo
 
 from .build import LIB_PATH, BENCH_LIB_PATH
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MLP_FP32, MLP_BF16, MLP_FFMA = 0, 1, 2
 LAYOUT_CHANNELS_LAST, LAYOUT_CHANNELS_FIRST = 0, 1
 
@@ -39,6 +39,7 @@ _SIGNATURES = {
     'tpr_last_error': (c_char_p, []),
     'tpr_packed_planes_bytes': (c_size_t, [c_int64, c_int32, c_int32]),
     'tpr_pack_planes': (ctypes.c_int, [_P, c_int64, c_int32, c_int32, _P, _P]),
+    'tpr_unpack_planes': (ctypes.c_int, [_P, c_int64, c_int32, c_int32, _P, _P]),
     'tpr_packed_decoder_bytes': (c_size_t, []),
     'tpr_pack_decoder': (ctypes.c_int, [_P, _P, _P, _P, c_float, c_float, c_float, c_float, _P, _P]),
     'tpr_ray_sample': (ctypes.c_int, [_P, _P, c_int64, c_int32, _P, _P, _P]),

@@ -68,6 +68,28 @@ __global__ void __launch_bounds__(256) pack_planes_kernel(const float* __restric
   }
 }
 
+// [P][HW][32] -> [P][32][HW]: the adjoint (plane gradients back to the backbone's layout)
+__global__ void __launch_bounds__(256) unpack_planes_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                            int hw, int tiles_per_plane) {
+  __shared__ float tile[32][33];
+  const int plane = blockIdx.x / tiles_per_plane;
+  const int p0 = (blockIdx.x - plane * tiles_per_plane) * 32;
+  const float* s = src + (size_t)plane * kC * hw;
+  float* d = dst + (size_t)plane * kC * hw;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int pp = ty; pp < 32; pp += 8) {
+    const int p = p0 + pp;
+    tile[pp][tx] = p < hw ? s[(size_t)p * kC + tx] : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = ty; c < 32; c += 8) {
+    const int p = p0 + tx;
+    if (p < hw) d[(size_t)c * hw + p] = tile[tx][c];
+  }
+}
+
 __global__ void pack_decoder_kernel(const float* __restrict__ w1, const float* __restrict__ b1,
                                     const float* __restrict__ w2, const float* __restrict__ b2,
                                     float g_w1, float g_b1, float g_w2, float g_b2, float* __restrict__ out) {
@@ -609,6 +631,20 @@ int tpr_pack_planes(const float* planes_nchw, int64_t n_img, int32_t height, int
   if (blocks > 0x7fffffffLL) return fail(TPR_E_SHAPE, "tpr_pack_planes: too many tiles");
   pack_planes_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(planes_nchw, planes_packed, hw, tiles);
   TPR_CHECK_LAUNCH("pack_planes_kernel");
+  return 0;
+}
+
+int tpr_unpack_planes(const float* planes_packed, int64_t n_img, int32_t height, int32_t width, float* planes_nchw,
+                      void* stream) {
+  if (!planes_nchw || !planes_packed) return fail(TPR_E_NULL, "tpr_unpack_planes: NULL pointer");
+  if (n_img <= 0 || height <= 0 || width <= 0 || (int64_t)height * width > (1 << 26))
+    return fail(TPR_E_SHAPE, "tpr_unpack_planes: bad shape");
+  const int hw = height * width;
+  const int tiles = (hw + 31) / 32;
+  const long long blocks = (long long)n_img * TPR_PLANES * tiles;
+  if (blocks > 0x7fffffffLL) return fail(TPR_E_SHAPE, "tpr_unpack_planes: too many tiles");
+  unpack_planes_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(planes_packed, planes_nchw, hw, tiles);
+  TPR_CHECK_LAUNCH("unpack_planes_kernel");
   return 0;
 }
 

@@ -76,8 +76,13 @@ class _Render(torch.autograd.Function):
                 g_b2 = torch.empty(33, device=dev, dtype=torch.float32)
                 _lib.check(L.tpr_unpack_decoder_grad(p(g_dec), *ctx.gains, p(g_w1), p(g_b1), p(g_w2), p(g_b2), st()),
                            'tpr_unpack_decoder_grad')
-        # the plane gradient lives in the packed layout [N,3,H,W,32]; hand autograd its [N,3,32,H,W] view (no copy)
-        return (None, None, None, None, g_planes.permute(0, 1, 4, 2, 3) if need[4] else None,
+            g_nchw = None
+            if want_planes:
+                # the plane gradient was scattered in the packed layout [N,3,H,W,32]; the backbone wants [N,3,32,H,W] contiguous
+                # (autograd would otherwise make that copy itself, strided: 0.22 ms vs 0.08 ms for 201 MB at config 2)
+                g_nchw = torch.empty((n, 3, 32, pp.height, pp.width), device=dev, dtype=torch.float32)
+                _lib.check(L.tpr_unpack_planes(p(g_planes), n, pp.height, pp.width, p(g_nchw), st()), 'tpr_unpack_planes')
+        return (None, None, None, None, g_nchw,
                 g_w1 if need[5] else None, g_b1 if need[6] else None, g_w2 if need[7] else None, g_b2 if need[8] else None,
                 None, None)
 

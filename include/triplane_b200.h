@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TPR_ABI_VERSION 7
+#define TPR_ABI_VERSION 8
 
 /* fixed by the reference model: OSGDecoder(32 -> 64 -> 1+32), three planes
  * (training/triplane.py:42,113-122; VR/renderer.py:29-37) */
@@ -106,6 +106,10 @@ const char* tpr_last_error(void);
 size_t tpr_packed_planes_bytes(int64_t n_img, int32_t height, int32_t width);
 int tpr_pack_planes(const float* planes_nchw, int64_t n_img, int32_t height, int32_t width,
                     float* planes_packed, void* stream);
+/* The inverse transpose, [N,3,H,W,32] -> [N,3,32,H,W]: the plane gradient of tpr_render_backward in the layout autograd hands to
+ * the backbone (the adjoint of the pack above; training/triplane.py:74). */
+int tpr_unpack_planes(const float* planes_packed, int64_t n_img, int32_t height, int32_t width, float* planes_nchw,
+                      void* stream);
 
 /* Decoder parameters as stored by OSGDecoder.net[0]/net[2] (training/triplane.py:118-122) plus
  * the runtime gains FullyConnectedLayer applies on every call (training/networks_stylegan2.py:

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(pkg):
     for s in header_symbols():
         assert hasattr(lib, s), f'{s} declared in the header but not exported'
     assert set(header_symbols()) == set(pkg._lib.EXPORTED_SYMBOLS), 'binding and header disagree'
-    assert lib.tpr_abi_version() == 7
+    assert lib.tpr_abi_version() == 8
 
 
 def test_options_struct_layout_matches_header(pkg):

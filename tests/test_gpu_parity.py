@@ -53,6 +53,16 @@ def test_pack_planes_is_a_pure_transpose(pkg, name):
     scene, _, _ = load_case(name)
     pp = pkg.pack_planes(T(scene['planes']))
     np.testing.assert_array_equal(pp.data.cpu().numpy(), scene['planes'].transpose(0, 1, 3, 4, 2))
+    # and back (tpr_unpack_planes: the layout the backward hands its plane gradient to autograd in)
+    import ctypes
+    from importlib import import_module
+    L = import_module('g-nerf_b200')._lib.lib()
+    n, _, _, h, w = scene['planes'].shape
+    back = torch.empty((n, 3, 32, h, w), device=dev())
+    rc = L.tpr_unpack_planes(ctypes.c_void_p(pp.data.data_ptr()), n, h, w, ctypes.c_void_p(back.data_ptr()),
+                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    np.testing.assert_array_equal(back.cpu().numpy(), scene['planes'])
 
 
 @pytest.mark.parametrize('name', list(CASES))
