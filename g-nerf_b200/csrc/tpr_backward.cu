@@ -57,7 +57,8 @@ __global__ void points_kernel(const float* __restrict__ origins, const float* __
 struct MarchArgs {
   const float* dc; const float* df; int Dc, Df;
   const float* sigma;            // [rays, S]
-  const float* colours;          // [rays, S, 32]
+  const float* colours;          // [rays, S, 32], or (chunked != 0) [rays, 8, S, 4] as tpr_render_train keeps them
+  int chunked;
   const float* g_rgb;            // [rays, 32]
   const float* g_depth;          // [rays]
   const float* g_wsum;           // [rays]
@@ -99,11 +100,13 @@ __global__ void __launch_bounds__(128) march_backward_kernel(const MarchArgs a) 
     for (int p = lane; p < S; p += 32) {
       z[p] = p < a.Dc ? __ldg(a.dc + g * a.Dc + p) : __ldg(a.df + g * a.Df + (p - a.Dc));
       sg[p] = __ldg(a.sigma + g * S + p);
-      const float4* row = reinterpret_cast<const float4*>(a.colours + (g * S + p) * 32);
+      // sample-major rows: float4 c4 of sample p at row + c4; chunk-major: at chunk c4's run of the ray + p (coalesced over lanes)
+      const float4* row = reinterpret_cast<const float4*>(a.colours + g * S * 32) + (a.chunked ? p : p * 8);
+      const int cstep = a.chunked ? S : 1;
       float acc = 0.0f;
 #pragma unroll
       for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 v = __ldg(row + c4);
+        const float4 v = __ldg(row + c4 * cstep);
         acc = fmaf(A2[4 * c4], v.x, acc); acc = fmaf(A2[4 * c4 + 1], v.y, acc);
         acc = fmaf(A2[4 * c4 + 2], v.z, acc); acc = fmaf(A2[4 * c4 + 3], v.w, acc);
       }
@@ -234,7 +237,8 @@ struct DecArgs {
   const float* planes; int H, W;        // packed [N,3,H,W,32]
   const float* dec;                     // packed decoder
   const float* pts;                     // [T,3]
-  const float* colours;                 // [T,32]
+  const float* colours;                 // [T,32], or (col_chunked != 0) [rays, 8, S, 4]
+  int col_chunked;
   const float* features;                // [T,32] summed plane features kept by the forward, or NULL: gather them again
   const float* gsig; const float* omega;// [T]
   const float* g_rgb;                   // [rays,32]
@@ -352,7 +356,9 @@ __global__ void __launch_bounds__(kBT, 2) decode_backward_kernel(const DecArgs a
       float gs_sig = 0.0f;
       if (gs < a.total) {
         const long long ray = ray0 + (unsigned)(rr0 + sr) / (unsigned)a.S;
-        const float4 col = __ldg(reinterpret_cast<const float4*>(a.colours + gs * 32) + sub);
+        const float4 col = a.col_chunked
+            ? __ldg(reinterpret_cast<const float4*>(a.colours + ray * a.S * 32) + sub * a.S + (gs - ray * a.S))
+            : __ldg(reinterpret_cast<const float4*>(a.colours + gs * 32) + sub);
         const float4 A = __ldg(reinterpret_cast<const float4*>(a.g_rgb + ray * 32) + sub);
         const float om = __ldg(a.omega + gs) * (2.0f * 1.002f);       // rgb*2-1 (VR/ray_marcher.py:55), sigmoid*1.002 (training/triplane.py:134)
         gs_sig = __ldg(a.gsig + gs);
@@ -615,11 +621,11 @@ int launch_bwd_points(const float* origins, const float* dirs, const float* dc, 
   return (int)cudaGetLastError();
 }
 
-int launch_bwd_march(const float* dc, const float* df, int Dc, int Df, const float* sigma, const float* colours,
+int launch_bwd_march(const float* dc, const float* df, int Dc, int Df, const float* sigma, const float* colours, int col_chunked,
                      const float* g_rgb, const float* g_depth, const float* g_wsum, const float* range, int white_back,
                      long long n_rays_total, float* gsig, float* omega, int sms, cudaStream_t st) {
   bwd::MarchArgs a;
-  a.dc = dc; a.df = df; a.Dc = Dc; a.Df = Df; a.sigma = sigma; a.colours = colours; a.g_rgb = g_rgb; a.g_depth = g_depth;
+  a.dc = dc; a.df = df; a.Dc = Dc; a.Df = Df; a.sigma = sigma; a.colours = colours; a.chunked = col_chunked; a.g_rgb = g_rgb; a.g_depth = g_depth;
   a.g_wsum = g_wsum; a.range = range; a.white_back = white_back; a.n_rays = n_rays_total; a.gsig = gsig; a.omega = omega;
   const int S = Dc + Df;
   const size_t smem = (size_t)4 * 7 * S * sizeof(float);
@@ -635,11 +641,11 @@ int launch_bwd_march(const float* dc, const float* df, int Dc, int Df, const flo
   return (int)cudaGetLastError();
 }
 
-int launch_bwd_decode(const float* planes, int H, int W, const float* dec, const float* pts, const float* colours,
+int launch_bwd_decode(const float* planes, int H, int W, const float* dec, const float* pts, const float* colours, int col_chunked,
                       const float* features, const float* gsig, const float* omega, const float* g_rgb, long long total, long long pts_per_img, int S,
                       float box_scale, float* g_planes, float* g_dec, int fast, int skip, int sms, cudaStream_t st) {
   bwd::DecArgs a;
-  a.planes = planes; a.H = H; a.W = W; a.dec = dec; a.pts = pts; a.colours = colours; a.features = features; a.gsig = gsig; a.omega = omega;
+  a.planes = planes; a.H = H; a.W = W; a.dec = dec; a.pts = pts; a.colours = colours; a.col_chunked = col_chunked; a.features = features; a.gsig = gsig; a.omega = omega;
   a.g_rgb = g_rgb; a.total = total; a.pts_per_img = pts_per_img; a.S = S; a.box_scale = box_scale; a.g_planes = g_planes;
   a.g_dec = g_dec;
   { const char* e = getenv("TPR_BWD_DEBUG"); a.debug = skip | (e ? atoi(e) : 0); }

@@ -79,7 +79,8 @@ struct Args {
   const float* planes; int H, W;        // packed [N,3,H,W,32]
   const float* dec;                     // packed decoder
   const float* pts;                     // [T,3]
-  const float* colours;                 // [T,32]
+  const float* colours;                 // [T,32], or (col_chunked != 0) [rays, 8, S, 4] as tpr_render_train keeps them
+  int col_chunked;
   const float* features;                // [T,32] kept by the forward, or NULL: gather again
   const float* gsig; const float* omega;// [T]
   const float* g_rgb;                   // [rays,32]
@@ -269,7 +270,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const A
             f[it] = gather_point(a.planes + (size_t)n * img_stride, a.H, a.W, px, py, pz, sub);
           }
           const long long ray = ray0 + (rr0 + (unsigned)sr) / (unsigned)a.S;
-          colq[it] = __ldg(reinterpret_cast<const float4*>(a.colours + gs * 32) + sub);
+          colq[it] = a.col_chunked
+              ? __ldg(reinterpret_cast<const float4*>(a.colours + ray * a.S * 32) + sub * a.S + (gs - ray * a.S))
+              : __ldg(reinterpret_cast<const float4*>(a.colours + gs * 32) + sub);
           Aq[it] = __ldg(reinterpret_cast<const float4*>(a.g_rgb + ray * 32) + sub);
           omq[it] = __ldg(a.omega + gs); gsq[it] = __ldg(a.gsig + gs);
         }
@@ -565,7 +568,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const A
 
 // Launch; returns cudaError_t (0 = ok) or -1 when the device cannot run it (the caller keeps the mma.sync kernel).
 // scale_buf: 4 floats of device scratch ([0..1] the power-of-two scale and its inverse, [2..3] the range accumulators).
-int launch_bwd_decode_tc(const float* planes, int H, int W, const float* dec, const float* pts, const float* colours,
+int launch_bwd_decode_tc(const float* planes, int H, int W, const float* dec, const float* pts, const float* colours, int col_chunked,
                          const float* features, const float* gsig, const float* omega, const float* g_rgb, long long total,
                          long long pts_per_img, int S, float box_scale, float* g_planes, float* g_dec, float* scale_buf,
                          int sms, int smem_optin, cudaStream_t st) {
@@ -578,7 +581,7 @@ int launch_bwd_decode_tc(const float* planes, int H, int W, const float* dec, co
   scale_kernel<<<sms * 4, 256, 0, st>>>(g_rgb, n_rgb, gsig, total, dec, reinterpret_cast<unsigned*>(scale_buf + 2));
   scale_finish_kernel<<<1, 64, 0, st>>>(reinterpret_cast<const unsigned*>(scale_buf + 2), dec, scale_buf);
   Args a;
-  a.planes = planes; a.H = H; a.W = W; a.dec = dec; a.pts = pts; a.colours = colours; a.features = features; a.gsig = gsig;
+  a.planes = planes; a.H = H; a.W = W; a.dec = dec; a.pts = pts; a.colours = colours; a.col_chunked = col_chunked; a.features = features; a.gsig = gsig;
   a.omega = omega; a.g_rgb = g_rgb; a.total = total; a.pts_per_img = pts_per_img; a.S = S; a.box_scale = box_scale;
   a.g_planes = g_planes; a.g_dec = g_dec; a.scale = scale_buf; a.prof = nullptr;
   { const char* dbg = getenv("TPR_BWD_DEBUG"); const int d = dbg ? atoi(dbg) : 0;      // profiling A/B: 1 = no scatter, 2 = no weight gradients

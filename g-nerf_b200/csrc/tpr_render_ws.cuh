@@ -546,11 +546,16 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
         // rows outside the group (om = 0) still hold finite values: the operand tiles start zeroed and only ever
         // receive finite features, so no select is needed to keep NaNs out of the sum
         const uint64_t om2 = pack2(om, om);
-        // training: this lane's sixteen colours of the sample also go to HBM (64 contiguous bytes), in the forward's
-        // sample order (ray-major, coarse then importance) -- what tpr_render_backward reads instead of re-running the decoder
+        // training: this lane's sixteen colours of the sample also go to HBM -- what tpr_render_backward reads instead of
+        // re-running the decoder.  Layout [ray][8 chunks of 4 channels][S samples][4 floats] (samples in the forward's order,
+        // coarse then importance): the lanes of a warp are consecutive samples of a ray, so one store instruction writes
+        // 16 B x 16 lanes = 256 contiguous bytes per ray.  (Sample-major rows -- 64 B per lane, 128 B apart -- cost the
+        // training forward 0.62 ms at config 2: 32 partial lines per store instruction.)
         ulonglong2* cdst = (TRAIN && a.sample_colours != nullptr && valid)
-            ? reinterpret_cast<ulonglong2*>(a.sample_colours + ((gg.ray0 + (long long)r * gg.rstride) * S + (fine ? Dc : 0) + di) * 32 + 16 * hc)
+            ? reinterpret_cast<ulonglong2*>(a.sample_colours + ((gg.ray0 + (long long)r * gg.rstride) * 8 + 4 * hc) * (long long)S * 4) +
+                  ((fine ? Dc : 0) + di)
             : nullptr;
+        const int cstep = S;                       // 16-byte units between two chunks of a ray
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           const ulonglong2 bz = *reinterpret_cast<const ulonglong2*>(tl.bias2 + 16 * hc + 4 * c4);
@@ -568,7 +573,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
             acc2[c >> 1] = fma2(om2, col, acc2[c >> 1]);
             if (h2 == 0) cpair.x = col; else cpair.y = col;
           }
-          if (TRAIN && cdst != nullptr) cdst[c4] = cpair;
+          if (TRAIN && cdst != nullptr) cdst[c4 * cstep] = cpair;
         }
       }
       float acc[16];

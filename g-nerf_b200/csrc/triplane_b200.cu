@@ -29,14 +29,14 @@ int launch_run_model_ws(const float* planes, long long n_img, int H, int W, cons
 // tpr_backward.cu
 int launch_bwd_points(const float* origins, const float* dirs, const float* dc, const float* df, int Dc, int Df,
                       long long n_rays_total, float* pts, int sms, cudaStream_t st);
-int launch_bwd_march(const float* dc, const float* df, int Dc, int Df, const float* sigma, const float* colours,
+int launch_bwd_march(const float* dc, const float* df, int Dc, int Df, const float* sigma, const float* colours, int col_chunked,
                      const float* g_rgb, const float* g_depth, const float* g_wsum, const float* range, int white_back,
                      long long n_rays_total, float* gsig, float* omega, int sms, cudaStream_t st);
-int launch_bwd_decode(const float* planes, int H, int W, const float* dec, const float* pts, const float* colours,
+int launch_bwd_decode(const float* planes, int H, int W, const float* dec, const float* pts, const float* colours, int col_chunked,
                       const float* features, const float* gsig, const float* omega, const float* g_rgb, long long total, long long pts_per_img, int S,
                       float box_scale, float* g_planes, float* g_dec, int fast, int skip, int sms, cudaStream_t st);
 // tpr_backward_tc.cu: the decoder backward on tcgen05 (returns -1 if it cannot run here)
-int launch_bwd_decode_tc(const float* planes, int H, int W, const float* dec, const float* pts, const float* colours,
+int launch_bwd_decode_tc(const float* planes, int H, int W, const float* dec, const float* pts, const float* colours, int col_chunked,
                          const float* features, const float* gsig, const float* omega, const float* g_rgb, long long total,
                          long long pts_per_img, int S, float box_scale, float* g_planes, float* g_dec, float* scale_buf,
                          int sms, int smem_optin, cudaStream_t st);
@@ -887,6 +887,11 @@ static int render_impl(const float* planes_packed, int64_t n_img, int32_t height
   if (opt->flags != TPR_MLP_FFMA && !env_int("TPR_FORCE_FFMA", 0) && ws_rays_per_group(Dc, Df, tc_mode(opt->flags)) > 0) {
     const bool keep = sample_colours && sample_sigma && ws_keeps_samples(Dc, Df) && !a.dbg;
     if (keep) { a.sample_colours = sample_colours; a.sample_sigma = sample_sigma; a.sample_features = sample_features; }   // (only this kernel can keep them)
+    if (keep) {                                   // profiling A/B only (results of the backward are then garbage): skip one of the kept streams
+      const int dbg = env_int("TPR_TRAIN_DEBUG", 0);
+      if (dbg & 1) a.sample_colours = nullptr;
+      if (dbg & 2) a.sample_features = nullptr;
+    }
     int rc = launch_render_ws(a, tc_mode(opt->flags), di.sms, di.smem_optin, n_img, n_rays, st);
     if (rc > 0) return cuda_fail((cudaError_t)rc, "render_ws_kernel");
     done = rc == 0;                       // < 0: does not fit shared memory, fall through
@@ -1254,7 +1259,7 @@ int tpr_march_backward(const float* depths_coarse, const float* depths_fine, int
   if (n_rays_total <= 0 || dc < 2 || df < 0 || dc + df > TPR_MAX_SAMPLES) return fail(TPR_E_SHAPE, "tpr_march_backward: bad shape");
   DeviceInfo di = device_info();
   if (!di.ok) return fail(TPR_E_DEVICE, "tpr_march_backward: no CUDA device");
-  const int rc = launch_bwd_march(depths_coarse, depths_fine, dc, df, sigma, colours, g_rgb, g_depth, g_weight_sum, depth_range,
+  const int rc = launch_bwd_march(depths_coarse, depths_fine, dc, df, sigma, colours, 0, g_rgb, g_depth, g_weight_sum, depth_range,
                                   white_back, n_rays_total, g_sigma, omega, di.sms, (cudaStream_t)stream);
   if (rc != 0) return cuda_fail((cudaError_t)rc, "march_backward_kernel");
   return 0;
@@ -1294,6 +1299,7 @@ int tpr_render_backward(const float* planes_packed, int64_t n_img, int32_t heigh
   int rc = launch_bwd_points(origins, dirs, depths_coarse, depths_fine, Dc, Df, rays, pts, di.sms, st);
   if (rc != 0) return cuda_fail((cudaError_t)rc, "points_kernel");
   const float* col_in = sample_colours; const float* sig_in = sample_sigma;
+  const int col_chunked = sample_colours != nullptr ? 1 : 0;      // tpr_render_train's layout; recomputed colours are sample-major
   if (!col_in) {
     // not kept by the forward (tpr_render_train): colours and densities of every sample through the forward's point query
     // (VR/renderer.py:142-148)
@@ -1302,7 +1308,7 @@ int tpr_render_backward(const float* planes_packed, int64_t n_img, int32_t heigh
     if (rc != 0) return rc;
     col_in = colours; sig_in = sigma;
   }
-  rc = launch_bwd_march(depths_coarse, depths_fine, Dc, Df, sig_in, col_in, g_rgb, g_depth, g_weight_sum, depth_range,
+  rc = launch_bwd_march(depths_coarse, depths_fine, Dc, Df, sig_in, col_in, col_chunked, g_rgb, g_depth, g_weight_sum, depth_range,
                         opt->white_back, rays, gsig, omega, di.sms, st);
   if (rc != 0) return cuda_fail((cudaError_t)rc, "march_backward_kernel");
   cudaError_t e = cudaSuccess;
@@ -1313,14 +1319,14 @@ int tpr_render_backward(const float* planes_packed, int64_t n_img, int32_t heigh
   // it replaced (A/B runs; also the fallback if the tcgen05 kernel's shared memory does not fit the device).
   const char* impl = getenv("TPR_BWD_IMPL");
   if (!(impl && strcmp(impl, "hmma") == 0)) {
-    rc = launch_bwd_decode_tc(planes_packed, height, width, decoder_packed, pts, col_in, sample_features, gsig, omega, g_rgb, (long long)T,
+    rc = launch_bwd_decode_tc(planes_packed, height, width, decoder_packed, pts, col_in, col_chunked, sample_features, gsig, omega, g_rgb, (long long)T,
                               (long long)n_rays * S, S, (float)(2.0 / opt->box_warp), g_planes_packed, g_decoder_packed, scale_buf,
                               di.sms, di.smem_optin, st);
     if (rc > 0) return cuda_fail((cudaError_t)rc, "decode_backward_tc_kernel");
     if (rc == 0) return 0;
   }
   float* g_dec_out = g_decoder_packed ? g_decoder_packed : reinterpret_cast<float*>(scratch);      // (never written when skipped)
-  rc = launch_bwd_decode(planes_packed, height, width, decoder_packed, pts, col_in, sample_features, gsig, omega, g_rgb, (long long)T,
+  rc = launch_bwd_decode(planes_packed, height, width, decoder_packed, pts, col_in, col_chunked, sample_features, gsig, omega, g_rgb, (long long)T,
                          (long long)n_rays * S, S, (float)(2.0 / opt->box_warp), g_planes_packed, g_dec_out,
                          opt->flags == TPR_MLP_BF16, (g_planes_packed ? 0 : 1) | (g_decoder_packed ? 0 : 2), di.sms, st);
   if (rc != 0) return cuda_fail((cudaError_t)rc, "decode_backward_kernel");

@@ -295,7 +295,7 @@ int tpr_sample_3dgrid(const float* grid, int64_t n_grids, int32_t channels, int3
  * g_planes_packed [N,3,H,W,32] (the layout of tpr_pack_planes; OVERWRITTEN) and g_decoder_packed
  * [tpr_packed_decoder_bytes()] (the layout of tpr_pack_decoder; OVERWRITTEN; convert with tpr_unpack_decoder_grad).
  * scratch: tpr_render_backward_scratch_bytes(n_img, n_rays, Dc + Df) bytes.
- * sample_colours [N*M,S,32] / sample_sigma [N*M,S]: the per-sample decoder outputs kept by tpr_render_train (both or
+ * sample_colours / sample_sigma [N*M,S]: the per-sample decoder outputs kept by tpr_render_train, in ITS layout (both or
  * neither); NULL = re-evaluate them here with the point-query kernel (tpr_run_model), 3 ms more at config 2.
  * sample_features [N*M,S,32]: the summed plane features of every sample, also kept by tpr_render_train; NULL = gather
  * them again. */
@@ -307,9 +307,10 @@ int tpr_render_backward(const float* planes_packed, int64_t n_img, int32_t heigh
                         const float* sample_colours, const float* sample_sigma, const float* sample_features,
                         float* g_planes_packed, float* g_decoder_packed, void* scratch, size_t scratch_bytes,
                         void* stream);
-/* tpr_render for a caller that will ask for gradients: additionally keeps every sample's colours [N*M,S,32] and sigma
- * [N*M,S] (the forward's sample order: ray-major, coarse then importance samples) and the importance depths fine_depths
- * [N*M,Df].  *samples_saved (host) = 1 if the kernel that ran kept them (the warp-specialised kernel), 0 if the sample
+/* tpr_render for a caller that will ask for gradients: additionally keeps every sample's colours (N*M*S*32 floats, an opaque
+ * hand-over to tpr_render_backward: [ray][8 chunks of 4 channels][S][4], which is what the kernel's warps store as 256-byte
+ * runs) and sigma [N*M,S] (the forward's sample order: ray-major, coarse then importance samples) and the importance depths
+ * fine_depths [N*M,Df].  *samples_saved (host) = 1 if the kernel that ran kept them (the warp-specialised kernel), 0 if the sample
  * counts forced another kernel -- then pass NULL for them to tpr_render_backward.  The depth clamp is applied. */
 int tpr_render_train(const float* planes_packed, int64_t n_img, int32_t height, int32_t width,
                      const float* decoder_packed, const float* origins, const float* dirs, int64_t n_rays,
