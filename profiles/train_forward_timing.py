@@ -1,5 +1,6 @@
+"""Training forward (kept samples) at config 2; TPR_TRAIN_DEBUG=1 skips the kept colours, 2 the kept features (timing A/B only)."""
 import importlib, os, sys
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bench
 pkg = importlib.import_module('g-nerf_b200')
 dev = torch.device('cuda:0')
