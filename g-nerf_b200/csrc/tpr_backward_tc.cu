@@ -238,8 +238,13 @@ __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const A
     // loads up front (needs the upstream gradient read at use to stay under the CTA's 72 registers per thread) 8.32 vs 7.92 ms
     // for the train step; prefetch.global.L2 of the next tile's rows: no change (7.86 vs 7.83); setmaxnreg.inc for these warps
     // without a matching .dec elsewhere never returns.
-    const int grp = lane >> 3, sub = lane & 7;
-    float b2acc[4] = {0.f, 0.f, 0.f, 0.f};          // partial sums of the (scaled) colour-logit gradients: channels 4 sub .. 4 sub + 3
+    // Colours use their own lane mapping: a thread owns ONE sample per half (slot cs of eight consecutive samples) and two
+    // 4-channel chunks (cq, cq + 4), so that a load instruction reads 4 chunks x 8 consecutive samples x 16 B = four full lines
+    // of the chunk-major layout tpr_render_train keeps the colours in (eight lanes per sample would touch eight lines for the
+    // same bytes: +0.19 ms for the kernel).
+    const int grp = lane >> 3, sub = lane & 7;       // features: eight lanes per sample row
+    const int cs = lane & 7, cq = lane >> 3;          // colours: sample slot, first chunk
+    float b2acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // (scaled) colour-logit gradient sums: channels 4 (cq + 4 j) + k
     float b2sig = 0.f;
     PROF_DECL();
     for (int i = 0; i < G; ++i) {
@@ -252,14 +257,13 @@ __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const A
       const long long ray0 = gs0 / a.S;
       const unsigned rr0 = (unsigned)(gs0 - ray0 * a.S);
       float4 f[2], colq[2], Aq[2];
-      float omq[2], gsq[2];
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
 #pragma unroll
       for (int it = 0; it < 2; ++it) {
         const int sr = warp * 16 + (2 * half + it) * 4 + grp;
         const long long gs = gs0 + sr;
-        f[it] = make_float4(0.f, 0.f, 0.f, 0.f); colq[it] = f[it]; Aq[it] = f[it]; omq[it] = 0.f; gsq[it] = 0.f;
+        f[it] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (gs < a.total) {
           if (a.features != nullptr) {
             f[it] = __ldg(reinterpret_cast<const float4*>(a.features + gs * 32) + sub);
@@ -269,44 +273,55 @@ __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const A
             const int n = (int)n0 + (rem0 + sr >= a.pts_per_img ? 1 : 0);
             f[it] = gather_point(a.planes + (size_t)n * img_stride, a.H, a.W, px, py, pz, sub);
           }
-          const long long ray = ray0 + (rr0 + (unsigned)sr) / (unsigned)a.S;
-          colq[it] = a.col_chunked
-              ? __ldg(reinterpret_cast<const float4*>(a.colours + ray * a.S * 32) + sub * a.S + (gs - ray * a.S))
-              : __ldg(reinterpret_cast<const float4*>(a.colours + gs * 32) + sub);
-          Aq[it] = __ldg(reinterpret_cast<const float4*>(a.g_rgb + ray * 32) + sub);
-          omq[it] = __ldg(a.omega + gs); gsq[it] = __ldg(a.gsig + gs);
         }
+      }
+      const int src = warp * 16 + 8 * half + cs;            // this thread's sample of the half
+      const long long gsc = gs0 + src;
+      float omq = 0.f, gsq = 0.f;
+      colq[0] = colq[1] = Aq[0] = Aq[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gsc < a.total) {
+        const long long ray = ray0 + (rr0 + (unsigned)src) / (unsigned)a.S;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int chunk = cq + 4 * j;
+          colq[j] = a.col_chunked
+              ? __ldg(reinterpret_cast<const float4*>(a.colours + ray * a.S * 32) + chunk * a.S + (gsc - ray * a.S))
+              : __ldg(reinterpret_cast<const float4*>(a.colours + gsc * 32) + chunk);
+          Aq[j] = __ldg(reinterpret_cast<const float4*>(a.g_rgb + ray * 32) + chunk);
+        }
+        omq = __ldg(a.omega + gsc); gsq = __ldg(a.gsig + gsc);
       }
       PROF(0);
       if (half == 0) mbar_wait_parked(&s.in_free[b], ((uint32_t)(i >> 1) & 1u) ^ 1u);   // the weight-gradient MMAs of tile i - 2 have read the tiles
       PROF(2);
 #pragma unroll
-      for (int it = 0; it < 2; ++it) {
-        const int sr = warp * 16 + (2 * half + it) * 4 + grp;
-        const bool valid = gs0 + sr < a.total;
+      for (int it = 0; it < 2; ++it) st_hilo4(s.in[b].hi, s.in[b].lo, warp * 16 + (2 * half + it) * 4 + grp, 0, sub, f[it]);
+      {
         // rgb*2-1 (VR/ray_marcher.py:55), sigmoid*1.002 (training/triplane.py:134); times the operand scale
-        const float om = omq[it] * (2.0f * 1.002f) * sc;
-        const float gsg = gsq[it] * sc;
-        const float cc[4] = {colq[it].x, colq[it].y, colq[it].z, colq[it].w}, aa[4] = {Aq[it].x, Aq[it].y, Aq[it].z, Aq[it].w};
-        float g4[4];
+        const float om = omq * (2.0f * 1.002f) * sc;
+        const float gsg = gsq * sc;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float sv = (cc[k] + 0.001f) * (1.0f / 1.002f);           // sigmoid(logit)
-          g4[k] = aa[k] * om * sv * (1.0f - sv);
-          b2acc[k] += g4[k];
+        for (int j = 0; j < 2; ++j) {
+          const float cc[4] = {colq[j].x, colq[j].y, colq[j].z, colq[j].w}, aa[4] = {Aq[j].x, Aq[j].y, Aq[j].z, Aq[j].w};
+          float g4[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float sv = (cc[k] + 0.001f) * (1.0f / 1.002f);           // sigmoid(logit)
+            g4[k] = aa[k] * om * sv * (1.0f - sv);
+            b2acc[j][k] += g4[k];
+          }
+          st_hilo4(s.in[b].hi, s.in[b].lo, src, 4, cq + 4 * j, make_float4(g4[0], g4[1], g4[2], g4[3]));
         }
-        st_hilo4(s.in[b].hi, s.in[b].lo, sr, 0, sub, f[it]);
-        st_hilo4(s.in[b].hi, s.in[b].lo, sr, 4, sub, make_float4(g4[0], g4[1], g4[2], g4[3]));
-        if (sub == 0) {
+        if (cq == 0) {
           b2sig += gsg;
-          s.gsig[b][sr] = gsg;
+          s.gsig[b][src] = gsg;
           // the third atom: columns (gsig hi, gsig lo, one, 0 ...) of this sample's row, 16-byte chunks 0 and 1
           const __half hi = __float2half_rn(gsg), lo = __float2half_rn(gsg - __half2float(hi));
           const uint32_t w0 = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
-          const uint32_t w1 = valid ? 0x3c00u : 0u;                       // fp16 1.0
-          uint8_t* rowp = s.in[b].sig + sr * 128;
-          *reinterpret_cast<uint4*>(rowp + ((0 ^ (sr & 7)) << 4)) = make_uint4(w0, w1, 0u, 0u);
-          *reinterpret_cast<uint4*>(rowp + ((1 ^ (sr & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+          const uint32_t w1 = gsc < a.total ? 0x3c00u : 0u;               // fp16 1.0
+          uint8_t* rowp = s.in[b].sig + src * 128;
+          *reinterpret_cast<uint4*>(rowp + ((0 ^ (src & 7)) << 4)) = make_uint4(w0, w1, 0u, 0u);
+          *reinterpret_cast<uint4*>(rowp + ((1 ^ (src & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
         }
       }
       PROF(3);
@@ -319,10 +334,13 @@ __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const A
     // gb2 (the bias of layer 2): sums of the outputs' gradients
     if (want_dec) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float v = b2acc[k];
-        v += __shfl_xor_sync(kFull, v, 8); v += __shfl_xor_sync(kFull, v, 16);
-        if (grp == 0) atomicAdd(a.g_dec + kB2Off + 1 + 4 * sub + k, v * inv_sc);
+      for (int j = 0; j < 2; ++j) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float v = b2acc[j][k];
+          v += __shfl_xor_sync(kFull, v, 1); v += __shfl_xor_sync(kFull, v, 2); v += __shfl_xor_sync(kFull, v, 4);
+          if (cs == 0) atomicAdd(a.g_dec + kB2Off + 1 + 4 * (cq + 4 * j) + k, v * inv_sc);
+        }
       }
       b2sig = warp_sum(b2sig);
       if (lane == 0) atomicAdd(a.g_dec + kB2Off, b2sig * inv_sc);
