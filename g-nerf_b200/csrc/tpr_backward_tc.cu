@@ -89,6 +89,7 @@ struct Args {
   float* g_planes;                      // packed, zero-initialised; NULL: no scatter
   float* g_dec;                         // [kDecFloats], zero-initialised; NULL: no weight gradients
   const float* scale;                   // [2] device: power-of-two scale of the gradient-side operands and its inverse
+  int lookahead;                        // G1 + G2 of tile i + 1 ahead of the weight-gradient MMAs of tile i
   long long* prof;                      // TPR_BWD_PROFILE: cycles CTA 0 spends per role and wait (NULL: off)
 };
 
@@ -405,8 +406,6 @@ __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const A
       PROF_T0();
       mbar_wait_parked(&s.g12_done, (uint32_t)i & 1u);
       PROF(7);
-      if (i > 0) mbar_wait_parked(&s.wg_done, (uint32_t)(i - 1) & 1u);           // the H / GA tiles of the previous tile have been consumed
-      PROF(8);
       tcgen05_fence_after();
       const float gsg = s.gsig[b][row];
 #pragma unroll 1
@@ -425,6 +424,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const A
           const float sp = x > 20.0f ? 1.0f : __fdividef(e, d);           // its derivative
           ga[k] = (__uint_as_float(gh[k]) + gsg * s.w2s[j]) * sp;         // d/d(layer-1 pre-activation), scaled
         }
+        // the H / GA tiles are single buffered: the weight-gradient MMAs of the previous tile must have read them.  Waiting here,
+        // after this chunk's TMEM loads and arithmetic, lets that work overlap those MMAs (G1 + G2 of this tile were issued
+        // ahead of them)
+        if (c == 2 * hh && i > 0) { mbar_wait_parked(&s.wg_done, (uint32_t)(i - 1) & 1u); PROF(8); }
         st_hilo16(s.h_hi, s.h_lo, row, c, h);
         st_hilo16(s.ga_hi, s.ga_lo, row, c, ga);
       }
@@ -548,6 +551,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const A
         mma_commit(&s.g3_done);
       }
       __syncwarp();
+      // G1 + G2 of the NEXT tile go ahead of this tile's weight-gradient MMAs when its inputs are already there (not waited for:
+      // the weight-gradient commit is what frees the loaders' other buffer): the next epilogue's TMEM loads and arithmetic then
+      // overlap WG instead of waiting behind it.  (TPR_BWD_DEBUG bit 3 = always after WG, for A/B.)
+      const bool early = a.lookahead && i + 1 < G && issue_g12(i + 1, false);
       if (elect_one_sync()) {
         // WG: the weight gradients, accumulated over every tile of this CTA.  A = [GA ; H] (M = 128: two 64-element atoms along
         // MN, 16 KB apart = LBO 1024 units), MN-major: K = samples = rows, 16 rows = 2048 bytes = 128 units per k-step, 8-row
@@ -568,10 +575,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const A
         if (i == G - 1) mma_commit(&s.all_done);
       }
       __syncwarp();
-      // (issuing G1 + G2 of the next tile AHEAD of the weight-gradient MMAs, so that its epilogue overlaps them, measured slower:
-      // 7.2 vs 6.6 ms for the backward at config 2 -- the MMAs' completion is what frees the input buffer the loaders wait for)
       PROF(15);
-      if (i + 1 < G) issue_g12(i + 1, true);
+      if (i + 1 < G && !early) issue_g12(i + 1, true);
       PROF(16);
     }
     PROF_FLUSH(13, 16, true);
@@ -604,7 +609,8 @@ int launch_bwd_decode_tc(const float* planes, int H, int W, const float* dec, co
   a.g_planes = g_planes; a.g_dec = g_dec; a.scale = scale_buf; a.prof = nullptr;
   { const char* dbg = getenv("TPR_BWD_DEBUG"); const int d = dbg ? atoi(dbg) : 0;      // profiling A/B: 1 = no scatter, 2 = no weight gradients
     if (d & 1) a.g_planes = nullptr;
-    if (d & 2) a.g_dec = nullptr; }
+    if (d & 2) a.g_dec = nullptr;
+    a.lookahead = (d & 8) ? 0 : 1; }
   static const bool profile = getenv("TPR_BWD_PROFILE") != nullptr;
   e = profile ? cudaFuncSetAttribute(decode_backward_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
               : cudaFuncSetAttribute(decode_backward_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
