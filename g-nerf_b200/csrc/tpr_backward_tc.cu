@@ -350,6 +350,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_backward_tc_kernel(const A
     // ================================================ SCATTER ================================================
     // Eight lanes per sample add GF x tap weight to the twelve texels of the sample (one 128-byte line each).  The taps are
     // recomputed here from the sample's position, loaded before the wait for GF.
+    // (Handing a quarter of the rows to the epilogue warps, which idle for half of a tile's time, was measured SLOWER: 7.9 vs
+    // 7.27 ms fwd+bwd.  The reductions are bound by the SM's own REDG rate -- ~0.74 cycles per 16-byte lane operation -- not by
+    // how many warps issue them, and the epilogue's share lengthened the MMA <-> epilogue chain.)
     const int sw = warp - kLoadWarps, grp = lane >> 3, sub = lane & 7;
     const int plane_stride = a.H * a.W * kC;
     PROF_DECL();
