@@ -10,7 +10,9 @@
 //                       -> sort by depth (VR/renderer.py:157-167) -> final march (VR/ray_marcher.py:25-57).
 //   * the first march (coarse weights) only feeds the resampling, i.e. nothing.
 //
-// Three kernels, none of which stores per-sample activations of the decoder:
+// Kernels, none of which stores per-sample activations of the decoder (the decoder's backward of the product path is
+// decode_backward_tc_kernel in tpr_backward_tc.cu -- tcgen05; the mma.sync kernel below is its A/B partner, TPR_BWD_IMPL=hmma,
+// and the fall-back for devices / shapes the tcgen05 kernel refuses):
 //   points_kernel           sample positions origin + depth * direction of all S samples of every ray
 //   (tpr_run_model)         colours and densities of those points: the forward's tcgen05 point-query kernel
 //   march_backward_kernel   one warp per ray: sort, march, and the march's backward -> per sample d(loss)/d(sigma) and
@@ -20,9 +22,7 @@
 //                           on mma.sync m16n8k8 TF32 with the 3xTF32 split, fp32 accumulation), then the bilinear
 //                           scatter of d(loss)/d(features) into the packed plane gradient with 128-bit reductions
 //                           (red.global.add.v4.f32: one texel = one 128-byte line = 8 lanes).
-// The decoder GEMMs here use warp-level mma.sync, not tcgen05: the tile shapes (K = samples for the weight gradients)
-// need transposed operands that the forward's UMMA staging does not produce; moving them to tcgen05 is the next step
-// for this kernel.
+// 
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>

@@ -725,7 +725,7 @@ static int launch_run_model(bool from_features, const float* planes, int64_t n_i
   DeviceInfo di = device_info();
   if (!di.ok) return fail(TPR_E_DEVICE, "run_model: no CUDA device");
   const float box_scale = (float)(2.0 / box_warp);      // python float (VR/renderer.py:61)
-  // Point queries with enough points to fill the GPU run the warp-specialised tensor-core kernel (3xTF32 in the fp32
+  // Point queries with enough points to fill the GPU run the warp-specialised tensor-core kernel (2xFP16 operand pairs in the fp32
   // mode, bf16 operands in the bf16 mode); small queries, pre-gathered features (tpr_decode) and TPR_MLP_FFMA run the
   // fp32 FFMA kernel below, whose 32-point chunks spread over the SMs at any size.
   if (!from_features && flags != TPR_MLP_FFMA && (long long)n_img * n_pts >= env_int("TPR_RM_WS_MIN_POINTS", 1 << 16) &&

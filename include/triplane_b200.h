@@ -50,8 +50,9 @@ enum {
 
 /* flags */
 enum {
-  TPR_MLP_FP32 = 0,     /* fp32-grade decoder, the 1e-4 max-abs parity mode: tcgen05 3xTF32 when the sample
-                           counts fit the TMEM slots, the FFMA kernel otherwise */
+  TPR_MLP_FP32 = 0,     /* fp32-grade decoder, the 1e-4 max-abs parity mode: tcgen05 with fp16 hi + lo operand pairs
+                           (three products per contraction, fp32 accumulation) when the sample counts fit the TMEM
+                           slots, the FFMA kernel otherwise */
   TPR_MLP_BF16 = 1,     /* decoder on tensor cores with bf16 operands: the >= 50 dB PSNR mode */
   TPR_MLP_FFMA = 2      /* force the fp32 FFMA kernel (A/B comparisons) */
 };

@@ -2,8 +2,8 @@
   * the gradient fixtures the UNMODIFIED reference produced under autograd (tests/golden/bwd_*.npz), and
   * autograd through the torch restatement (oracle/torch_oracle.py, pinned to those fixtures on CPU) on the same device
     at sizes the fixtures do not cover.
-Tolerance: 2e-4 of the largest gradient entry of each tensor (fp32 everywhere; the decoder GEMMs run as 3xTF32 on the
-tensor cores, the plane gradient is accumulated with floating-point atomics, so the summation order differs from torch's)."""
+Tolerance: 2e-4 of the largest gradient entry of each tensor (fp32 accumulation everywhere; the decoder GEMMs run on tcgen05 with fp16 hi + lo
+operand pairs -- or as 3xTF32 mma.sync with TPR_BWD_IMPL=hmma --, the plane gradient is accumulated with floating-point atomics, so the summation order differs from torch's)."""
 import ctypes
 
 import numpy as np

@@ -115,7 +115,7 @@ def test_render_bf16_decoder_psnr(pkg, name):
 @pytest.mark.parametrize('mode', ['fp32', 'fp32_ffma'])
 @pytest.mark.parametrize('name', list(CASES))
 def test_render_against_oracle_and_reference_fixture(pkg, name, mode):
-    """'fp32' = decoder on tcgen05 with 3xTF32 operands; 'fp32_ffma' = decoder in fp32 FFMA.  Same 1e-4 gate."""
+    """'fp32' = decoder on tcgen05 with fp16 hi + lo operand pairs (2xFP16); 'fp32_ffma' = decoder in fp32 FFMA.  Same 1e-4 gate."""
     scene, opts, gold = load_case(name)
     opts = dict(opts, decoder_precision=mode)
     R = pkg.ImportanceRenderer()

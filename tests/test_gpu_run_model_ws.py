@@ -24,7 +24,7 @@ def test_small_queries_through_the_tensor_core_kernel(pkg, force_ws, name):
     out = R.run_model(T(scene['planes']), dec, T(gold['pts']), None, opts)
     rgb_o, sig_o = O.run_model(scene['planes'], scene['dec'], gold['pts'], opts['box_warp'])
     for got, want in ((out['rgb'], rgb_o), (out['sigma'], sig_o), (out['rgb'], gold['pts_rgb']), (out['sigma'], gold['pts_sigma'])):
-        assert np.abs(got.cpu().numpy() - want).max() < 1e-4            # fp32 mode (3xTF32): the north_star tolerance
+        assert np.abs(got.cpu().numpy() - want).max() < 1e-4            # fp32 mode (2xFP16 operand pairs): the north_star tolerance
     sig_only = R.run_model(T(scene['planes']), dec, T(gold['pts']), None, opts, want_rgb=False)
     assert sig_only['rgb'] is None
     torch.testing.assert_close(sig_only['sigma'], out['sigma'], rtol=0, atol=0)
