@@ -23,6 +23,7 @@ struct RenderArgs {
   float* rgb; float* depth; float* wsum; float* fine_depths; int* fine_inds;
   unsigned* range_enc;                   // [2]: ordered-uint encoded (min, max) of all depths
   int variant;                           // debug: A/B switches (TPR_WS_VARIANT)
+  int bulk_inputs;                       // jitter / u rows are 16-byte aligned multiples of 16 bytes: fetch them with cp.async.bulk
   int col_w;                             // > 0: rays form an image col_w pixels wide and a group is R rays of one image COLUMN
   long long* dbg;                        // optional [16] per-phase cycle counters of CTA 0 (TPR_PHASE_TIMING=1)
   int plane_sets;                        // >= 1: image (camera) n samples plane set n % plane_sets

@@ -49,6 +49,7 @@ struct Barriers {
   uint64_t csig_ready[kCtx];    // 4 decode-warp arrivals: every coarse sigma of the group is in shared memory
   uint64_t fsig_ready[kCtx];    // 4 decode-warp arrivals (every sigma of the group's last pass is in shared memory) + 1
                                 // tcgen05.commit (the last layer 2, and with it every colour slot of the group, is final)
+  uint64_t stg_full[2];         // expect_tx: the bulk copies of a group's jitter / u rows have landed in the staging buffer
 };
 
 // per-group shared-memory context
@@ -210,6 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
     range_sm[0] = 0xffffffffu; range_sm[1] = 0u;
     for (int b = 0; b < kBufs; ++b) { mbar_init(&bars.a1_full[b], kGatherWarps); mbar_init(&bars.a1_free[b], 1); }
     mbar_init(&bars.d1_full, 1); mbar_init(&bars.a2_full, kDecodeWarps);
+    mbar_init(&bars.stg_full[0], 1); mbar_init(&bars.stg_full[1], 1);
     for (int c = 0; c < kCtx; ++c) {
       mbar_init(&bars.coarse_ready[c], kRayWarps); mbar_init(&bars.fine_ready[c], kRayWarps);
       // coarse-only renders (nf == 0) composite straight after the coarse pass: csig then also carries the MMA completion
@@ -376,7 +378,12 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
     // The group's per-ray inputs (6 ray floats, Dc jitter draws, Df uniform draws per ray) are DRAM reads with
     // nothing to overlap them inside setup, so they are fetched with cp.async into a staging area one step ahead;
     // each thread later converts exactly the elements it copied itself (no barrier needed, only wait_group).
-    float* stg_jit = rayw + R; float* stg_u = stg_jit + R * Dc; float* stg_ray = stg_u + R * Df;
+    // Jitter / u rows, optional path (a.bulk_inputs, opt-in: measured 2 % slower at config 2): one cp.async.bulk per ray and
+    // array (192-byte rows at 48 + 48), issued by one thread, completion counted on an mbarrier, staging double buffered (any
+    // thread may then convert any element); needs 16-byte aligned rows.  Default, and always for the 12-byte origin /
+    // direction rows: 4-byte cp.async, each thread converting the elements it copied itself.
+    const bool bulk = a.bulk_inputs != 0;
+    float* stg_jit = rayw + R; float* stg_u = stg_jit + 2 * R * Dc; float* stg_ray = stg_u + 2 * R * Df;
     int* hist = reinterpret_cast<int*>(stg_ray + R * 8 + 8);      // [R][Dc + 4] (R = 4: warp_merge_scatter)
     // R = 4 (more than 64 samples per pass): a ray's samples are merged instead of rank-counted (tpr_render.cuh)
     const bool merge = R == 4 && nf > 0 && (Df & 3) == 0 && a.variant != 3;
@@ -394,13 +401,25 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
         const long long g = gg.ray0 + (long long)r * gg.rstride;
         cp_async4(stg_ray + rtid, c < 3 ? a.origins + g * 3 + c : a.dirs + g * 3 + c - 3);
       }
-      for (int s = rtid; s < gg.nr * Dc; s += kRayThreads) {
-        const int r = s / Dc, k = s - r * Dc;
-        cp_async4(stg_jit + s, a.jitter + (gg.ray0 + (long long)r * gg.rstride) * Dc + k);
-      }
-      for (int s = rtid; s < gg.nr * Df; s += kRayThreads) {
-        const int r = s / Df, k = s - r * Df;
-        cp_async4(stg_u + s, a.u + (gg.ray0 + (long long)r * gg.rstride) * Df + k);
+      float* sj = stg_jit + (gi & 1) * R * Dc; float* su = stg_u + (gi & 1) * R * Df;
+      if (bulk) {
+        if (rtid == 0) {
+          mbar_arrive_expect_tx(&bars.stg_full[gi & 1], (uint32_t)(gg.nr * (Dc + Df)) * 4u);
+          for (int r = 0; r < gg.nr; ++r) {
+            const long long g = gg.ray0 + (long long)r * gg.rstride;
+            bulk_copy_g2s(sj + r * Dc, a.jitter + g * Dc, (uint32_t)Dc * 4u, &bars.stg_full[gi & 1]);
+            if (Df > 0) bulk_copy_g2s(su + r * Df, a.u + g * Df, (uint32_t)Df * 4u, &bars.stg_full[gi & 1]);
+          }
+        }
+      } else {
+        for (int s = rtid; s < gg.nr * Dc; s += kRayThreads) {
+          const int r = s / Dc, k = s - r * Dc;
+          cp_async4(sj + s, a.jitter + (gg.ray0 + (long long)r * gg.rstride) * Dc + k);
+        }
+        for (int s = rtid; s < gg.nr * Df; s += kRayThreads) {
+          const int r = s / Df, k = s - r * Df;
+          cp_async4(su + s, a.u + (gg.ray0 + (long long)r * gg.rstride) * Df + k);
+        }
       }
       cp_async_commit();
     };
@@ -410,14 +429,16 @@ __global__ void __launch_bounds__(kThreads, 1) render_ws_kernel(const RenderArgs
       const Geom gg = group_geom(a, blockIdx.x + (unsigned)gi * gridDim.x, R);
       const Ctx cx = ctx_of(gi);
       cp_async_wait_all();
+      if (bulk) mbar_wait_parked(&bars.stg_full[gi & 1], (uint32_t)(gi >> 1) & 1u);
+      const float* sj = stg_jit + (gi & 1) * R * Dc; const float* su = stg_u + (gi & 1) * R * Df;
       if (rtid < gg.nr * 6) { const int r = rtid / 6; cx.ray[r * 8 + (rtid - r * 6)] = stg_ray[rtid]; }
       for (int s = rtid; s < gg.nr * Dc; s += kRayThreads) {
         const int r = s / Dc, k = s - r * Dc;
         const long long g = gg.ray0 + (long long)r * gg.rstride;
         const float lo = per_ray ? __ldg(a.rs + g) : a.ray_start, hi = per_ray ? __ldg(a.re + g) : a.ray_end;
-        cx.dep[r * S + k] = coarse_depth(a, k, stg_jit[s], lo, hi, per_ray);
+        cx.dep[r * S + k] = coarse_depth(a, k, sj[s], lo, hi, per_ray);
       }
-      for (int s = rtid; s < gg.nr * Df; s += kRayThreads) cx.u[s] = stg_u[s];
+      for (int s = rtid; s < gg.nr * Df; s += kRayThreads) cx.u[s] = su[s];
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.coarse_ready[gi & 3]);
       PROF_ADD(12, pl);
@@ -668,7 +689,7 @@ template <int MODE>
 static size_t smem_bytes(int R, int S, int Df) {
   return 1024 + sizeof(Tiles<MODE>) + sizeof(Tap2) * kGatherWarps * 24 +
          sizeof(float) * ((size_t)kCtx * (2 * R * S + R * Df + R * 8 + (R == 4 ? R * Df : 0)) + (size_t)3 * R * S + R +
-                          (size_t)R * S + R * 8 + 8 + (R == 4 ? R * (S - Df + 4) + (size_t)3 * R * S : 0));
+                          (size_t)2 * R * S + R * 8 + 8 + (R == 4 ? R * (S - Df + 4) + (size_t)3 * R * S : 0));
 }
 
 typedef void (*Kernel)(const RenderArgs);

@@ -874,6 +874,11 @@ static int render_impl(const float* planes_packed, int64_t n_img, int32_t height
     a.col_w = w;
   }
   a.variant = env_int("TPR_WS_VARIANT", 0);
+  // cp.async.bulk for the per-group jitter / u rows: built, parity-clean, and measured SLOWER than the 4-byte cp.async prefetch
+  // (config 2, same box: 2.266 vs 2.218 ms; equal at 96+96) -- one thread issuing 16 small bulk copies per group costs its warp
+  // more than 3 fire-and-forget LDGSTS per thread cost all of them.  Opt-in for A/B: TPR_WS_VARIANT bit 6.
+  a.bulk_inputs = (a.variant & 64) && (Dc % 4 == 0) && (Df % 4 == 0) && ((uintptr_t)jitter % 16 == 0) &&
+                  (Df == 0 || (uintptr_t)u % 16 == 0);
   a.dbg = env_int("TPR_PHASE_TIMING", 0) ? reinterpret_cast<long long*>(reinterpret_cast<char*>(scratch) + 64) : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   if (phases & kRangeInit) {
