@@ -28,6 +28,19 @@ using namespace tc;
 using namespace ws;
 
 constexpr int kColourWarps = 8;
+// Gather warps: 16 when a COLOUR role shares the SM (sigma + rgb); 24 for sigma-only queries, where the eight warps the COLOUR
+// role does not need gather as well.  With 24 they work as three teams of eight warps, team k gathering the tiles i = k (mod 3)
+// into A1 buffer k, sixteen rows per warp: three tiles are in flight instead of one, and the random-line gather -- latency
+// bound, more lines in flight = more bandwidth (profiles/r02_gather_shapes.json: 24 warps x 4 lines 17.2 TB/s, 16 x 4 14.6) --
+// is what this kernel waits for.
+template <bool RGB> struct Roles {
+  static constexpr int gather = RGB ? ws::kGatherWarps : 24;
+  static constexpr int teams = RGB ? 1 : 3;
+  static constexpr int team_warps = gather / teams;                 // 16 or 8
+  static constexpr int passes = ws::kRows / (8 * team_warps);       // 8-row passes per warp and tile: 1 or 2
+  static constexpr int threads = 32 * (gather + ws::kDecodeWarps + (RGB ? kColourWarps : 0));
+};
+static_assert(Roles<false>::teams == ws::kBufs, "team k owns A1 buffer k");
 constexpr int kStages = 2;                         // TMEM: stage s = columns [128 s, 128 s + 128) (D1, and bf16's activations behind it)
 constexpr uint32_t kRmStageCols = 128;
 constexpr int kSlots = 8;                          // colour slots: columns [256 + 32 k, 256 + 32 k + 32)
@@ -53,11 +66,12 @@ struct RmBarriers {
 // one tile of 128 points -> A1 buffer.  Warp w owns rows [8w, 8w+8); same two steps as the forward's gather_tile.
 template <int MODE>
 __device__ __forceinline__ void gather_tile_points(const RmArgs& a, float* a1_hi, const float* __restrict__ img,
-                                                   const float* __restrict__ pts, int nvalid, Tap2* tw, int warp, int lane) {
+                                                   const float* __restrict__ pts, int nvalid, Tap2* tw, int row0, int lane) {
+  // row0: the first of this warp's eight rows
   const int grp = lane >> 3, sub = lane & 7;
   {
     const int s = lane / 3, p = lane - s * 3;
-    const int row = warp * 8 + s;
+    const int row = row0 + s;
     if (lane < 24 && row < nvalid) {
       const float* c = pts + (size_t)row * 3;
       // (2/box_warp) * coordinates (VR/renderer.py:61)
@@ -78,14 +92,14 @@ __device__ __forceinline__ void gather_tile_points(const RmArgs& a, float* a1_hi
 #pragma unroll 1
   for (int rd = 0; rd < 2; ++rd) {
     const int s = rd * 4 + grp;
-    const int row = warp * 8 + s;
+    const int row = row0 + s;
     if (row < nvalid) blend_sample<MODE>(a1_hi, base, tw + s * 3, row, sub);
   }
   __syncwarp();           // the tap table is rewritten by the next tile
 }
 
 template <int MODE, bool RGB>
-__global__ void __launch_bounds__(32 * (kGatherWarps + kDecodeWarps + (RGB ? kColourWarps : 0)), 1)
+__global__ void __launch_bounds__(Roles<RGB>::threads, 1)
 run_model_ws_kernel(const RmArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -94,9 +108,10 @@ run_model_ws_kernel(const RmArgs a) {
   __shared__ RmBarriers bars;
   __shared__ uint32_t tmem_base_sm;
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  constexpr int kGW = Roles<RGB>::gather;
 
   if (tid == 0) {
-    for (int b = 0; b < kBufs; ++b) { mbar_init(&bars.a1_full[b], kGatherWarps); mbar_init(&bars.a1_free[b], 1); }
+    for (int b = 0; b < kBufs; ++b) { mbar_init(&bars.a1_full[b], Roles<RGB>::team_warps); mbar_init(&bars.a1_free[b], 1); }
     for (int s = 0; s < kStages; ++s) { mbar_init(&bars.d1_full[s], 1); mbar_init(&bars.a2_full[s], kDecodeWarps); }
     for (int k = 0; k < kSlots; ++k) { mbar_init(&bars.slot_full[k], 1); mbar_init(&bars.slot_free[k], kColourWarps); }
     fence_mbar_init();
@@ -124,25 +139,28 @@ run_model_ws_kernel(const RmArgs a) {
     nvalid = (int)min((long long)kRows, a.n_pts - p0);
   };
 
-  if (warp < kGatherWarps) {
+  if (warp < kGW) {
     // ====================================== GATHER ======================================
     Tap2* tw = taps + warp * 24;
-    int b = 0; uint32_t ph = 0;
+    const int team = warp / Roles<RGB>::team_warps, wt = warp - team * Roles<RGB>::team_warps;
 #pragma unroll 1
-    for (int i = 0; i < G; ++i) {
+    for (int i = team; i < G; i += Roles<RGB>::teams) {
+      const int b = i % kBufs;
+      const uint32_t ph = (uint32_t)(i / kBufs) & 1u;         // the tile's turn of the ring
       long long n, p0; int nvalid;
       tile_of(i, n, p0, nvalid);
       mbar_wait_parked(&bars.a1_free[b], ph ^ 1u);          // passes immediately the first time round
-      gather_tile_points<MODE>(a, tl.a1[b][0], a.planes + (size_t)n * img_stride,
-                               a.xyz + (size_t)(n * a.n_pts + p0) * 3, nvalid, tw, warp, lane);
+#pragma unroll 1
+      for (int ps = 0; ps < Roles<RGB>::passes; ++ps)
+        gather_tile_points<MODE>(a, tl.a1[b][0], a.planes + (size_t)n * img_stride,
+                                 a.xyz + (size_t)(n * a.n_pts + p0) * 3, nvalid, tw, (wt * Roles<RGB>::passes + ps) * 8, lane);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.a1_full[b]);
-      if (++b == kBufs) { b = 0; ph ^= 1u; }
     }
-  } else if (warp < kGatherWarps + kDecodeWarps) {
+  } else if (warp < kGW + kDecodeWarps) {
     // ====================================== DECODE ======================================
-    const int dw = warp - kGatherWarps, q = dw & 3, h = dw >> 2;
+    const int dw = warp - kGW, q = dw & 3, h = dw >> 2;
     const bool issuer = dw == 0;
     const uint32_t dbase = smem_desc_lo(smem_u32(&tl));
     int b = 0; uint32_t ph = 0;                         // A1 ring position of the NEXT layer-1 issue
@@ -199,7 +217,7 @@ run_model_ws_kernel(const RmArgs a) {
     }
   } else if (RGB) {
     // ====================================== COLOUR ======================================
-    const int cw = warp - kGatherWarps - kDecodeWarps, q = cw & 3, hc = cw >> 2;
+    const int cw = warp - kGW - kDecodeWarps, q = cw & 3, hc = cw >> 2;
 #pragma unroll 1
     for (int i = 0; i < G; ++i) {
       long long n, p0; int nvalid;
@@ -233,7 +251,7 @@ run_model_ws_kernel(const RmArgs a) {
 }
 
 template <int MODE>
-static size_t smem_bytes() { return 1024 + sizeof(Tiles<MODE>) + sizeof(Tap2) * kGatherWarps * 24; }
+static size_t smem_bytes() { return 1024 + sizeof(Tiles<MODE>) + sizeof(Tap2) * Roles<false>::gather * 24; }
 
 }  // namespace wsrm
 
@@ -259,7 +277,7 @@ int launch_run_model_ws(const float* planes, long long n_img, int H, int W, cons
   e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const long long grid = a.n_tiles < sms ? a.n_tiles : sms;            // one CTA per SM: each owns all 512 TMEM columns
-  const int threads = 32 * (ws::kGatherWarps + ws::kDecodeWarps + (want_rgb ? kColourWarps : 0));
+  const int threads = want_rgb ? Roles<true>::threads : Roles<false>::threads;
   k<<<(unsigned)grid, threads, smem, st>>>(a);
   return (int)cudaGetLastError();
 }
