@@ -80,22 +80,26 @@ __device__ __forceinline__ float warp_excl_suffix_sum(float v, int lane) {
 }
 
 template <int E>
-__global__ void __launch_bounds__(128) march_backward_kernel(const MarchArgs a) {
+__global__ void __launch_bounds__(128, 8) march_backward_kernel(const MarchArgs a) {
   extern __shared__ float sm[];
   const int S = a.Dc + a.Df, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   float* z = sm + wid * 7 * S; float* sg = z + S; float* q = sg + S;
   float* zs = q + S; float* ss = zs + S; float* qs = ss + S; int* idx = reinterpret_cast<int*>(qs + S);
+  float* a2s = sm + 4 * 7 * S + wid * 32;          // 2 x the ray's upstream rgb gradient (shared memory: 32 registers less per
+                                                   // thread = 10 instead of 6 resident CTAs, and the kernel waits for DRAM)
+  const bool vec = (S & 3) == 0 && (a.Dc & 3) == 0; // float4 reads of the depth rows are aligned
   const float lo = __ldg(a.range), hi = __ldg(a.range + 1);
   for (long long g = blockIdx.x * 4ll + wid; g < a.n_rays; g += gridDim.x * 4ll) {
     // upstream gradient of rgb (x2: VR/ray_marcher.py:55)
-    float A2[32];
     float sumA2 = 0.0f;
-#pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(a.g_rgb + g * 32) + c4);
-      A2[4 * c4] = 2.0f * v.x; A2[4 * c4 + 1] = 2.0f * v.y; A2[4 * c4 + 2] = 2.0f * v.z; A2[4 * c4 + 3] = 2.0f * v.w;
-      sumA2 += (A2[4 * c4] + A2[4 * c4 + 1]) + (A2[4 * c4 + 2] + A2[4 * c4 + 3]);
+    if (lane < 8) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(a.g_rgb + g * 32) + lane);
+      const float4 w = make_float4(2.0f * v.x, 2.0f * v.y, 2.0f * v.z, 2.0f * v.w);
+      *reinterpret_cast<float4*>(a2s + 4 * lane) = w;
+      sumA2 = (w.x + w.y) + (w.z + w.w);
     }
+    sumA2 = warp_sum(sumA2);
+    __syncwarp();
     const float B = __ldg(a.g_depth + g), C = __ldg(a.g_wsum + g);
     for (int p = lane; p < S; p += 32) {
       z[p] = p < a.Dc ? __ldg(a.dc + g * a.Dc + p) : __ldg(a.df + g * a.Df + (p - a.Dc));
@@ -107,8 +111,9 @@ __global__ void __launch_bounds__(128) march_backward_kernel(const MarchArgs a) 
 #pragma unroll
       for (int c4 = 0; c4 < 8; ++c4) {
         const float4 v = __ldg(row + c4 * cstep);
-        acc = fmaf(A2[4 * c4], v.x, acc); acc = fmaf(A2[4 * c4 + 1], v.y, acc);
-        acc = fmaf(A2[4 * c4 + 2], v.z, acc); acc = fmaf(A2[4 * c4 + 3], v.w, acc);
+        const float4 w = *reinterpret_cast<const float4*>(a2s + 4 * c4);
+        acc = fmaf(w.x, v.x, acc); acc = fmaf(w.y, v.y, acc);
+        acc = fmaf(w.z, v.z, acc); acc = fmaf(w.w, v.w, acc);
       }
       q[p] = acc;                                   // sum_c d(loss)/d(rgb_raw_c) * colour_c
     }
@@ -116,24 +121,56 @@ __global__ void __launch_bounds__(128) march_backward_kernel(const MarchArgs a) 
     // sort by depth (VR/renderer.py:157-167): rank = number of smaller depths, ties by sample index (a stable sort).  The
     // coarse depths of a ray ascend (stratified: VR/renderer.py:199-224), so a coarse sample's rank among them is its index and
     // an importance sample's is an upper bound found by bisection; only the Df importance depths are compared one by one.
+    // Fast path: importance depths counted with strict compares, four per shared-memory read; two EQUAL importance depths would
+    // then share a rank, which the rank sum detects -- the exact loop (ties by index) runs again only for such a ray.
     bool ascending = true;
     for (int p = lane; p + 1 < a.Dc; p += 32) ascending = ascending && (z[p] <= z[p + 1]);
     ascending = __all_sync(kFull, ascending);
-    for (int p = lane; p < S; p += 32) {
-      const float zp = z[p];
-      int cnt = 0;
-      if (ascending) {
-        if (p < a.Dc) cnt = p;
-        else {
-          int lo_i = 0, hi_i = a.Dc;                      // first coarse index whose depth is > zp
-          while (lo_i < hi_i) { const int mid = (lo_i + hi_i) >> 1; if (z[mid] <= zp) lo_i = mid + 1; else hi_i = mid; }
-          cnt = lo_i;
+    int cnt[E];
+    bool exact = !(ascending && vec);
+    if (!exact) {
+      int rsum = 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int p = lane + 32 * e;
+        cnt[e] = 0;
+        if (p < S) {
+          const float zp = z[p];
+          int c = p;
+          if (p >= a.Dc) {
+            int lo_i = 0, hi_i = a.Dc;                      // first coarse index whose depth is > zp
+            while (lo_i < hi_i) { const int mid = (lo_i + hi_i) >> 1; if (z[mid] <= zp) lo_i = mid + 1; else hi_i = mid; }
+            c = lo_i;
+          }
+          for (int j = a.Dc; j < S; j += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(z + j);
+            c += (int)(v.x < zp) + (int)(v.y < zp) + (int)(v.z < zp) + (int)(v.w < zp);
+          }
+          cnt[e] = c;
+          rsum += c;
         }
-        for (int j = a.Dc; j < S; ++j) { const float v = z[j]; cnt += (int)((v < zp) || (v == zp && j < p)); }
-      } else {
-        for (int j = 0; j < S; ++j) { const float v = z[j]; cnt += (int)((v < zp) || (v == zp && j < p)); }
       }
-      zs[cnt] = zp; ss[cnt] = sg[p]; qs[cnt] = q[p]; idx[cnt] = p;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(kFull, rsum, o);
+      exact = rsum != S * (S - 1) / 2;                      // (warp-uniform)
+    }
+    if (exact) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int p = lane + 32 * e;
+        cnt[e] = 0;
+        if (p < S) {
+          const float zp = z[p];
+          int c = 0;
+          for (int j = 0; j < S; ++j) { const float v = z[j]; c += (int)((v < zp) || (v == zp && j < p)); }
+          cnt[e] = c;
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int p = lane + 32 * e;
+      if (p < S) { zs[cnt[e]] = z[p]; ss[cnt[e]] = sg[p]; qs[cnt[e]] = q[p]; idx[cnt[e]] = p; }
     }
     __syncwarp();
     // blocked: position p = lane * E + e
@@ -628,7 +665,7 @@ int launch_bwd_march(const float* dc, const float* df, int Dc, int Df, const flo
   a.dc = dc; a.df = df; a.Dc = Dc; a.Df = Df; a.sigma = sigma; a.colours = colours; a.chunked = col_chunked; a.g_rgb = g_rgb; a.g_depth = g_depth;
   a.g_wsum = g_wsum; a.range = range; a.white_back = white_back; a.n_rays = n_rays_total; a.gsig = gsig; a.omega = omega;
   const int S = Dc + Df;
-  const size_t smem = (size_t)4 * 7 * S * sizeof(float);
+  const size_t smem = (size_t)4 * (7 * S + 32) * sizeof(float);
   long long blocks = (n_rays_total + 3) / 4;
   if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
   const int E = (S + 31) / 32;

@@ -52,20 +52,31 @@ def test_gradients_match_reference_fixture(pkg, name):
     assert max(errs.values()) < REL, errs
 
 
-def test_march_backward_against_autograd(pkg):
-    """tpr_march_backward alone: d/d(sigma) and the colour weights omega of random (depth, sigma, colour) rows."""
+@pytest.mark.parametrize('variant', ['random', 'ties', 'unsorted_coarse', 'odd_counts'])
+def test_march_backward_against_autograd(pkg, variant):
+    """tpr_march_backward alone: d/d(sigma) and the colour weights omega of random (depth, sigma, colour) rows.  'ties': equal
+    depths among the importance samples, between a coarse and an importance sample and inside the coarse row (the kernel's fast
+    rank count detects them by its rank sum and falls back to the exact, index-tie-broken count = a stable sort);
+    'unsorted_coarse': a coarse row that does not ascend (the general path); 'odd_counts': sample counts that are not multiples
+    of four (no vector reads)."""
     torch.manual_seed(5)
     d = dev()
-    r, dc, df = 37, 24, 16
+    r, dc, df = (37, 24, 16) if variant != 'odd_counts' else (19, 23, 13)
     s = dc + df
     coarse = torch.sort(torch.rand(r, dc, device=d) * 0.8 + 2.3, -1).values.contiguous()
     fine = (torch.rand(r, df, device=d) * 0.8 + 2.3).contiguous()
+    if variant == 'ties':
+        fine[:, 3] = fine[:, 7]
+        fine[::2, 0] = coarse[::2, 5]
+        coarse[1::3, 11] = coarse[1::3, 10]
+    if variant == 'unsorted_coarse':
+        coarse[::2, [4, 9]] = coarse[::2, [9, 4]]
     sigma = (torch.randn(r, s, device=d) * 3).requires_grad_(True)
     col = torch.rand(r, s, 32, device=d).requires_grad_(True)
     A, B, C = torch.randn(r, 32, device=d), torch.randn(r, device=d), torch.randn(r, device=d)
     for white in (False, True):
         depths = torch.cat([coarse, fine], -1)
-        d_all, order = torch.sort(depths, -1)
+        d_all, order = torch.sort(depths, dim=-1, stable=True)      # ties: the earlier sample first (coarse before importance)
         rgb, depth, w = TO.march(torch.gather(col, 1, order.unsqueeze(-1).expand(-1, -1, 32)).unsqueeze(0),
                                  torch.gather(sigma, 1, order).unsqueeze(0).unsqueeze(-1), d_all.unsqueeze(0).unsqueeze(-1), white)
         loss = (rgb[0] * A).sum() + (depth[0, :, 0] * B).sum() + (w.sum(2)[0, :, 0] * C).sum()
