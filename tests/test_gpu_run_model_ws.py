@@ -45,6 +45,11 @@ def test_ragged_point_counts(pkg, force_ws, n_img, n_pts):
     assert out['rgb'].shape == (n_img, n_pts, 32) and out['sigma'].shape == (n_img, n_pts, 1)
     assert float((out['rgb'] - ref['rgb']).abs().max()) < 2e-5
     assert float((out['sigma'] - ref['sigma']).abs().max()) < 5e-5
+    # sigma-only queries run a different role layout (24 gather warps in three teams, sixteen rows per warp, no COLOUR role):
+    # same tiles, same arithmetic, so the same bits -- also with fewer tiles than teams and a partial last tile
+    sig_only = R.run_model(T(scene['planes']), dec, T(pts), None, opts, want_rgb=False)
+    assert sig_only['rgb'] is None and sig_only['sigma'].shape == (n_img, n_pts, 1)
+    torch.testing.assert_close(sig_only['sigma'], out['sigma'], rtol=0, atol=0)
     if n_pts <= 1000:
         rgb_o, sig_o = O.run_model(scene['planes'], scene['dec'], pts, opts['box_warp'])
         assert np.abs(out['rgb'].cpu().numpy() - rgb_o).max() < 1e-4 and np.abs(out['sigma'].cpu().numpy() - sig_o).max() < 1e-4
